@@ -1,0 +1,118 @@
+/*
+ * neuralfoil_b200 -- C ABI of the B200 (sm_100a) evaluator for NeuralFoil's learned core.
+ *
+ * The reference (peterdsharpe/NeuralFoil v0.3.3) has no FFI layer: its boundary for this path is the
+ * Python callable `neuralfoil.get_aero_from_kulfan_parameters` (reference neuralfoil/main.py:64-332).
+ * This header declares what a ctypes stub placed behind that callable binds to; INTEGRATION.md shows
+ * the stub.  Nothing here uses torch or C++ types: plain pointers, sizes and integer codes.
+ *
+ * Every entry point returns NFB_OK (0) or a negative error code; `nfb_last_error()` gives the
+ * message of the last failure on the calling thread.
+ *
+ * Layout conventions ("SoA", the reference's effective layout, main.py:240):
+ *   inputs : 23 raw rows, row r = one scalar per query.  Row order
+ *            upper_weights[0..7], lower_weights[0..7], leading_edge_weight, TE_thickness,
+ *            alpha [deg], Re, n_crit, xtr_upper, xtr_lower          (main.py:171-184)
+ *            Each row has its own base pointer and element stride; stride 0 broadcasts one value
+ *            (the reference's `np.ones(N_cases) * row`, main.py:198-199).
+ *   outputs: 198 rows x N in the reference's dict order (main.py:318-331): analysis_confidence, CL,
+ *            CD, CM, Top_Xtr, Bot_Xtr, upper_bl_theta_0..31, upper_bl_H_0..31, upper_bl_ue/vinf_0..31,
+ *            lower_bl_theta_*, lower_bl_H_*, lower_bl_ue/vinf_*.  Row r starts at out + r * out_ld
+ *            elements; out_ld >= N.
+ */
+#ifndef NEURALFOIL_B200_H
+#define NEURALFOIL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFB_N_RAW_ROWS 23
+#define NFB_N_LATENT_INPUTS 25
+#define NFB_N_OUTPUT_ROWS 198
+#define NFB_N_BL_STATIONS 32
+#define NFB_MAX_MODELS 16
+#define NFB_MAX_LAYERS 16
+
+enum nfb_status {
+  NFB_OK = 0,
+  NFB_ERR_INVALID_ARGUMENT = -1, /* bad pointer / size / id; maps to ValueError on the Python side   */
+  NFB_ERR_UNSUPPORTED_MODEL = -2,/* layer shapes this build has no kernel for (main.py:206-215 analogue) */
+  NFB_ERR_NOT_LOADED = -3,       /* model slot or distribution not set before nfb_eval_*               */
+  NFB_ERR_CUDA = -4,             /* CUDA runtime failure; message carries cudaGetErrorString           */
+  NFB_ERR_NO_DEVICE = -5         /* no sm_100 device visible; there is NO CPU fallback                  */
+};
+
+enum nfb_dtype { NFB_F32 = 0, NFB_F64 = 1 };
+
+/* Which kernel evaluates the network.  FFMA = fp32 CUDA-core path (the correctness reference). */
+enum nfb_variant { NFB_VARIANT_FP32_FFMA = 0 };
+
+typedef struct nfb_context nfb_context;
+
+/* Library / build identification (static string, never NULL). */
+const char* nfb_version(void);
+
+/* Message of the last error raised on this thread (static storage, never NULL). */
+const char* nfb_last_error(void);
+
+/* Create an evaluator bound to CUDA device `device` (its primary context).  Replaces the reference's
+ * import-time state (main.py:25-44).  Fails with NFB_ERR_NO_DEVICE when no sm_100 GPU is present. */
+int nfb_create(int device, nfb_context** out_ctx);
+void nfb_destroy(nfb_context* ctx);
+
+/* Number of SMs / device ordinal the context runs on. */
+int nfb_device_info(const nfb_context* ctx, int* device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* Mean (25) and inverse covariance (25x25, row-major) of the scaled inputs, float64.
+ * Replaces `_scaled_input_distribution` (main.py:27-32) as used by `_squared_mahalanobis_distance`
+ * (main.py:47-61). */
+int nfb_set_distribution(nfb_context* ctx, const double* mean25, const double* inv_cov_25x25);
+
+/* Load one network into slot `model_id` (0 <= id < NFB_MAX_MODELS).
+ *   n_layers       number of affine layers L (3..7 for the shipped sizes)
+ *   dims[L + 1]    25, hidden..., 198
+ *   weights[l]     float32, shape (dims[l+1], dims[l]) row-major -- exactly `net.{2l}.weight` of the
+ *                  reference's .npz (training/convert_all_pth_files_to_npz.py:16-19)
+ *   biases[l]      float32, shape (dims[l+1],)
+ * Host pointers; the library repacks them into its own device layout.  Replaces
+ * `_nn_parameters[model_size]` (main.py:41-44) and the layer discovery at main.py:206-215. */
+int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims,
+                   const float* const* weights, const float* const* biases);
+
+/* Evaluate N queries.  All data pointers are DEVICE pointers valid on the context's device.
+ *   in_rows[23], in_strides[23]  per-row base pointer and element stride (0 or 1, or any >= 0)
+ *   in_dtype / out_dtype         NFB_F32 or NFB_F64 element type of the rows
+ *   out, out_ld                  198 x out_ld block, row-major
+ *   stream                       a cudaStream_t (NULL = default stream); the call only enqueues work
+ * Replaces the body of get_aero_from_kulfan_parameters from featurisation to decode
+ * (main.py:171-184, 218-316). */
+int nfb_eval_device(nfb_context* ctx, int model_id, int variant, int64_t n,
+                    const void* const* in_rows, const int64_t* in_strides, int in_dtype,
+                    void* out, int64_t out_ld, int out_dtype, void* stream);
+
+/* Same, with HOST pointers (pageable or pinned).  The library moves data in chunks of `chunk`
+ * queries (0 = default) over two streams so that host->device copies, the kernel and
+ * device->host copies overlap, and returns after the last byte has landed in `out`. */
+int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n,
+                  const void* const* in_rows, const int64_t* in_strides, int in_dtype,
+                  void* out, int64_t out_ld, int out_dtype, int64_t chunk);
+
+/* Pinned host memory helpers for callers without their own allocator. */
+int nfb_host_alloc(void** out_ptr, int64_t bytes);
+int nfb_host_free(void* ptr);
+
+/* Number of kernel launches this context has enqueued so far (bench.py's `gpu_launches`). */
+int64_t nfb_launch_count(const nfb_context* ctx);
+
+/* Measure the device's fp32 FFMA throughput with a register-resident outer-product loop
+ * (the roofline denominator for the FFMA variant; MEASURED_PEAKS.json has no fp32 figure).
+ * Runs `iters` timed launches and returns the best rate in TFLOP/s. */
+int nfb_measure_fp32_peak(nfb_context* ctx, int iters, double* out_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURALFOIL_B200_H */

@@ -1,0 +1,18 @@
+"""
+neuralfoil_b200 -- B200-native (sm_100a) evaluation of NeuralFoil's learned core.
+
+Drop-in surface for the path (reference neuralfoil/__init__.py:1-15): `get_aero_from_kulfan_parameters`
+and `bl_x_points`.  Importing the package needs no GPU; the first evaluation creates the CUDA context
+and raises if the library or a B200 is missing (there is no CPU fallback).
+"""
+
+from .main import (  # noqa: F401
+    MODEL_SIZES,
+    Evaluator,
+    bl_x_points,
+    default_evaluator,
+    get_aero_from_kulfan_parameters,
+    output_keys,
+)
+
+__version__ = "0.1.0"

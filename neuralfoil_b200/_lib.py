@@ -1,0 +1,87 @@
+"""
+ctypes binding of include/neuralfoil_b200.h.  This is the only place the package touches the
+shared library; there is no fallback of any kind -- if the library is missing or no B200 is
+present, the calls raise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libneuralfoil_b200.so"
+
+N_RAW_ROWS = 23
+N_OUTPUT_ROWS = 198
+F32, F64 = 0, 1
+VARIANT_FP32_FFMA = 0
+
+OK = 0
+ERR_INVALID_ARGUMENT = -1
+ERR_UNSUPPORTED_MODEL = -2
+ERR_NOT_LOADED = -3
+ERR_CUDA = -4
+ERR_NO_DEVICE = -5
+
+# Every symbol include/neuralfoil_b200.h declares (tests/test_cabi_symbols.py checks the two agree).
+_SIGNATURES = {
+    "nfb_version": (C.c_char_p, []),
+    "nfb_last_error": (C.c_char_p, []),
+    "nfb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "nfb_destroy": (None, [C.c_void_p]),
+    "nfb_device_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
+    "nfb_set_distribution": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "nfb_load_model": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)],
+    ),
+    "nfb_eval_device": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+         C.c_void_p, C.c_int64, C.c_int, C.c_void_p],
+    ),
+    "nfb_eval_host": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+         C.c_void_p, C.c_int64, C.c_int, C.c_int64],
+    ),
+    "nfb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "nfb_host_free": (C.c_int, [C.c_void_p]),
+    "nfb_launch_count": (C.c_int64, [C.c_void_p]),
+    "nfb_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+class NeuralFoilB200Error(RuntimeError):
+    """A failure inside the CUDA library that is not a caller mistake."""
+
+
+def load() -> C.CDLL:
+    """dlopen the library (once) and declare the prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NeuralFoilB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m neuralfoil_b200._build` "
+            "(neuralfoil_b200 has no CPU or PyTorch fallback)."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    """Map a status code to the exception the reference's callers expect."""
+    if rc == OK:
+        return
+    msg = load().nfb_last_error().decode("utf-8", "replace")
+    if rc in (ERR_INVALID_ARGUMENT, ERR_UNSUPPORTED_MODEL, ERR_NOT_LOADED):
+        raise ValueError(msg)
+    raise NeuralFoilB200Error(msg)

@@ -1,0 +1,428 @@
+// C ABI of neuralfoil_b200 (see include/neuralfoil_b200.h).  Single translation unit: the kernels are
+// included below.  No torch, no CPU fallback: every entry point that computes needs an sm_100 device.
+#include "../../include/neuralfoil_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "nfb_ffma.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define NFB_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(NFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                   \
+  } while (0)
+
+struct Model {
+  bool loaded = false;
+  int n_layers = 0;
+  int h_pad = 0;  // 64 / 128 / 256 / 512
+  int dims[NFB_MAX_LAYERS + 1] = {0};
+  float* blob = nullptr;  // device
+};
+
+// Kernel tuning per padded width: <H, KC, STAGES>.
+using Cfg64 = nfb::FfmaCfg<64, 8, 4>;
+using Cfg128 = nfb::FfmaCfg<128, 8, 4>;
+using Cfg256 = nfb::FfmaCfg<256, 8, 4>;
+using Cfg512 = nfb::FfmaCfg<512, 8, 4>;
+
+struct HostSlot {  // one in-flight chunk of nfb_eval_host
+  cudaStream_t stream = nullptr;
+  void* d_in = nullptr;
+  void* d_out = nullptr;
+  size_t in_bytes = 0, out_bytes = 0;
+  void* h_stage = nullptr;  // pinned staging for the small-batch path
+  size_t stage_bytes = 0;
+};
+
+}  // namespace
+
+struct nfb_context {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  bool have_distribution = false;
+  Model models[NFB_MAX_MODELS];
+  HostSlot slots[2];
+  int64_t launches = 0;
+};
+
+namespace {
+
+// Host-side repack of the reference's (out, in) row-major weights into the kernel's K-major,
+// zero-padded layout; the last layer's rows are permuted by nfb::pack_last_layer_row.
+template <int H>
+std::vector<float> pack_model(int L, const int* dims, const float* const* W, const float* const* B) {
+  std::vector<float> blob(nfb::blob_total_floats<H>(L), 0.0f);
+  for (int l = 0; l < L; ++l) {
+    const int in = dims[l], out = dims[l + 1];
+    const bool last = (l == L - 1);
+    const int K = (l == 0) ? nfb::K0_PAD : H;
+    const int M = last ? nfb::M_LAST : H;
+    float* wt = blob.data() + nfb::blob_layer_offset<H>(l);
+    float* bias = wt + size_t(K) * M;
+    for (int m = 0; m < M; ++m) {
+      const int src_row = last ? nfb::pack_last_layer_row(m) : (m < out ? m : -1);
+      if (src_row < 0 || src_row >= out) continue;
+      for (int k = 0; k < in; ++k) wt[size_t(k) * M + m] = W[l][size_t(src_row) * in + k];
+      bias[m] = B[l][src_row];
+    }
+  }
+  return blob;
+}
+
+template <class Cfg>
+int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_ffma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(Cfg::SMEM_BYTES)));
+    configured_device = ctx->device;
+  }
+  const long long tiles = (p.n + Cfg::NQ - 1) / Cfg::NQ;
+  const int grid = int(std::min<long long>(tiles, ctx->sm_count));
+  nfb::nfb_ffma_kernel<Cfg><<<grid, nfb::COMPUTE_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
+int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
+                    const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype) {
+  if (!ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (model_id < 0 || model_id >= NFB_MAX_MODELS)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "model_id %d out of range [0, %d)", model_id, NFB_MAX_MODELS);
+  if (!ctx->models[model_id].loaded) return fail(NFB_ERR_NOT_LOADED, "model slot %d is empty", model_id);
+  if (!ctx->have_distribution)
+    return fail(NFB_ERR_NOT_LOADED, "nfb_set_distribution has not been called");
+  if (variant != NFB_VARIANT_FP32_FFMA) return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
+  if (n < 0) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld is negative", (long long)n);
+  if ((in_dtype != NFB_F32 && in_dtype != NFB_F64) || (out_dtype != NFB_F32 && out_dtype != NFB_F64))
+    return fail(NFB_ERR_INVALID_ARGUMENT, "dtype must be NFB_F32 or NFB_F64");
+  if (n == 0) return NFB_OK;
+  if (!in_rows || !in_strides || !out) return fail(NFB_ERR_INVALID_ARGUMENT, "NULL data pointer");
+  if (out_ld < n) return fail(NFB_ERR_INVALID_ARGUMENT, "out_ld (%lld) < n (%lld)", (long long)out_ld, (long long)n);
+  for (int i = 0; i < NFB_N_RAW_ROWS; ++i) {
+    if (!in_rows[i]) return fail(NFB_ERR_INVALID_ARGUMENT, "in_rows[%d] is NULL", i);
+    if (in_strides[i] < 0) return fail(NFB_ERR_INVALID_ARGUMENT, "in_strides[%d] is negative", i);
+  }
+  return NFB_OK;
+}
+
+int eval_device_impl(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                     const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
+                     cudaStream_t stream) {
+  const Model& m = ctx->models[model_id];
+  nfb::EvalParams p;
+  for (int i = 0; i < nfb::N_RAW; ++i) {
+    p.in[i] = in_rows[i];
+    p.in_stride[i] = in_strides[i];
+  }
+  p.out = out;
+  p.out_ld = out_ld;
+  p.n = n;
+  p.blob = m.blob;
+  p.n_layers = m.n_layers;
+  p.in_f64 = (in_dtype == NFB_F64);
+  p.out_f64 = (out_dtype == NFB_F64);
+  switch (m.h_pad) {
+    case 64: return launch_ffma<Cfg64>(ctx, p, stream);
+    case 128: return launch_ffma<Cfg128>(ctx, p, stream);
+    case 256: return launch_ffma<Cfg256>(ctx, p, stream);
+    case 512: return launch_ffma<Cfg512>(ctx, p, stream);
+  }
+  return fail(NFB_ERR_UNSUPPORTED_MODEL, "no kernel for padded width %d", m.h_pad);
+}
+
+int ensure(void** ptr, size_t* have, size_t need, bool pinned_host) {
+  if (*have >= need) return NFB_OK;
+  if (*ptr) {
+    if (pinned_host) NFB_CUDA(cudaFreeHost(*ptr));
+    else NFB_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *have = 0;
+  }
+  const size_t want = need + need / 4;
+  if (pinned_host) NFB_CUDA(cudaMallocHost(ptr, want));
+  else NFB_CUDA(cudaMalloc(ptr, want));
+  *have = want;
+  return NFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nfb_version(void) { return "neuralfoil_b200 0.1 (sm_100a; fp32 FFMA fused evaluator)"; }
+
+const char* nfb_last_error(void) { return g_err; }
+
+int nfb_create(int device, nfb_context** out_ctx) {
+  if (!out_ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
+  *out_ctx = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(NFB_ERR_NO_DEVICE, "no CUDA device visible (%s); neuralfoil_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "device %d out of range [0, %d)", device, count);
+  cudaDeviceProp prop;
+  NFB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(NFB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  NFB_CUDA(cudaSetDevice(device));
+  nfb_context* ctx = new nfb_context();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  for (auto& s : ctx->slots) {
+    cudaError_t se = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+      delete ctx;
+      return fail(NFB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se));
+    }
+  }
+  *out_ctx = ctx;
+  return NFB_OK;
+}
+
+void nfb_destroy(nfb_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& m : ctx->models)
+    if (m.blob) cudaFree(m.blob);
+  for (auto& s : ctx->slots) {
+    if (s.stream) {
+      cudaStreamSynchronize(s.stream);
+      cudaStreamDestroy(s.stream);
+    }
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.h_stage) cudaFreeHost(s.h_stage);
+  }
+  delete ctx;
+}
+
+int nfb_device_info(const nfb_context* ctx, int* device, int* sm_count, int* cc_major, int* cc_minor) {
+  if (!ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (device) *device = ctx->device;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  return NFB_OK;
+}
+
+int nfb_set_distribution(nfb_context* ctx, const double* mean25, const double* inv_cov) {
+  if (!ctx || !mean25 || !inv_cov) return fail(NFB_ERR_INVALID_ARGUMENT, "NULL argument");
+  double quad[nfb::N_MAHA];
+  int idx = 0;
+  for (int i = 0; i < nfb::N_IN; ++i)
+    for (int j = i; j < nfb::N_IN; ++j)
+      quad[idx++] = (i == j) ? inv_cov[i * nfb::N_IN + i] : inv_cov[i * nfb::N_IN + j] + inv_cov[j * nfb::N_IN + i];
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  NFB_CUDA(cudaMemcpyToSymbol(nfb::c_mean, mean25, sizeof(double) * nfb::N_IN));
+  NFB_CUDA(cudaMemcpyToSymbol(nfb::c_quad, quad, sizeof(quad)));
+  ctx->have_distribution = true;
+  return NFB_OK;
+}
+
+int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims, const float* const* weights,
+                   const float* const* biases) {
+  if (!ctx || !dims || !weights || !biases) return fail(NFB_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (model_id < 0 || model_id >= NFB_MAX_MODELS)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "model_id %d out of range [0, %d)", model_id, NFB_MAX_MODELS);
+  if (n_layers < 2 || n_layers > NFB_MAX_LAYERS)
+    return fail(NFB_ERR_UNSUPPORTED_MODEL, "n_layers = %d; supported: 2..%d", n_layers, NFB_MAX_LAYERS);
+  if (dims[0] != NFB_N_LATENT_INPUTS || dims[n_layers] != NFB_N_OUTPUT_ROWS)
+    return fail(NFB_ERR_UNSUPPORTED_MODEL, "network must map %d inputs to %d outputs, got %d -> %d",
+                NFB_N_LATENT_INPUTS, NFB_N_OUTPUT_ROWS, dims[0], dims[n_layers]);
+  int hmax = 0;
+  for (int l = 1; l < n_layers; ++l) {
+    if (dims[l] < 1) return fail(NFB_ERR_UNSUPPORTED_MODEL, "hidden width %d", dims[l]);
+    hmax = std::max(hmax, dims[l]);
+  }
+  for (int l = 0; l < n_layers; ++l)
+    if (!weights[l] || !biases[l]) return fail(NFB_ERR_INVALID_ARGUMENT, "layer %d has a NULL array", l);
+  const int h_pad = hmax <= 64 ? 64 : hmax <= 128 ? 128 : hmax <= 256 ? 256 : hmax <= 512 ? 512 : 0;
+  if (!h_pad) return fail(NFB_ERR_UNSUPPORTED_MODEL, "hidden width %d > 512 has no kernel", hmax);
+
+  std::vector<float> blob;
+  switch (h_pad) {
+    case 64: blob = pack_model<64>(n_layers, dims, weights, biases); break;
+    case 128: blob = pack_model<128>(n_layers, dims, weights, biases); break;
+    case 256: blob = pack_model<256>(n_layers, dims, weights, biases); break;
+    default: blob = pack_model<512>(n_layers, dims, weights, biases); break;
+  }
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  Model& m = ctx->models[model_id];
+  if (m.blob) {
+    NFB_CUDA(cudaDeviceSynchronize());
+    NFB_CUDA(cudaFree(m.blob));
+    m = Model();
+  }
+  NFB_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
+  NFB_CUDA(cudaMemcpy(m.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  m.loaded = true;
+  m.n_layers = n_layers;
+  m.h_pad = h_pad;
+  std::copy(dims, dims + n_layers + 1, m.dims);
+  return NFB_OK;
+}
+
+int nfb_eval_device(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
+                    const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
+                    void* stream) {
+  int rc = check_eval_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype);
+  if (rc != NFB_OK || n == 0) return rc;
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  return eval_device_impl(ctx, model_id, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
+                  const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
+                  int64_t chunk) {
+  int rc = check_eval_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype);
+  if (rc != NFB_OK || n == 0) return rc;
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
+  if (chunk <= 0) chunk = 1 << 19;
+  chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
+  const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(nfb::N_OUT) * chunk * osz;
+
+  // Small batches (a design optimiser's per-iteration call): pack everything into one pinned block so
+  // that there is exactly one H2D copy, one launch and one D2H copy.
+  const bool small = n <= 16384;
+  int64_t done = 0;
+  for (int64_t c0 = 0, ci = 0; c0 < n; c0 += chunk, ++ci) {
+    HostSlot& s = ctx->slots[ci & 1];
+    const int64_t cn = std::min<int64_t>(chunk, n - c0);
+    NFB_CUDA(cudaStreamSynchronize(s.stream));  // the slot's previous chunk has fully landed
+    if ((rc = ensure(&s.d_in, &s.in_bytes, in_need, false)) != NFB_OK) return rc;
+    if ((rc = ensure(&s.d_out, &s.out_bytes, out_need, false)) != NFB_OK) return rc;
+
+    const void* d_rows[nfb::N_RAW];
+    int64_t d_strides[nfb::N_RAW];
+    if (small) {
+      if ((rc = ensure(&s.h_stage, &s.stage_bytes, in_need + out_need, true)) != NFB_OK) return rc;
+      char* hs = static_cast<char*>(s.h_stage);
+      for (int r = 0; r < nfb::N_RAW; ++r) {
+        char* dst = hs + size_t(r) * chunk * isz;
+        const char* src = static_cast<const char*>(in_rows[r]);
+        if (in_strides[r] == 1) {
+          memcpy(dst, src + size_t(c0) * isz, size_t(cn) * isz);
+          d_strides[r] = 1;
+        } else if (in_strides[r] == 0) {
+          memcpy(dst, src, isz);
+          d_strides[r] = 0;
+        } else {
+          for (int64_t i = 0; i < cn; ++i) memcpy(dst + i * isz, src + size_t(c0 + i) * in_strides[r] * isz, isz);
+          d_strides[r] = 1;
+        }
+        d_rows[r] = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
+      }
+      NFB_CUDA(cudaMemcpyAsync(s.d_in, hs, in_need, cudaMemcpyHostToDevice, s.stream));
+    } else {
+      for (int r = 0; r < nfb::N_RAW; ++r) {
+        char* dst = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
+        const char* src = static_cast<const char*>(in_rows[r]);
+        if (in_strides[r] == 0) {
+          NFB_CUDA(cudaMemcpyAsync(dst, src, isz, cudaMemcpyHostToDevice, s.stream));
+          d_strides[r] = 0;
+        } else if (in_strides[r] == 1) {
+          NFB_CUDA(cudaMemcpyAsync(dst, src + size_t(c0) * isz, size_t(cn) * isz, cudaMemcpyHostToDevice, s.stream));
+          d_strides[r] = 1;
+        } else {
+          NFB_CUDA(cudaMemcpy2DAsync(dst, isz, src + size_t(c0) * in_strides[r] * isz, size_t(in_strides[r]) * isz,
+                                     isz, size_t(cn), cudaMemcpyHostToDevice, s.stream));
+          d_strides[r] = 1;
+        }
+        d_rows[r] = dst;
+      }
+    }
+    rc = eval_device_impl(ctx, model_id, cn, d_rows, d_strides, in_dtype, s.d_out, chunk, out_dtype, s.stream);
+    if (rc != NFB_OK) return rc;
+    char* out_c = static_cast<char*>(out) + size_t(c0) * osz;
+    if (small) {
+      char* hs_out = static_cast<char*>(s.h_stage) + in_need;
+      NFB_CUDA(cudaMemcpyAsync(hs_out, s.d_out, out_need, cudaMemcpyDeviceToHost, s.stream));
+      NFB_CUDA(cudaStreamSynchronize(s.stream));
+      for (int r = 0; r < nfb::N_OUT; ++r)
+        memcpy(out_c + size_t(r) * out_ld * osz, hs_out + size_t(r) * chunk * osz, size_t(cn) * osz);
+    } else {
+      NFB_CUDA(cudaMemcpy2DAsync(out_c, size_t(out_ld) * osz, s.d_out, size_t(chunk) * osz, size_t(cn) * osz,
+                                 nfb::N_OUT, cudaMemcpyDeviceToHost, s.stream));
+    }
+    done += cn;
+  }
+  for (auto& s : ctx->slots) NFB_CUDA(cudaStreamSynchronize(s.stream));
+  (void)done;
+  return NFB_OK;
+}
+
+int nfb_host_alloc(void** out_ptr, int64_t bytes) {
+  if (!out_ptr || bytes < 0) return fail(NFB_ERR_INVALID_ARGUMENT, "bad argument");
+  *out_ptr = nullptr;
+  if (bytes == 0) return NFB_OK;
+  NFB_CUDA(cudaMallocHost(out_ptr, size_t(bytes)));
+  return NFB_OK;
+}
+
+int nfb_host_free(void* ptr) {
+  if (ptr) NFB_CUDA(cudaFreeHost(ptr));
+  return NFB_OK;
+}
+
+int64_t nfb_launch_count(const nfb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int nfb_measure_fp32_peak(nfb_context* ctx, int iters, double* out_tflops) {
+  if (!ctx || !out_tflops) return fail(NFB_ERR_INVALID_ARGUMENT, "NULL argument");
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  float* sink = nullptr;
+  NFB_CUDA(cudaMalloc(&sink, 4));
+  cudaEvent_t e0, e1;
+  NFB_CUDA(cudaEventCreate(&e0));
+  NFB_CUDA(cudaEventCreate(&e1));
+  const int inner = 4096, blocks = ctx->sm_count * 4;
+  const double flops = 2.0 * 64 * 8 * double(inner) * 512.0 * blocks;
+  double best = 0.0;
+  if (iters < 1) iters = 1;
+  for (int i = 0; i < iters + 2; ++i) {  // two warm-up launches
+    NFB_CUDA(cudaEventRecord(e0, 0));
+    nfb::nfb_ffma_peak_kernel<<<blocks, 512>>>(sink, inner);
+    NFB_CUDA(cudaEventRecord(e1, 0));
+    NFB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    NFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ctx->launches += 1;
+    if (i >= 2) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  NFB_CUDA(cudaEventDestroy(e0));
+  NFB_CUDA(cudaEventDestroy(e1));
+  NFB_CUDA(cudaFree(sink));
+  *out_tflops = best;
+  return NFB_OK;
+}
+
+}  // extern "C"

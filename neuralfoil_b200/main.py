@@ -1,0 +1,354 @@
+"""
+Host side of the B200 evaluator: the reference's `get_aero_from_kulfan_parameters`
+(/root/reference/neuralfoil/main.py:64-332) with the same signature, return value and errors, whose
+numerical body -- featurisation, both network passes, Mahalanobis correction, un-flip, averaging,
+squashing and decode -- runs in one fused CUDA kernel behind the C ABI of
+include/neuralfoil_b200.h.
+
+What stays on the host is what the reference does before `x = np.stack(...)` (main.py:154-199):
+argument validation and the decision of how many cases N the call describes.  The 23 raw rows are
+handed to the library as they are (a pointer and a stride each; scalars are stride-0 rows), so no
+(N, 25) matrix is ever built on the host.
+
+Two entry levels:
+  * `get_aero_from_kulfan_parameters(...)`  NumPy in, dict of 198 float64 arrays out (drop-in).
+  * `Evaluator.evaluate_device(...)`        torch CUDA tensors in and out, nothing crosses PCIe.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from . import _lib
+
+N_BL = 32  # reference neuralfoil/_basic_data_type.py:51
+bl_x_points = (np.arange(N_BL) + 0.5) / N_BL  # _basic_data_type.py:23-38,52; re-exported like main.py:11
+
+MODEL_SIZES = ("xxsmall", "xsmall", "small", "medium", "large", "xlarge", "xxlarge", "xxxlarge")
+nn_weights_dir = Path(__file__).resolve().parent / "nn_weights_and_biases"
+
+
+def output_keys() -> list[str]:
+    """The 198 keys of the returned dict, in the reference's insertion order (main.py:318-331)."""
+    keys = ["analysis_confidence", "CL", "CD", "CM", "Top_Xtr", "Bot_Xtr"]
+    for side in ("upper", "lower"):
+        for quantity in ("theta", "H", "ue/vinf"):
+            keys += [f"{side}_bl_{quantity}_{i}" for i in range(N_BL)]
+    return keys
+
+
+_OUTPUT_KEYS = output_keys()
+
+
+def _length(x) -> int:
+    """aerosandbox.numpy.length as used at main.py:161,189-193: len() of sized things, 1 for scalars."""
+    try:
+        return len(x)
+    except TypeError:
+        return 1
+
+
+def layers_from_params(nn_params: dict) -> list[tuple[np.ndarray, np.ndarray]]:
+    """[(W, b), ...] in layer order from `net.{i}.weight/bias` keys; rule and error of main.py:206-215."""
+    try:
+        layer_indices = sorted({int(key.split(".")[1]) for key in nn_params.keys()})
+    except (TypeError, ValueError, IndexError) as e:
+        raise ValueError(
+            "Got an unexpected neural network file format.\n"
+            "Dictionary keys should be strings of the form 'net.0.weight', 'net.0.bias', 'net.2.weight', etc.'.\n"
+            f"Instead, got keys of the form {nn_params.keys()}.\n"
+        ) from e
+    layers = []
+    for i in layer_indices:
+        w = np.ascontiguousarray(nn_params[f"net.{i}.weight"], dtype=np.float32)
+        b = np.ascontiguousarray(nn_params[f"net.{i}.bias"], dtype=np.float32)
+        if w.ndim != 2 or b.shape != (w.shape[0],):
+            raise ValueError(f"Layer net.{i} has inconsistent shapes {w.shape} / {b.shape}.")
+        layers.append((w, b))
+    for (w0, _), (w1, _) in zip(layers[:-1], layers[1:]):
+        if w1.shape[1] != w0.shape[0]:
+            raise ValueError("Consecutive layers of the network do not chain.")
+    return layers
+
+
+def prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower):
+    """
+    Validation and case counting of main.py:160-199.  Returns (rows, n_cases): 23 float64 1-D arrays,
+    each of size n_cases or 1 (a size-1 row is broadcast by the kernel, like `np.ones(N) * row`).
+
+    Differences from the reference, both supersets: Python lists are accepted for the flow inputs
+    (the reference's `2 * alpha` duplicates a list and then fails the length check), and the raw
+    inputs, not the featurised ones, are what gets counted.
+    """
+    for key in ("upper_weights", "lower_weights"):
+        n_weights = _length(kulfan_parameters[key])
+        if n_weights != 8:
+            raise ValueError(
+                f"NeuralFoil's neural networks expect exactly 8 CST weights per side, but "
+                f"`kulfan_parameters[{key!r}]` has {n_weights}. If your airfoil is parameterized "
+                f"with a different CST resolution, refit it with 8 weights per side (e.g., via "
+                f"`aerosandbox.Airfoil.to_kulfan_airfoil(n_weights_per_side=8)`)."
+            )
+    rows = [kulfan_parameters["upper_weights"][i] for i in range(8)]
+    rows += [kulfan_parameters["lower_weights"][i] for i in range(8)]
+    rows += [
+        kulfan_parameters["leading_edge_weight"],
+        kulfan_parameters["TE_thickness"],
+        alpha,
+        Re,
+        n_crit,
+        xtr_upper,
+        xtr_lower,
+    ]
+    n_cases = 1
+    arrays = []
+    for row in rows:
+        a = np.asarray(row, dtype=np.float64)
+        if a.ndim > 1:
+            raise ValueError("The inputs to the neural network must be scalars or 1-D arrays.")
+        a = np.ascontiguousarray(a.reshape(-1))
+        if a.size == 0:
+            raise ValueError("The inputs to the neural network must not be empty.")
+        if a.size > 1:
+            if n_cases == 1:
+                n_cases = a.size
+            elif a.size != n_cases:
+                raise ValueError(
+                    "The inputs to the neural network must all have the same length. "
+                    f"(Conflicting lengths: {n_cases} and {a.size})"
+                )
+        arrays.append(a)
+    return arrays, n_cases
+
+
+class Evaluator:
+    """
+    One CUDA context's worth of state: the distribution statistics and every network, repacked and
+    resident on the GPU.  Mirrors the reference's import-time globals (main.py:25-44).
+    """
+
+    def __init__(self, device: int | None = None, weights_dir: Path | str | None = None, extra_models=None):
+        self._lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get("NEURALFOIL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        self.device = int(device)
+        self.weights_dir = Path(weights_dir) if weights_dir is not None else nn_weights_dir
+        handle = C.c_void_p()
+        _lib.check(self._lib.nfb_create(self.device, C.byref(handle)))
+        self._ctx = handle
+        self._model_ids: dict[str, int] = {}
+        self.model_dims: dict[str, list[int]] = {}
+
+        with np.load(self.weights_dir / "scaled_input_distribution.npz") as f:  # main.py:27-32
+            mean = np.ascontiguousarray(f["mean_inputs_scaled"], dtype=np.float64)
+            inv_cov = np.ascontiguousarray(f["inv_cov_inputs_scaled"], dtype=np.float64)
+        if mean.shape != (25,) or inv_cov.shape != (25, 25):
+            raise ValueError("scaled_input_distribution.npz does not describe 25 inputs.")
+        _lib.check(
+            self._lib.nfb_set_distribution(
+                self._ctx, mean.ctypes.data_as(C.POINTER(C.c_double)), inv_cov.ctypes.data_as(C.POINTER(C.c_double))
+            )
+        )
+        for path in sorted(self.weights_dir.glob("nn-*.npz")):  # main.py:35-44
+            with np.load(path) as f:
+                self.load_model(path.stem.removeprefix("nn-"), {k: f[k] for k in f.files})
+        for name, params in (extra_models or {}).items():
+            self.load_model(name, params)
+
+    # -- model management ------------------------------------------------------------------------
+    @property
+    def allowable_model_sizes(self) -> set[str]:
+        return set(self._model_ids)
+
+    def load_model(self, name: str, nn_params: dict) -> None:
+        """Upload a network given as the reference's `.npz` dictionary (`net.{2j}.weight/bias`)."""
+        layers = layers_from_params(nn_params)
+        dims = [layers[0][0].shape[1]] + [w.shape[0] for w, _ in layers]
+        model_id = self._model_ids.get(name, len(self._model_ids))
+        n = len(layers)
+        w_ptrs = (C.c_void_p * n)(*[w.ctypes.data for w, _ in layers])
+        b_ptrs = (C.c_void_p * n)(*[b.ctypes.data for _, b in layers])
+        c_dims = (C.c_int * (n + 1))(*dims)
+        _lib.check(self._lib.nfb_load_model(self._ctx, model_id, n, c_dims, w_ptrs, b_ptrs))
+        self._model_ids[name] = model_id
+        self.model_dims[name] = dims
+
+    def _model_id(self, model_size: str) -> int:
+        if model_size not in self._model_ids:
+            raise ValueError(f"Invalid {model_size=}. Must be one of {self.allowable_model_sizes}.")
+        return self._model_ids[model_size]
+
+    # -- the drop-in call --------------------------------------------------------------------------
+    def get_aero_from_kulfan_parameters(
+        self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"
+    ) -> dict[str, np.ndarray]:
+        model_id = self._model_id(model_size)  # main.py:154-157
+        rows, n_cases = prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower)
+        block = self._evaluate_host_rows(model_id, rows, n_cases, np.float64)
+        # Row views of one (198, ld) block: each value is a contiguous (N,) float64 array, as in the
+        # reference, where the keys are views of a shared Fortran-ordered block.
+        return {key: block[i, :n_cases] for i, key in enumerate(_OUTPUT_KEYS)}
+
+    def evaluate_host(self, raw: np.ndarray, model_size: str = "xlarge", out_dtype=np.float32, chunk: int = 0):
+        """raw (23, N) float32/float64 host array -> (198, N) host array (rows are contiguous)."""
+        raw = np.asarray(raw)
+        if raw.ndim != 2 or raw.shape[0] != _lib.N_RAW_ROWS:
+            raise ValueError(f"raw must have shape (23, N), got {raw.shape}")
+        if raw.dtype not in (np.float32, np.float64):
+            raw = raw.astype(np.float64)
+        rows = [np.ascontiguousarray(raw[i]) for i in range(_lib.N_RAW_ROWS)]
+        block = self._evaluate_host_rows(self._model_id(model_size), rows, raw.shape[1], out_dtype, chunk)
+        return block[:, : raw.shape[1]]
+
+    def evaluate_host_into(self, raw: np.ndarray, model_size: str, out: np.ndarray, chunk: int = 0) -> np.ndarray:
+        """
+        Like `evaluate_host`, but writes into a caller-owned (ideally pinned) block `out` of shape
+        (198, ld >= N) with contiguous rows, and reads `raw` (23, N) in place: no host allocation
+        or copy happens on this side of the C ABI.  Returns the (198, N) view of `out`.
+        """
+        if raw.ndim != 2 or raw.shape[0] != _lib.N_RAW_ROWS or raw.dtype not in (np.float32, np.float64):
+            raise ValueError("raw must be a (23, N) float32/float64 array")
+        if raw.strides[1] != raw.itemsize:
+            raise ValueError("raw rows must be contiguous")
+        n = raw.shape[1]
+        if (out.ndim != 2 or out.shape[0] != _lib.N_OUTPUT_ROWS or out.shape[1] < n
+                or out.strides[1] != out.itemsize or out.dtype not in (np.float32, np.float64)):
+            raise ValueError("out must be a (198, >=N) float32/float64 array with contiguous rows")
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].ctypes.data for i in range(_lib.N_RAW_ROWS)])
+        strides = (C.c_int64 * _lib.N_RAW_ROWS)(*([1] * _lib.N_RAW_ROWS))
+        _lib.check(
+            self._lib.nfb_eval_host(
+                self._ctx, self._model_id(model_size), _lib.VARIANT_FP32_FFMA, n, ptrs, strides,
+                _lib.F64 if raw.dtype == np.float64 else _lib.F32,
+                out.ctypes.data_as(C.c_void_p), out.strides[0] // out.itemsize,
+                _lib.F64 if out.dtype == np.float64 else _lib.F32, chunk,
+            )
+        )
+        return out[:, :n]
+
+    def _evaluate_host_rows(self, model_id: int, rows, n: int, out_dtype, chunk: int = 0):
+        in_dtype = rows[0].dtype
+        if any(r.dtype != in_dtype for r in rows):
+            rows = [r.astype(np.float64) for r in rows]
+            in_dtype = np.dtype(np.float64)
+        ld = (n + 3) & ~3
+        block = np.empty((_lib.N_OUTPUT_ROWS, ld), dtype=out_dtype)
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[r.ctypes.data for r in rows])
+        strides = (C.c_int64 * _lib.N_RAW_ROWS)(*[0 if r.size == 1 and n > 1 else 1 for r in rows])
+        _lib.check(
+            self._lib.nfb_eval_host(
+                self._ctx, model_id, _lib.VARIANT_FP32_FFMA, n, ptrs, strides,
+                _lib.F64 if in_dtype == np.float64 else _lib.F32,
+                block.ctypes.data_as(C.c_void_p), ld,
+                _lib.F64 if np.dtype(out_dtype) == np.float64 else _lib.F32, chunk,
+            )
+        )
+        return block
+
+    # -- device-resident call ----------------------------------------------------------------------
+    def evaluate_device(self, raw, model_size: str = "xlarge", out=None, out_dtype=None):
+        """
+        raw: torch CUDA tensor (23, N), float32 or float64, rows contiguous -- or a list of 23 1-D CUDA
+        tensors of length N or 1 (length-1 rows are broadcast).  Returns a (198, N) CUDA tensor view
+        (row stride padded to a multiple of 4).  Enqueues on torch's current stream; does not synchronise.
+        """
+        import torch
+
+        model_id = self._model_id(model_size)
+        if isinstance(raw, torch.Tensor):
+            if raw.dim() != 2 or raw.shape[0] != _lib.N_RAW_ROWS:
+                raise ValueError(f"raw must have shape (23, N), got {tuple(raw.shape)}")
+            rows = list(raw.unbind(0))
+        else:
+            rows = list(raw)
+            if len(rows) != _lib.N_RAW_ROWS:
+                raise ValueError(f"expected 23 raw rows, got {len(rows)}")
+        n = max(int(r.numel()) for r in rows)
+        dtype = rows[0].dtype
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("raw rows must be float32 or float64")
+        strides = []
+        for r in rows:
+            if not r.is_cuda or r.device.index != self.device or r.dtype != dtype or r.dim() != 1:
+                raise ValueError(f"every raw row must be a 1-D {dtype} tensor on cuda:{self.device}")
+            if r.numel() == n and n > 1:
+                strides.append(int(r.stride(0)))
+            elif r.numel() == 1:
+                strides.append(0)
+            else:
+                raise ValueError("The inputs to the neural network must all have the same length.")
+        if out_dtype is None:
+            out_dtype = out.dtype if out is not None else torch.float32
+        ld = (n + 3) & ~3
+        if out is None:
+            out = torch.empty((_lib.N_OUTPUT_ROWS, ld), dtype=out_dtype, device=f"cuda:{self.device}")
+        else:
+            if out.dim() != 2 or out.shape[0] != _lib.N_OUTPUT_ROWS or out.shape[1] < n or out.stride(1) != 1:
+                raise ValueError("out must be a (198, >=N) tensor with contiguous rows")
+            ld = int(out.stride(0))
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[r.data_ptr() for r in rows])
+        c_strides = (C.c_int64 * _lib.N_RAW_ROWS)(*strides)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(
+            self._lib.nfb_eval_device(
+                self._ctx, model_id, _lib.VARIANT_FP32_FFMA, n, ptrs, c_strides,
+                _lib.F64 if dtype == torch.float64 else _lib.F32,
+                C.c_void_p(out.data_ptr()), ld, _lib.F64 if out.dtype == torch.float64 else _lib.F32,
+                C.c_void_p(stream),
+            )
+        )
+        return out[:, :n]
+
+    # -- measurement helpers -----------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self._lib.nfb_launch_count(self._ctx))
+
+    def device_info(self) -> dict:
+        vals = [C.c_int() for _ in range(4)]
+        _lib.check(self._lib.nfb_device_info(self._ctx, *[C.byref(v) for v in vals]))
+        return dict(zip(("device", "sm_count", "cc_major", "cc_minor"), (v.value for v in vals)))
+
+    def measure_fp32_peak_tflops(self, iters: int = 5) -> float:
+        out = C.c_double()
+        _lib.check(self._lib.nfb_measure_fp32_peak(self._ctx, iters, C.byref(out)))
+        return out.value
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.nfb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default: Evaluator | None = None
+
+
+def default_evaluator() -> Evaluator:
+    """The process-wide evaluator the module-level functions use (created on first call)."""
+    global _default
+    if _default is None:
+        _default = Evaluator()
+    return _default
+
+
+def get_aero_from_kulfan_parameters(
+    kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"
+) -> dict[str, np.ndarray]:
+    """
+    Drop-in for the reference's `neuralfoil.get_aero_from_kulfan_parameters` (main.py:64-332): same
+    arguments, same 198-key dict of float64 arrays of shape (N_cases,), same ValueErrors.  The values
+    come from the fp32 CUDA path and agree with the reference's float64 NumPy path to the tolerance
+    stated in DESIGN.md.
+    """
+    return default_evaluator().get_aero_from_kulfan_parameters(
+        kulfan_parameters, alpha, Re, n_crit=n_crit, xtr_upper=xtr_upper, xtr_lower=xtr_lower, model_size=model_size
+    )

@@ -127,6 +127,22 @@ def mlp(layers, x: np.ndarray) -> np.ndarray:
     return h
 
 
+def mlp_fp32(layers, x: np.ndarray) -> np.ndarray:
+    """
+    The same network evaluated entirely in float32 (inputs rounded to float32, float32 GEMM,
+    float32 SiLU).  Not part of the reference: it is the "plain fp32 reference" that tells the tests
+    how much of the CUDA path's deviation from float64 is inherent to fp32 arithmetic.
+    """
+    h = np.asarray(x, dtype=np.float32)
+    last = len(layers) - 1
+    for j, (w, b) in enumerate(layers):
+        h = np.asarray(w, dtype=np.float32) @ h + np.asarray(b, dtype=np.float32)[:, None]
+        if j != last:
+            with np.errstate(over="ignore"):
+                h = (h / (np.float32(1) + np.exp(-h))).astype(np.float32)
+    return h.astype(np.float64)
+
+
 def squared_mahalanobis(dist, x: np.ndarray) -> np.ndarray:
     """(25, N) -> (N,).  main.py:47-61."""
     d = x - dist["mean"][:, None]
@@ -160,15 +176,15 @@ def unflip_outputs(f: np.ndarray) -> np.ndarray:
     return u
 
 
-def latent_twins(layers, dist, x: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+def latent_twins(layers, dist, x: np.ndarray, net=mlp) -> tuple[np.ndarray, np.ndarray]:
     """
     Both network evaluations with the Mahalanobis logit correction applied to each
     (main.py:243-246, 267-270).  Returns (y, y_flipped), each (198, N), latent space.
     """
-    y = mlp(layers, x)
+    y = net(layers, x)
     y[0] = y[0] - squared_mahalanobis(dist, x) / (2 * N_INPUTS)
     xf = flip_inputs(x)
-    yf = mlp(layers, xf)
+    yf = net(layers, xf)
     yf[0] = yf[0] - squared_mahalanobis(dist, xf) / (2 * N_INPUTS)
     return y, yf
 
@@ -204,11 +220,14 @@ def decode(z: np.ndarray, Re: np.ndarray) -> np.ndarray:
     return out
 
 
-def evaluate_raw(layers, dist, raw: np.ndarray, return_latent: bool = False):
-    """raw (23, N) float64 -> (198, N) float64 physical outputs (and optionally the fused latent)."""
+def evaluate_raw(layers, dist, raw: np.ndarray, return_latent: bool = False, fp32_mlp: bool = False):
+    """
+    raw (23, N) float64 -> (198, N) float64 physical outputs (and optionally the fused latent).
+    `fp32_mlp=True` swaps in `mlp_fp32` (everything else stays float64): the fp32 yardstick.
+    """
     raw = np.asarray(raw, dtype=np.float64)
     x = featurise(raw)
-    y, yf = latent_twins(layers, dist, x)
+    y, yf = latent_twins(layers, dist, x, net=mlp_fp32 if fp32_mlp else mlp)
     z = fuse(y, yf)
     out = decode(z, raw[19])
     return (out, z) if return_latent else out
@@ -275,8 +294,8 @@ class Oracle:
         for size, params in (extra_models or {}).items():
             self.models[size] = layers_from_npz_dict(params)
 
-    def evaluate_raw(self, raw, model_size="xlarge", return_latent=False):
-        return evaluate_raw(self.models[model_size], self.dist, raw, return_latent)
+    def evaluate_raw(self, raw, model_size="xlarge", return_latent=False, fp32_mlp=False):
+        return evaluate_raw(self.models[model_size], self.dist, raw, return_latent, fp32_mlp)
 
     def get_aero_from_kulfan_parameters(
         self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"

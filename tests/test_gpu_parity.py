@@ -1,0 +1,308 @@
+"""
+Parity of the CUDA path (through the C ABI) against
+  * fixtures written by the unmodified reference (tests/golden/*.npz, tests/golden/make_golden.py),
+  * the reference's own known-answer vector (reference tests/test_golden_values.py:22-37),
+  * the CPU oracle on seeded inputs, every model size, ragged and tiny batches,
+  * the reference's structural invariants (reference tests/test_invariants.py, test_robustness.py),
+  * size-independent properties at BASELINE.json's batch sizes (mirror identity, batch-position
+    independence, a subsample against the oracle).
+The tolerance is defined and justified in tests/parity.py.
+"""
+
+import numpy as np
+import pytest
+
+from neuralfoil_b200 import synthetic
+from neuralfoil_b200.main import MODEL_SIZES, output_keys
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+KULFAN = synthetic.FIXED_KULFAN
+SCALARS = ["analysis_confidence", "CL", "CD", "CM", "Top_Xtr", "Bot_Xtr"]
+
+# reference tests/test_golden_values.py:29-37
+GOLDEN_MEDIUM = {
+    "analysis_confidence": 0.955711837783,
+    "CL": 1.10332809679,
+    "CD": 0.00919882438456,
+    "CM": -0.110598030451,
+    "Top_Xtr": 0.250543496781,
+    "Bot_Xtr": 0.964878409058,
+}
+
+
+def stack(aero: dict) -> np.ndarray:
+    return np.stack([aero[k] for k in output_keys()])
+
+
+def mirrored(raw: np.ndarray) -> np.ndarray:
+    """The airfoil mirrored about its chord, at -alpha, transition locations swapped (test_invariants.py:55-90)."""
+    m = raw.copy()
+    m[0:8] = -raw[8:16]
+    m[8:16] = -raw[0:8]
+    m[16] = -raw[16]
+    m[18] = -raw[18]
+    m[21] = raw[22]
+    m[22] = raw[21]
+    return m
+
+
+def unmirror_outputs(out: np.ndarray) -> np.ndarray:
+    """What the mirrored airfoil's outputs must look like in terms of the original's."""
+    n = 32
+    u = out.copy()
+    u[1] = -out[1]
+    u[3] = -out[3]
+    u[4], u[5] = out[5], out[4]
+    u[6 : 6 + 2 * n], u[6 + 3 * n : 6 + 5 * n] = out[6 + 3 * n : 6 + 5 * n], out[6 : 6 + 2 * n]
+    u[6 + 2 * n : 6 + 3 * n] = -out[6 + 5 * n : 6 + 6 * n]
+    u[6 + 5 * n : 6 + 6 * n] = -out[6 + 2 * n : 6 + 3 * n]
+    return u
+
+
+# ---------------------------------------------------------------------------------------------
+# Known answers
+# ---------------------------------------------------------------------------------------------
+def test_reference_known_answer_medium(evaluator):
+    aero = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=5.0, Re=1e6, model_size="medium")
+    for key, want in GOLDEN_MEDIUM.items():
+        # reference tolerance is rel 1e-6 for its own float64 path; fp32 bound from tests/parity.py
+        assert float(aero[key][0]) == pytest.approx(want, rel=1e-5, abs=6e-5), key
+
+
+@pytest.mark.parametrize("size", MODEL_SIZES)
+def test_matches_reference_fixture_all_outputs(evaluator, golden_dir, size):
+    g = np.load(golden_dir / "golden_all_sizes.npz")
+    raw = g["raw"]
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64)
+    assert got.shape == (198, raw.shape[1]) and got.dtype == np.float64
+    parity.assert_parity(got, g[f"out_{size}"], raw[19], check_distribution=False, label=size)
+
+
+def test_matches_reference_fixture_config1(evaluator, golden_dir):
+    """BASELINE.json configs[0]: alpha sweep of 1000 points, Re = 5e6, xlarge, through the dict API."""
+    g = np.load(golden_dir / "golden_config1_xlarge.npz")
+    aero = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=g["alpha"], Re=float(g["Re"]), model_size="xlarge")
+    full = stack(aero)
+    for i, tol in enumerate([6.25e-5, 1.25e-4, None, 1.25e-5, 2.5e-4, 2.5e-4]):
+        if tol is None:
+            np.testing.assert_allclose(full[i], g["scalars"][i], rtol=5e-4)
+        else:
+            np.testing.assert_allclose(full[i], g["scalars"][i], rtol=1e-5, atol=tol)
+    parity.assert_parity(full[:, ::20], g["full_every_20"], np.full(50, float(g["Re"])), check_distribution=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# Against the oracle, every size, both I/O precisions, ragged sizes
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", MODEL_SIZES)
+def test_matches_oracle_random_batch(evaluator, oracle, size):
+    raw = synthetic.sample_training_distribution(5003, seed=11)  # not a multiple of any tile size
+    want = oracle.evaluate_raw(raw, size)
+    got64 = evaluator.evaluate_host(raw, size, out_dtype=np.float64)
+    rep = parity.assert_parity(got64, want, raw[19], label=f"{size} f64 io")
+    # fp32 inputs and outputs: the oracle sees the same rounded inputs
+    raw32 = raw.astype(np.float32)
+    got32 = evaluator.evaluate_host(raw32, size, out_dtype=np.float32)
+    assert got32.dtype == np.float32
+    want32 = oracle.evaluate_raw(raw32.astype(np.float64), size)
+    parity.assert_parity(got32, want32, raw32[19].astype(np.float64), label=f"{size} f32 io")
+    # the CUDA path must be no worse than a plain fp32 evaluation by more than a small factor
+    yard = parity.error_report(oracle.evaluate_raw(raw, size, fp32_mlp=True), want, raw[19])
+    assert rep["median_rel"] <= 3 * yard["median_rel"] + 1e-7, (rep, yard)
+    assert rep["worst_ratio"] <= 4 * yard["worst_ratio"] + 0.05, (rep, yard)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 32, 33, 63, 65, 255, 257, 1000])
+@pytest.mark.parametrize("size", ["xxsmall", "large", "xxxlarge"])
+def test_ragged_batch_sizes(evaluator, oracle, size, n):
+    raw = synthetic.sample_training_distribution(n, seed=100 + n)
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64)
+    assert got.shape == (198, n)
+    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], check_distribution=False, label=f"{size} n={n}")
+
+
+def test_polar_grid_broadcast_rows(evaluator, oracle):
+    """BASELINE.json configs[1] shape: one airfoil (18 broadcast scalars), 3 varying flow columns."""
+    raw = synthetic.polar_grid(12, 11, 10)
+    kulfan, flow = synthetic.kulfan_dict_from_raw(raw[:, :1])
+    aero = evaluator.get_aero_from_kulfan_parameters(
+        {k: (v[:, 0] if v.ndim == 2 else float(v[0])) for k, v in kulfan.items()},
+        alpha=raw[18], Re=raw[19], n_crit=raw[20], model_size="large",
+    )
+    parity.assert_parity(stack(aero), oracle.evaluate_raw(raw, "large"), raw[19], check_distribution=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's invariants (exact in the reference; must stay exact in fp32)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", ["medium", "xlarge", "xxxlarge"])
+def test_symmetric_airfoil_zero_alpha(evaluator, size):
+    """reference tests/test_invariants.py:35-52"""
+    w = np.array([0.15, 0.20, 0.15, 0.20, 0.15, 0.20, 0.15, 0.15])
+    sym = dict(upper_weights=w, lower_weights=-w, leading_edge_weight=0.0, TE_thickness=0.002)
+    aero = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size=size)
+    assert abs(aero["CL"][0]) < 1e-14 and abs(aero["CM"][0]) < 1e-14
+    assert aero["Top_Xtr"][0] == pytest.approx(aero["Bot_Xtr"][0], abs=1e-14)
+
+
+def test_mirror_identity_reference_case(evaluator, golden_dir):
+    """reference tests/test_invariants.py:55-90, plus agreement with the reference's numbers"""
+    g = np.load(golden_dir / "golden_mirror_large.npz")
+    alpha = g["alpha"]
+    kw = dict(Re=5e5, n_crit=8.0, model_size="large")
+    mirror = dict(
+        upper_weights=-KULFAN["lower_weights"],
+        lower_weights=-KULFAN["upper_weights"],
+        leading_edge_weight=-KULFAN["leading_edge_weight"],
+        TE_thickness=KULFAN["TE_thickness"],
+    )
+    a = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=alpha, xtr_upper=0.7, xtr_lower=0.4, **kw)
+    m = evaluator.get_aero_from_kulfan_parameters(mirror, alpha=-alpha, xtr_upper=0.4, xtr_lower=0.7, **kw)
+    re = np.full(alpha.size, 5e5)
+    parity.assert_parity(stack(a), g["out"], re, check_distribution=False)
+    parity.assert_parity(stack(m), g["out_mirror"], re, check_distribution=False)
+    tol = dict(rtol=0, atol=1e-12)  # the reference's own tolerance
+    np.testing.assert_allclose(m["CL"], -a["CL"], **tol)
+    np.testing.assert_allclose(m["CM"], -a["CM"], **tol)
+    np.testing.assert_allclose(m["CD"], a["CD"], **tol)
+    np.testing.assert_allclose(m["analysis_confidence"], a["analysis_confidence"], **tol)
+    np.testing.assert_allclose(m["Top_Xtr"], a["Bot_Xtr"], **tol)
+    np.testing.assert_allclose(m["Bot_Xtr"], a["Top_Xtr"], **tol)
+    for i in range(32):
+        for q in ("theta", "H"):
+            np.testing.assert_allclose(m[f"upper_bl_{q}_{i}"], a[f"lower_bl_{q}_{i}"], **tol)
+            np.testing.assert_allclose(m[f"lower_bl_{q}_{i}"], a[f"upper_bl_{q}_{i}"], **tol)
+        np.testing.assert_allclose(m[f"upper_bl_ue/vinf_{i}"], -a[f"lower_bl_ue/vinf_{i}"], **tol)
+        np.testing.assert_allclose(m[f"lower_bl_ue/vinf_{i}"], -a[f"upper_bl_ue/vinf_{i}"], **tol)
+
+
+def test_output_contract(evaluator):
+    """reference tests/test_invariants.py:93-118"""
+    aero = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=3.0, Re=1e6, model_size="large")
+    assert list(aero) == output_keys() and len(aero) == 198
+    for k, v in aero.items():
+        assert isinstance(v, np.ndarray) and v.shape == (1,) and v.dtype == np.float64, k
+        assert np.isfinite(v).all() and v.flags["C_CONTIGUOUS"] and v.flags["WRITEABLE"], k
+    assert 0 <= aero["analysis_confidence"][0] <= 1 and aero["CD"][0] > 0
+    assert 0 <= aero["Top_Xtr"][0] <= 1 and 0 <= aero["Bot_Xtr"][0] <= 1
+    for i in range(32):
+        for side in ("upper", "lower"):
+            assert aero[f"{side}_bl_theta_{i}"][0] > 0 and aero[f"{side}_bl_H_{i}"][0] > 1
+
+
+def test_vectorised_matches_scalar_loop(evaluator):
+    """reference tests/test_invariants.py:121-136 -- here bit for bit: a query's result may not depend on its position"""
+    alphas = np.array([-10.0, -2.0, 3.0, 8.0, 15.0])
+    Res = np.array([5e4, 2e5, 1e6, 5e6, 2e7])
+    batch = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=alphas, Re=Res, model_size="medium")
+    for i in range(5):
+        one = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=alphas[i], Re=Res[i], model_size="medium")
+        for k in output_keys():
+            assert batch[k][i] == one[k][0], (k, i)
+
+
+@pytest.mark.parametrize("size", [s for s in MODEL_SIZES])
+def test_all_model_sizes_load_and_run(evaluator, size):
+    """reference tests/test_robustness.py:31-40 (xxxlarge: seeded synthetic weights, physics ranges not asserted)"""
+    aero = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=5.0, Re=1e6, model_size=size)
+    for k in SCALARS:
+        assert np.isfinite(aero[k]).all(), k
+    if size != "xxxlarge" or "xxxlarge" not in evaluator.model_dims or not _is_synthetic(evaluator):
+        assert 0 < aero["CD"][0] < 1 and -1 < aero["CL"][0] < 3
+
+
+def _is_synthetic(evaluator) -> bool:
+    return not (evaluator.weights_dir / "nn-xxxlarge.npz").exists()
+
+
+@pytest.mark.parametrize("alpha", [-180.0, -90.0, 90.0, 180.0])
+@pytest.mark.parametrize("Re", [1e2, 1e10])
+def test_always_returns_an_answer(evaluator, oracle, alpha, Re):
+    """reference tests/test_robustness.py:43-57"""
+    aero = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=alpha, Re=Re, model_size="large")
+    for k in SCALARS:
+        assert np.isfinite(aero[k]).all(), k
+    assert 0 <= aero["analysis_confidence"][0] <= 1 and aero["CD"][0] > 0
+    want = oracle.get_aero_from_kulfan_parameters(KULFAN, alpha=alpha, Re=Re, model_size="large")
+    parity.assert_parity(stack(aero), np.stack(list(want.values())), np.array([Re]), check_distribution=False)
+
+
+def test_error_paths(evaluator):
+    """reference tests/test_robustness.py:60-83"""
+    with pytest.raises(ValueError, match="model_size"):
+        evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=5.0, Re=1e6, model_size="gigantic")
+    with pytest.raises(ValueError, match="same length"):
+        evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=np.linspace(0, 5, 3), Re=np.full(4, 1e6))
+    bad = dict(KULFAN, upper_weights=np.full(7, 0.2), lower_weights=np.full(7, -0.1))
+    with pytest.raises(ValueError, match="8 CST weights per side"):
+        evaluator.get_aero_from_kulfan_parameters(bad, alpha=5.0, Re=1e6)
+
+
+def test_nan_inputs_propagate(evaluator):
+    """NaN input -> NaN outputs, silently; Re <= 0 -> NaN."""
+    aero = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=np.array([np.nan, 2.0]), Re=1e6, model_size="medium")
+    assert np.isnan(aero["CL"][0]) and np.isnan(aero["Top_Xtr"][0]) and np.isfinite(aero["CL"][1])
+    aero = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=2.0, Re=-1.0, model_size="medium")
+    assert np.isnan(aero["CL"][0])
+
+
+def test_kulfan_weights_as_8_by_n(evaluator, oracle):
+    """(8, N) weight arrays, the layout of studies/naca_airfoil_extrapolation_study.py:44-53"""
+    raw = synthetic.sample_training_distribution(77, seed=3)
+    kulfan, flow = synthetic.kulfan_dict_from_raw(raw)
+    aero = evaluator.get_aero_from_kulfan_parameters(kulfan, model_size="small", **flow)
+    parity.assert_parity(stack(aero), oracle.evaluate_raw(raw, "small"), raw[19], check_distribution=False)
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-resident API and BASELINE-sized batches
+# ---------------------------------------------------------------------------------------------
+def test_device_api_equals_host_api(evaluator):
+    import torch
+
+    raw = synthetic.sample_training_distribution(4099, seed=21).astype(np.float32)
+    host = evaluator.evaluate_host(raw, "xlarge", out_dtype=np.float32)
+    dev = evaluator.evaluate_device(torch.from_numpy(raw).cuda(), "xlarge")
+    torch.cuda.synchronize()
+    assert dev.shape == (198, 4099) and dev.dtype == torch.float32
+    np.testing.assert_array_equal(dev.cpu().numpy(), host)
+    # unaligned leading dimension -> scalar-store path, same numbers
+    out = torch.empty((198, 4101), dtype=torch.float32, device="cuda")
+    dev2 = evaluator.evaluate_device(torch.from_numpy(raw).cuda(), "xlarge", out=out)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dev2.cpu().numpy(), host)
+
+
+def test_host_chunking_is_invisible(evaluator):
+    raw = synthetic.sample_training_distribution(50_000, seed=8).astype(np.float32)
+    one = evaluator.evaluate_host(raw, "small", out_dtype=np.float32)
+    many = evaluator.evaluate_host(raw, "small", out_dtype=np.float32, chunk=7000)
+    np.testing.assert_array_equal(one, many)
+
+
+@pytest.mark.parametrize("size,n", [("xxxlarge", 1_000_000), ("xlarge", 1_000_000), ("xxsmall", 2_000_000)])
+def test_large_batch_properties(evaluator, oracle, size, n):
+    """
+    BASELINE-sized batches, checked through properties that do not need the oracle at full size:
+    (a) mirror identity, bit for bit, over the whole batch; (b) batch-position independence: a
+    permuted batch gives permuted results, bit for bit; (c) a strided subsample against the oracle.
+    """
+    import torch
+
+    raw = synthetic.sample_training_distribution(n, seed=2).astype(np.float32)
+    d_raw = torch.from_numpy(raw).cuda()
+    out = evaluator.evaluate_device(d_raw, size)
+    out_m = evaluator.evaluate_device(torch.from_numpy(mirrored(raw)).cuda(), size)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(0)).cuda()
+    out_p = evaluator.evaluate_device(d_raw[:, perm].contiguous(), size)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out[:6]).all()
+    assert torch.equal(out_p, out[:, perm])
+    o, m = out.cpu().numpy(), out_m.cpu().numpy()
+    np.testing.assert_array_equal(m, unmirror_outputs(o))
+    idx = np.arange(0, n, n // 2000)
+    want = oracle.evaluate_raw(raw[:, idx].astype(np.float64), size)
+    parity.assert_parity(o[:, idx], want, raw[19, idx].astype(np.float64), label=f"{size} n={n}")
