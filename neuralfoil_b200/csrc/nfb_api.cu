@@ -404,13 +404,13 @@ int nfb_measure_fp32_peak(nfb_context* ctx, int iters, double* out_tflops) {
   cudaEvent_t e0, e1;
   NFB_CUDA(cudaEventCreate(&e0));
   NFB_CUDA(cudaEventCreate(&e1));
-  const int inner = 4096, blocks = ctx->sm_count * 4;
-  const double flops = 2.0 * 64 * 8 * double(inner) * 512.0 * blocks;
+  const int inner = 2048, blocks = ctx->sm_count * 2;
+  const double flops = 2.0 * 16 * 32 * double(inner) * 1024.0 * blocks;
   double best = 0.0;
   if (iters < 1) iters = 1;
   for (int i = 0; i < iters + 2; ++i) {  // two warm-up launches
     NFB_CUDA(cudaEventRecord(e0, 0));
-    nfb::nfb_ffma_peak_kernel<<<blocks, 512>>>(sink, inner);
+    nfb::nfb_ffma_peak_kernel<<<blocks, 1024>>>(sink, inner);
     NFB_CUDA(cudaEventRecord(e1, 0));
     NFB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

@@ -56,12 +56,21 @@ __device__ __forceinline__ float silu(float h) {
 // One K-slice of the register-blocked GEMM: acc[TM][8] += W[k][rows] * act[k][cols], k = 0..KC-1.
 // `w` points at this thread's first row inside the slice (row stride MP floats per k);
 // `a` points at this thread's first column in the activation tile (row stride NC).
+//
+// The multiply-adds are issued as packed FFMA2 (fma.rn.f32x2, sm_100+): one weight scalar times a
+// pair of adjacent columns.  Measured on B200 (scripts/ffma_peak.cu): the scalar 8x8 outer product
+// tops out at 85 of 128 FFMA lanes/clk/SM because every FFMA reads two new 32-bit registers that ptxas
+// cannot keep in opposite banks; FFMA2 with the column pair held in the operand-reuse cache while the
+// eight rows stream past it (j outer, i inner) reaches 126.  Each accumulator still sees one IEEE
+// fma per k, in k order, so results are bit-identical to the scalar loop.
+// acc[i][jj] holds columns (2 jj, 2 jj + 1) of row i: jj = 0,1 -> queries, jj = 2,3 -> their twins.
 template <int TM, int MP, int NC, int KC>
 __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const float* __restrict__ a,
-                                           float (&acc)[TM][8]) {
+                                           float2 (&acc)[TM][4]) {
 #pragma unroll
   for (int kk = 0; kk < KC; ++kk) {
-    float wv[TM], av[8];
+    float wv[TM];
+    float2 av[4];
     {
       const float4 t = *reinterpret_cast<const float4*>(w + kk * MP);
       wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
@@ -72,16 +81,17 @@ __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const fl
     }
     {
       const float4 t = *reinterpret_cast<const float4*>(a + kk * NC);
-      av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+      av[0] = make_float2(t.x, t.y); av[1] = make_float2(t.z, t.w);
     }
     {
       const float4 t = *reinterpret_cast<const float4*>(a + kk * NC + NC / 2);
-      av[4] = t.x; av[5] = t.y; av[6] = t.z; av[7] = t.w;
+      av[2] = make_float2(t.x, t.y); av[3] = make_float2(t.z, t.w);
     }
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
+    for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], av[j], acc[i][j]);
+      for (int i = 0; i < TM; ++i)
+        acc[i][jj] = __ffma2_rn(make_float2(wv[i], wv[i]), av[jj], acc[i][jj]);
   }
 }
 
@@ -192,10 +202,18 @@ __device__ __forceinline__ float clip01_keep_nan(float z) {  // np.clip propagat
 // Un-flip + average + squash + decode for one thread's 4 rows x (4 queries + 4 twins) and store.
 // acc[i][j]: packed row 4g+i, query j (j < 4) or twin of query j-4.   [main.py:274-316]
 __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, long long q0, int nvalid,
-                                                 bool vec_ok, const float (&acc)[4][8],
+                                                 bool vec_ok, const float2 (&acc2)[4][4],
                                                  const float* __restrict__ maha_o,
                                                  const float* __restrict__ maha_t,
                                                  const float* __restrict__ re4) {
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      acc[i][2 * jj] = acc2[i][jj].x;
+      acc[i][2 * jj + 1] = acc2[i][jj].y;
+    }
   float o0[4], o1[4], o2[4], o3[4];
   if (g < N_BL) {  // theta_u, ue_u, theta_l, ue_l of station g
 #pragma unroll
@@ -347,14 +365,14 @@ __global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const Eval
     for (int l = 0; l < L - 1; ++l) {
       const int K = (l == 0) ? K0_PAD : H;
       const float* bias = p.blob + blob_layer_offset<H>(l) + size_t(K) * H;
-      float acc[8][8];
+      float2 acc[8][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float b_lo = __ldg(bias + h_row + i), b_hi = __ldg(bias + H / 2 + h_row + i);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[i][j] = b_lo;
-          acc[4 + i][j] = b_hi;
+        for (int jj = 0; jj < 4; ++jj) {
+          acc[i][jj] = make_float2(b_lo, b_lo);
+          acc[4 + i][jj] = make_float2(b_hi, b_hi);
         }
       }
       for (int c = 0; c < K / KC; ++c, ++it) {
@@ -374,8 +392,8 @@ __global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const Eval
       for (int i = 0; i < 8; ++i) {
         const int row = (i < 4) ? h_row + i : H / 2 + h_row + (i - 4);
         float4 lo, hi;
-        lo.x = silu(acc[i][0]); lo.y = silu(acc[i][1]); lo.z = silu(acc[i][2]); lo.w = silu(acc[i][3]);
-        hi.x = silu(acc[i][4]); hi.y = silu(acc[i][5]); hi.z = silu(acc[i][6]); hi.w = silu(acc[i][7]);
+        lo.x = silu(acc[i][0].x); lo.y = silu(acc[i][0].y); lo.z = silu(acc[i][1].x); lo.w = silu(acc[i][1].y);
+        hi.x = silu(acc[i][2].x); hi.y = silu(acc[i][2].y); hi.z = silu(acc[i][3].x); hi.w = silu(acc[i][3].y);
         *reinterpret_cast<float4*>(act + row * NC + h_col) = lo;
         *reinterpret_cast<float4*>(act + row * NC + NC / 2 + h_col) = hi;
       }
@@ -387,13 +405,13 @@ __global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const Eval
       const float* bias = p.blob + blob_layer_offset<H>(L - 1) + size_t(H) * M_LAST;
       for (int pass = 0; pass < WN; ++pass) {
         const int col = pass * 32 + ln * 4;
-        float acc[4][8];
+        float2 acc[4][4];
         if (last_active) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float b = __ldg(bias + g_last * 4 + i);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = b;
+            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = make_float2(b, b);
           }
         }
         for (int c = 0; c < H / KC; ++c, ++it) {
@@ -420,31 +438,23 @@ __global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const Eval
   }
 }
 
-// ---- fp32 peak microbenchmark: the same 8x8 outer-product FFMA pattern, operands in registers ------
-__global__ void __launch_bounds__(512, 1) nfb_ffma_peak_kernel(float* sink, int iters) {
-  float a[8], b[8], acc[8][8];
+// ---- fp32 peak microbenchmark -----------------------------------------------------------------------
+// 16 independent x <- x * a + b chains per thread, 32 warps per SM: the FFMA issue-rate ceiling of the
+// chip (measured 126.8 of 128 lanes/clk/SM on B200; scripts/ffma_peak.cu has the other patterns).
+__global__ void __launch_bounds__(1024, 1) nfb_ffma_peak_kernel(float* sink, int iters) {
+  float x[16];
+  const float a = 1.0f + 1e-6f * threadIdx.x, b = 1e-3f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
-    b[i] = 1.0f - 1e-3f * (threadIdx.x * 3 + i);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-  }
+  for (int i = 0; i < 16; ++i) x[i] = float(i);
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 32; ++u)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      a[u] = -a[u];  // keeps the compiler from collapsing iterations; 1 op per 64 FFMA
-    }
+      for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
   }
   float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += acc[i][j];
+  for (int i = 0; i < 16; ++i) s += x[i];
   if (s == 123.456f) sink[0] = s;  // never true in practice; defeats dead-code elimination
 }
 
