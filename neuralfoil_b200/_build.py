@@ -61,7 +61,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
     tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(tmp), *map(str, _sources())]
+    extra = os.environ.get("NFB_NVCC_EXTRA", "").split()  # tuning experiments only, e.g. "-DNFB_TN=8"
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-o", str(tmp), *map(str, _sources())]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd), flush=True)

@@ -39,10 +39,21 @@ struct Model {
 };
 
 // Kernel tuning per padded width: <H, KC, STAGES>.
-using Cfg64 = nfb::FfmaCfg<64, 8, 4>;
-using Cfg128 = nfb::FfmaCfg<128, 8, 4>;
-using Cfg256 = nfb::FfmaCfg<256, 8, 4>;
-using Cfg512 = nfb::FfmaCfg<512, 8, 4>;
+// Measured on B200: the 8 x 16 thread tile (8 warps) wins where the GEMM dominates
+// (wide models), the 8 x 8 tile (16 warps) where the per-query fp64/MUFU work does (narrow models).
+#ifndef NFB_TN_WIDE
+#define NFB_TN_WIDE 16
+#endif
+#ifndef NFB_TN_NARROW
+#define NFB_TN_NARROW 8
+#endif
+#ifndef NFB_KC
+#define NFB_KC 8
+#endif
+using Cfg64 = nfb::FfmaCfg<64, NFB_KC, 4, NFB_TN_NARROW>;
+using Cfg128 = nfb::FfmaCfg<128, NFB_KC, 4, NFB_TN_WIDE>;
+using Cfg256 = nfb::FfmaCfg<256, NFB_KC, 4, NFB_TN_WIDE>;
+using Cfg512 = nfb::FfmaCfg<512, NFB_KC, 4, NFB_TN_WIDE>;
 
 struct HostSlot {  // one in-flight chunk of nfb_eval_host
   cudaStream_t stream = nullptr;
@@ -99,7 +110,7 @@ int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream)
   }
   const long long tiles = (p.n + Cfg::NQ - 1) / Cfg::NQ;
   const int grid = int(std::min<long long>(tiles, ctx->sm_count));
-  nfb::nfb_ffma_kernel<Cfg><<<grid, nfb::COMPUTE_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  nfb::nfb_ffma_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   NFB_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return NFB_OK;

@@ -10,13 +10,13 @@ constexpr int N_IN = 25;         // latent inputs
 constexpr int K0_PAD = 32;       // first layer's K, zero-padded from 25
 constexpr int N_OUT = 198;       // latent / physical outputs per query
 constexpr int N_BL = 32;         // boundary-layer stations per side (_basic_data_type.py:51)
-constexpr int M_LAST = 208;      // last layer's rows, permuted + padded (see pack_last_layer_row)
+constexpr int M_LAST_USED = 200;  // last layer's rows after the permutation of pack_last_layer_row
+constexpr int M_LAST = 224;      // ... padded to a whole number of warps' row groups (16 or 32 rows)
 constexpr int N_MAHA = 325;      // packed upper triangle of the 25x25 quadratic form
 
 constexpr int NFB_MAX_LAYERS_K = 16;  // == NFB_MAX_LAYERS of the C header
 
-constexpr int COMPUTE_WARPS = 16;
-constexpr int COMPUTE_THREADS = COMPUTE_WARPS * 32;  // the whole CTA
+
 
 // Per-launch arguments.  Passed by value (kernel parameter space, constant bank).
 struct EvalParams {
@@ -45,7 +45,7 @@ __constant__ double c_quad[N_MAHA];
 //   g in [32,48) : stations 2(g-32), +1 -> H_upper x2, H_lower x2
 //   g == 48      : analysis_confidence logit, CL, ln CD, CM latents
 //   g == 49      : Top_Xtr, Bot_Xtr, pad, pad
-//   g in {50,51} : pad
+//   g in [50,56) : pad
 __host__ __device__ constexpr int pack_last_layer_row(int p) {
   const int g = p >> 2, i = p & 3;
   if (g < 32) return (i == 0) ? 6 + g : (i == 1) ? 70 + g : (i == 2) ? 102 + g : 166 + g;

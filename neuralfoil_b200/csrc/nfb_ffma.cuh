@@ -6,7 +6,7 @@
 //      rounded to fp32 into the activation tile in shared memory.
 //   2. every hidden layer: act <- SiLU(W act + b) [218-241] as a register-blocked FFMA GEMM, the
 //      tile (H x NC fp32) never leaving shared memory; weights arrive in K-slices through a ring of
-//      TMA bulk copies (L2 -> smem) issued by lane 0 of the compute warps in turn (see issue_slice).
+//      TMA bulk copies (L2 -> smem) issued by lane 0 of the warps in turn (see issue_slice).
 //   3. last layer with its rows permuted so that each thread owns, for four queries AND their twins,
 //      exactly the rows that un-flip, average, squash and decode need [244-246, 268-316]; results go
 //      straight from registers to global memory as 16-byte streaming stores, full 128-byte lines.
@@ -18,21 +18,28 @@
 
 namespace nfb {
 
-template <int H_, int KC_, int STAGES_>
+template <int H_, int KC_, int STAGES_, int TN_>
 struct FfmaCfg {
   static constexpr int H = H_;                  // padded hidden width: 64, 128, 256 or 512
   static constexpr int KC = KC_;                // K rows per streamed weight slice
   static constexpr int STAGES = STAGES_;        // ring depth
-  static constexpr int NC = 32768 / H;          // columns per tile: 64 accumulators x 512 threads / H
+  static constexpr int TN = TN_;                // columns per thread: 8 (4 queries + twins) or 16 (8 + twins)
+  static constexpr int WARPS = 128 / TN;        // 64 accumulators x 512 threads == 128 x 256 threads
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int LN = 64 / TN;            // lanes along columns: a warp always spans 64 columns
+  static constexpr int LM = 32 / LN;            // lanes along rows
+  static constexpr int NC = 32768 / H;          // columns per tile (queries + twins)
   static constexpr int NQ = NC / 2;             // queries per tile
-  static constexpr int WM = H / 32;             // warps along rows (hidden layers)
-  static constexpr int WN = COMPUTE_WARPS / WM; // warps along columns == last-layer passes
+  static constexpr int WM = H / (8 * LM);       // warps along rows (hidden layers, 8 rows per thread)
+  static constexpr int WN = WARPS / WM;         // warps along columns == last-layer passes == NC / 64
   static constexpr int SLOT_FLOATS = KC * (H > M_LAST ? H : M_LAST);
   static constexpr int MAX_SLICES =  // slices per tile at the deepest supported network
       K0_PAD / KC + (NFB_MAX_LAYERS_K - 2) * (H / KC) + WN * (H / KC);
   static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t(H) * NC + size_t(STAGES) * SLOT_FLOATS + NC + NQ) +
                                        16 * STAGES + 8 * size_t(MAX_SLICES);
-  static_assert(H % 32 == 0 && COMPUTE_WARPS % WM == 0, "bad width");
+  static_assert(TN == 8 || TN == 16, "thread tile is 8 or 16 columns wide");
+  static_assert(H % (8 * LM) == 0 && WARPS % WM == 0 && WN * 64 == NC, "bad width");
+  static_assert(WARPS * LM * 4 >= M_LAST_USED, "last layer does not fit the row groups");
   static_assert((STAGES & (STAGES - 1)) == 0 && STAGES >= 4, "STAGES must be a power of two >= 4");
   static_assert(K0_PAD % KC == 0 && H % KC == 0, "KC must divide every K");
 };
@@ -63,14 +70,14 @@ __device__ __forceinline__ float silu(float h) {
 // cannot keep in opposite banks; FFMA2 with the column pair held in the operand-reuse cache while the
 // eight rows stream past it (j outer, i inner) reaches 126.  Each accumulator still sees one IEEE
 // fma per k, in k order, so results are bit-identical to the scalar loop.
-// acc[i][jj] holds columns (2 jj, 2 jj + 1) of row i: jj = 0,1 -> queries, jj = 2,3 -> their twins.
-template <int TM, int MP, int NC, int KC>
+// acc[i][jj] holds columns (2 jj, 2 jj + 1) of row i: jj < TN/4 -> queries, the rest -> their twins.
+template <int TM, int TN, int MP, int NC, int KC>
 __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const float* __restrict__ a,
-                                           float2 (&acc)[TM][4]) {
+                                           float2 (&acc)[TM][TN / 2]) {
 #pragma unroll
   for (int kk = 0; kk < KC; ++kk) {
     float wv[TM];
-    float2 av[4];
+    float2 av[TN / 2];
     {
       const float4 t = *reinterpret_cast<const float4*>(w + kk * MP);
       wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
@@ -79,16 +86,15 @@ __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const fl
       const float4 t = *reinterpret_cast<const float4*>(w + kk * MP + MP / 2);
       wv[4] = t.x; wv[5] = t.y; wv[6] = t.z; wv[7] = t.w;
     }
-    {
-      const float4 t = *reinterpret_cast<const float4*>(a + kk * NC);
-      av[0] = make_float2(t.x, t.y); av[1] = make_float2(t.z, t.w);
-    }
-    {
-      const float4 t = *reinterpret_cast<const float4*>(a + kk * NC + NC / 2);
-      av[2] = make_float2(t.x, t.y); av[3] = make_float2(t.z, t.w);
+#pragma unroll
+    for (int v = 0; v < TN / 8; ++v) {  // queries, then twins (NC / 2 columns further)
+      const float4 t = *reinterpret_cast<const float4*>(a + kk * NC + 4 * v);
+      av[2 * v] = make_float2(t.x, t.y); av[2 * v + 1] = make_float2(t.z, t.w);
+      const float4 u = *reinterpret_cast<const float4*>(a + kk * NC + NC / 2 + 4 * v);
+      av[TN / 4 + 2 * v] = make_float2(u.x, u.y); av[TN / 4 + 2 * v + 1] = make_float2(u.z, u.w);
     }
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
+    for (int jj = 0; jj < TN / 2; ++jj)
 #pragma unroll
       for (int i = 0; i < TM; ++i)
         acc[i][jj] = __ffma2_rn(make_float2(wv[i], wv[i]), av[jj], acc[i][jj]);
@@ -202,18 +208,10 @@ __device__ __forceinline__ float clip01_keep_nan(float z) {  // np.clip propagat
 // Un-flip + average + squash + decode for one thread's 4 rows x (4 queries + 4 twins) and store.
 // acc[i][j]: packed row 4g+i, query j (j < 4) or twin of query j-4.   [main.py:274-316]
 __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, long long q0, int nvalid,
-                                                 bool vec_ok, const float2 (&acc2)[4][4],
+                                                 bool vec_ok, const float (&acc)[4][8],
                                                  const float* __restrict__ maha_o,
                                                  const float* __restrict__ maha_t,
                                                  const float* __restrict__ re4) {
-  float acc[4][8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      acc[i][2 * jj] = acc2[i][jj].x;
-      acc[i][2 * jj + 1] = acc2[i][jj].y;
-    }
   float o0[4], o1[4], o2[4], o3[4];
   if (g < N_BL) {  // theta_u, ue_u, theta_l, ue_l of station g
 #pragma unroll
@@ -275,9 +273,9 @@ __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, lon
 // ---- the kernel ----------------------------------------------------------------------------------
 // Weight streaming: the slices of one tile form a fixed sequence (layer 0's K-slices, each hidden
 // layer's, then the last layer's once per pass) described by a table in shared memory.  Slice j of
-// the CTA's whole run lands in ring slot j % STAGES.  There is no producer warp (a 17th warp would
-// cap the compute warps at 96 registers): when a warp starts slice `it`, its lane 0 -- for the one
-// warp with (it + STAGES - 2) % 16 == warp -- issues the TMA bulk copy of slice it + STAGES - 2, whose
+// the CTA's whole run lands in ring slot j % STAGES.  There is no producer warp (an extra warp would
+// cap the compute warps' registers): when a warp starts slice `it`, its lane 0 -- for the one warp
+// with (it + STAGES - 2) % WARPS == warp -- issues the TMA bulk copy of slice it + STAGES - 2, whose
 // slot was last read by slice it - 2, which every warp has normally long finished.
 template <class Cfg>
 __device__ __forceinline__ void issue_slice(uint32_t j, uint32_t slices_per_tile, const uint2* __restrict__ table,
@@ -286,15 +284,16 @@ __device__ __forceinline__ void issue_slice(uint32_t j, uint32_t slices_per_tile
   constexpr int STAGES = Cfg::STAGES;
   const uint2 e = table[j % slices_per_tile];
   const uint32_t s = j & (STAGES - 1), ph = (j / STAGES) & 1;
-  mbar_wait(bar_empty + 8 * s, ph ^ 1);  // previous occupant (slice j - STAGES) released by all 16 warps
+  mbar_wait(bar_empty + 8 * s, ph ^ 1);  // previous occupant (slice j - STAGES) released by every warp
   mbar_arrive_expect_tx(bar_full + 8 * s, e.y);
   bulk_copy_g2s(smem_u32(ring + s * Cfg::SLOT_FLOATS), blob + e.x, e.y, bar_full + 8 * s);
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const EvalParams p) {
-  constexpr int H = Cfg::H, NC = Cfg::NC, NQ = Cfg::NQ, KC = Cfg::KC, STAGES = Cfg::STAGES;
-  constexpr int WM = Cfg::WM, WN = Cfg::WN, SLOT = Cfg::SLOT_FLOATS;
+__global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_kernel(const EvalParams p) {
+  constexpr int H = Cfg::H, NC = Cfg::NC, NQ = Cfg::NQ, KC = Cfg::KC, STAGES = Cfg::STAGES, TN = Cfg::TN;
+  constexpr int WM = Cfg::WM, WN = Cfg::WN, SLOT = Cfg::SLOT_FLOATS, LM = Cfg::LM, LN = Cfg::LN;
+  constexpr int WARPS = Cfg::WARPS, THREADS = Cfg::THREADS, QT = TN / 2;  // QT queries per thread
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* const act = reinterpret_cast<float*>(smem_raw);  // [H][NC]
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const Eval
   const uint32_t my_tiles = uint32_t((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const uint32_t total_slices = my_tiles * slices_per_tile;
 
-  for (uint32_t j = tid; j < slices_per_tile; j += COMPUTE_THREADS) {
+  for (uint32_t j = tid; j < slices_per_tile; j += THREADS) {
     uint32_t l, c;  // layer and K-slice index of slice j
     if (j < K0_PAD / KC) {
       l = 0; c = j;
@@ -327,7 +326,7 @@ __global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const Eval
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, COMPUTE_WARPS);
+      mbar_init(bar_empty + 8 * s, WARPS);
     }
     fence_mbar_init();
   }
@@ -336,102 +335,120 @@ __global__ void __launch_bounds__(COMPUTE_THREADS, 1) nfb_ffma_kernel(const Eval
     for (uint32_t j = 0; j < STAGES - 2 && j < total_slices; ++j)
       issue_slice<Cfg>(j, slices_per_tile, table, p.blob, ring, bar_full, bar_empty);
 
-  const int lm = lane >> 3, ln = lane & 7;
-  // hidden layers: warp grid WM x WN, thread tile 8 rows (two groups of 4) x 8 columns (4 + 4 twins)
+  const int lm = lane / LN, ln = lane % LN;
+  // hidden layers: warp grid WM x WN, thread tile 8 rows (two groups of 4) x TN columns (QT + QT twins)
   const int wm = warp % WM, wn = warp / WM;
-  const int h_row = (wm * 4 + lm) * 4;    // rows h_row..+3 and H/2 + h_row..+3
-  const int h_col = wn * 32 + ln * 4;     // columns h_col..+3 and NC/2 + h_col..+3
-  // last layer: all 16 warps along rows, thread tile 4 packed rows x 8 columns, WN passes
-  const int g_last = warp * 4 + lm;       // packed row group; rows 4g..4g+3; active if < 52
-  const bool last_active = (warp * 16 < M_LAST);
+  const int h_row = (wm * LM + lm) * 4;   // rows h_row..+3 and H/2 + h_row..+3
+  const int h_col = wn * 32 + ln * QT;    // columns h_col..+QT-1 and NC/2 + h_col..
+  // last layer: every warp along rows, thread tile 4 packed rows x TN columns, WN passes of 32 queries
+  const int g_last = warp * LM + lm;      // packed row group; rows 4g..4g+3
+  const bool last_active = (warp * LM * 4 < M_LAST_USED);
 
   const bool vec_ok =
       p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
                 : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
 
   uint32_t it = 0;
+  auto wait_slice = [&](uint32_t& s_out) {  // make slice `it` visible; keep the ring fed
+    const uint32_t j = it + STAGES - 2;
+    if (lane == 0 && (j & (WARPS - 1)) == uint32_t(warp) && j < total_slices)
+      issue_slice<Cfg>(j, slices_per_tile, table, p.blob, ring, bar_full, bar_empty);
+    s_out = it & (STAGES - 1);
+    mbar_wait(bar_full + 8 * s_out, (it / STAGES) & 1);
+  };
+  auto release_slice = [&](uint32_t s) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    ++it;
+  };
+
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long tile_q0 = tile * NQ;
 
-    named_bar_sync(1, COMPUTE_THREADS);  // previous tile's readers of `act`, `maha`, `re_s` are done
-    for (int col = tid; col < NC; col += COMPUTE_THREADS) {
+    named_bar_sync(1, THREADS);  // previous tile's readers of `act`, `maha`, `re_s` are done
+    for (int col = tid; col < NC; col += THREADS) {
       const bool twin = col >= NQ;
       const long long q = tile_q0 + (twin ? col - NQ : col);
       featurise_column<NC>(p, q, q < p.n, twin, col, act, maha, re_s);
     }
-    named_bar_sync(1, COMPUTE_THREADS);
+    named_bar_sync(1, THREADS);
 
     // ---------------- hidden layers ----------------
     for (int l = 0; l < L - 1; ++l) {
       const int K = (l == 0) ? K0_PAD : H;
       const float* bias = p.blob + blob_layer_offset<H>(l) + size_t(K) * H;
-      float2 acc[8][4];
+      float2 acc[8][TN / 2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float b_lo = __ldg(bias + h_row + i), b_hi = __ldg(bias + H / 2 + h_row + i);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < TN / 2; ++jj) {
           acc[i][jj] = make_float2(b_lo, b_lo);
           acc[4 + i][jj] = make_float2(b_hi, b_hi);
         }
       }
-      for (int c = 0; c < K / KC; ++c, ++it) {
-        const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
-        {
-          const uint32_t j = it + STAGES - 2;
-          if (lane == 0 && (j & (COMPUTE_WARPS - 1)) == uint32_t(warp) && j < total_slices)
-            issue_slice<Cfg>(j, slices_per_tile, table, p.blob, ring, bar_full, bar_empty);
-        }
-        mbar_wait(bar_full + 8 * s, ph);
-        ffma_slice<8, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+      for (int c = 0; c < K / KC; ++c) {
+        uint32_t s;
+        wait_slice(s);
+        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+        release_slice(s);
       }
-      named_bar_sync(1, COMPUTE_THREADS);  // everyone has finished reading this layer's input
+      named_bar_sync(1, THREADS);  // everyone has finished reading this layer's input
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = (i < 4) ? h_row + i : H / 2 + h_row + (i - 4);
-        float4 lo, hi;
-        lo.x = silu(acc[i][0].x); lo.y = silu(acc[i][0].y); lo.z = silu(acc[i][1].x); lo.w = silu(acc[i][1].y);
-        hi.x = silu(acc[i][2].x); hi.y = silu(acc[i][2].y); hi.z = silu(acc[i][3].x); hi.w = silu(acc[i][3].y);
-        *reinterpret_cast<float4*>(act + row * NC + h_col) = lo;
-        *reinterpret_cast<float4*>(act + row * NC + NC / 2 + h_col) = hi;
+#pragma unroll
+        for (int v = 0; v < TN / 8; ++v) {
+          float4 lo, hi;
+          lo.x = silu(acc[i][2 * v].x); lo.y = silu(acc[i][2 * v].y);
+          lo.z = silu(acc[i][2 * v + 1].x); lo.w = silu(acc[i][2 * v + 1].y);
+          hi.x = silu(acc[i][TN / 4 + 2 * v].x); hi.y = silu(acc[i][TN / 4 + 2 * v].y);
+          hi.z = silu(acc[i][TN / 4 + 2 * v + 1].x); hi.w = silu(acc[i][TN / 4 + 2 * v + 1].y);
+          *reinterpret_cast<float4*>(act + row * NC + h_col + 4 * v) = lo;
+          *reinterpret_cast<float4*>(act + row * NC + NC / 2 + h_col + 4 * v) = hi;
+        }
       }
-      named_bar_sync(1, COMPUTE_THREADS);
+      named_bar_sync(1, THREADS);
     }
 
     // ---------------- last layer + fused epilogue, WN passes of 32 queries ----------------
     {
       const float* bias = p.blob + blob_layer_offset<H>(L - 1) + size_t(H) * M_LAST;
       for (int pass = 0; pass < WN; ++pass) {
-        const int col = pass * 32 + ln * 4;
-        float2 acc[4][4];
+        const int col = pass * 32 + ln * QT;
+        float2 acc[4][TN / 2];
         if (last_active) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float b = __ldg(bias + g_last * 4 + i);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[i][jj] = make_float2(b, b);
+            for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(b, b);
           }
         }
-        for (int c = 0; c < H / KC; ++c, ++it) {
-          const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
-          {
-            const uint32_t j = it + STAGES - 2;
-            if (lane == 0 && (j & (COMPUTE_WARPS - 1)) == uint32_t(warp) && j < total_slices)
-              issue_slice<Cfg>(j, slices_per_tile, table, p.blob, ring, bar_full, bar_empty);
-          }
-          mbar_wait(bar_full + 8 * s, ph);
+        for (int c = 0; c < H / KC; ++c) {
+          uint32_t s;
+          wait_slice(s);
           if (last_active)
-            ffma_slice<4, M_LAST, NC, KC>(ring + s * SLOT + g_last * 4, act + (c * KC) * NC + col, acc);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            ffma_slice<4, TN, M_LAST, NC, KC>(ring + s * SLOT + g_last * 4, act + (c * KC) * NC + col, acc);
+          release_slice(s);
         }
         if (last_active) {
-          const long long q0 = tile_q0 + col;
-          const long long left = p.n - q0;
-          const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
-          decode_and_store(p, g_last, q0, nvalid, vec_ok, acc, maha + col, maha + NQ + col, re_s + col);
+#pragma unroll
+          for (int v = 0; v < TN / 8; ++v) {  // groups of 4 queries (+ their twins)
+            float yf[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              yf[i][0] = acc[i][2 * v].x; yf[i][1] = acc[i][2 * v].y;
+              yf[i][2] = acc[i][2 * v + 1].x; yf[i][3] = acc[i][2 * v + 1].y;
+              yf[i][4] = acc[i][TN / 4 + 2 * v].x; yf[i][5] = acc[i][TN / 4 + 2 * v].y;
+              yf[i][6] = acc[i][TN / 4 + 2 * v + 1].x; yf[i][7] = acc[i][TN / 4 + 2 * v + 1].y;
+            }
+            const int c4 = col + 4 * v;
+            const long long q0 = tile_q0 + c4;
+            const long long left = p.n - q0;
+            const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
+            decode_and_store(p, g_last, q0, nvalid, vec_ok, yf, maha + c4, maha + NQ + c4, re_s + c4);
+          }
         }
       }
     }
