@@ -71,33 +71,58 @@ __device__ __forceinline__ float silu(float h) {
 // eight rows stream past it (j outer, i inner) reaches 126.  Each accumulator still sees one IEEE
 // fma per k, in k order, so results are bit-identical to the scalar loop.
 // acc[i][jj] holds columns (2 jj, 2 jj + 1) of row i: jj < TN/4 -> queries, the rest -> their twins.
+template <int TM, int TN, int MP, int NC>
+__device__ __forceinline__ void load_fragments(const float* __restrict__ w, const float* __restrict__ a,
+                                               float (&wv)[TM], float2 (&av)[TN / 2]) {
+  {
+    const float4 t = *reinterpret_cast<const float4*>(w);
+    wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+  }
+  if constexpr (TM == 8) {
+    const float4 t = *reinterpret_cast<const float4*>(w + MP / 2);
+    wv[4] = t.x; wv[5] = t.y; wv[6] = t.z; wv[7] = t.w;
+  }
+#pragma unroll
+  for (int v = 0; v < TN / 8; ++v) {  // queries, then twins (NC / 2 columns further)
+    const float4 t = *reinterpret_cast<const float4*>(a + 4 * v);
+    av[2 * v] = make_float2(t.x, t.y); av[2 * v + 1] = make_float2(t.z, t.w);
+    const float4 u = *reinterpret_cast<const float4*>(a + NC / 2 + 4 * v);
+    av[TN / 4 + 2 * v] = make_float2(u.x, u.y); av[TN / 4 + 2 * v + 1] = make_float2(u.z, u.w);
+  }
+}
+
+// Two schedules of the same arithmetic.  For the 8 x 8 tile the k loop is software-pipelined by hand
+// (fragments of k + 1 are requested before the FFMA2 block of k); for the 8 x 16 tile, which already
+// uses every register, the plain loop lets ptxas place the loads (measured: DESIGN.md section 6).
 template <int TM, int TN, int MP, int NC, int KC>
 __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const float* __restrict__ a,
                                            float2 (&acc)[TM][TN / 2]) {
+  if constexpr (TN == 8) {
+    float wv[2][TM];
+    float2 av[2][TN / 2];
+    load_fragments<TM, TN, MP, NC>(w, a, wv[0], av[0]);
 #pragma unroll
-  for (int kk = 0; kk < KC; ++kk) {
-    float wv[TM];
-    float2 av[TN / 2];
-    {
-      const float4 t = *reinterpret_cast<const float4*>(w + kk * MP);
-      wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+    for (int kk = 0; kk < KC; ++kk) {
+      const int cur = kk & 1;
+      if (kk + 1 < KC) load_fragments<TM, TN, MP, NC>(w + (kk + 1) * MP, a + (kk + 1) * NC, wv[cur ^ 1], av[cur ^ 1]);
+#pragma unroll
+      for (int jj = 0; jj < TN / 2; ++jj)
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+          acc[i][jj] = __ffma2_rn(make_float2(wv[cur][i], wv[cur][i]), av[cur][jj], acc[i][jj]);
     }
-    if constexpr (TM == 8) {
-      const float4 t = *reinterpret_cast<const float4*>(w + kk * MP + MP / 2);
-      wv[4] = t.x; wv[5] = t.y; wv[6] = t.z; wv[7] = t.w;
+  } else {
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float wv[TM];
+      float2 av[TN / 2];
+      load_fragments<TM, TN, MP, NC>(w + kk * MP, a + kk * NC, wv, av);
+#pragma unroll
+      for (int jj = 0; jj < TN / 2; ++jj)
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+          acc[i][jj] = __ffma2_rn(make_float2(wv[i], wv[i]), av[jj], acc[i][jj]);
     }
-#pragma unroll
-    for (int v = 0; v < TN / 8; ++v) {  // queries, then twins (NC / 2 columns further)
-      const float4 t = *reinterpret_cast<const float4*>(a + kk * NC + 4 * v);
-      av[2 * v] = make_float2(t.x, t.y); av[2 * v + 1] = make_float2(t.z, t.w);
-      const float4 u = *reinterpret_cast<const float4*>(a + kk * NC + NC / 2 + 4 * v);
-      av[TN / 4 + 2 * v] = make_float2(u.x, u.y); av[TN / 4 + 2 * v + 1] = make_float2(u.z, u.w);
-    }
-#pragma unroll
-    for (int jj = 0; jj < TN / 2; ++jj)
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-        acc[i][jj] = __ffma2_rn(make_float2(wv[i], wv[i]), av[jj], acc[i][jj]);
   }
 }
 
