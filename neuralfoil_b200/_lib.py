@@ -15,6 +15,8 @@ N_RAW_ROWS = 23
 N_OUTPUT_ROWS = 198
 F32, F64 = 0, 1
 VARIANT_FP32_FFMA = 0
+VARIANT_TENSOR_FP16 = 1
+VARIANTS = {"fp32": VARIANT_FP32_FFMA, "tensor": VARIANT_TENSOR_FP16}
 
 OK = 0
 ERR_INVALID_ARGUMENT = -1

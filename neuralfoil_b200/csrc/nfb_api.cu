@@ -3,12 +3,14 @@
 #include "../../include/neuralfoil_b200.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <vector>
 
 #include "nfb_ffma.cuh"
+#include "nfb_tc.cuh"
 
 namespace {
 
@@ -36,6 +38,10 @@ struct Model {
   int h_pad = 0;  // 64 / 128 / 256 / 512
   int dims[NFB_MAX_LAYERS + 1] = {0};
   float* blob = nullptr;  // device
+  // tensor-core variant (512-wide models only): fp16 weight slices, fp32 biases, per-layer 1 / scale
+  __half* tc_w = nullptr;
+  float* tc_bias = nullptr;
+  float* tc_inv_scale = nullptr;
 };
 
 // Kernel tuning per padded width: <H, KC, STAGES>.
@@ -100,6 +106,60 @@ std::vector<float> pack_model(int L, const int* dims, const float* const* W, con
   return blob;
 }
 
+// Tensor-core variant: fp16 weight slices (256 features x 32 k, K-major no-swizzle core matrices: element (r, kk)
+// at (r/8)*512 + (kk/8)*128 + (r%8)*16 + (kk%8)*2 bytes) in streaming order, see nfb_tc.cuh.
+struct TcPack {
+  std::vector<__half> w;
+  std::vector<float> bias, inv_scale;
+};
+TcPack pack_model_tc(int L, const int* dims, const float* const* W, const float* const* B) {
+  using namespace nfb::tc;
+  TcPack out;
+  size_t n_slices = 0;
+  for (int l = 0; l < L; ++l) n_slices += slices_in_layer(l, L);
+  out.w.assign(n_slices * (SLICE_BYTES / 2), __float2half_rn(0.0f));
+  out.bias.assign(size_t(L) * H, 0.0f);
+  out.inv_scale.assign(L, 1.0f);
+  size_t slice = 0;
+  for (int l = 0; l < L; ++l) {
+    const int in = dims[l], outd = dims[l + 1];
+    const bool last = (l == L - 1);
+    float wmax = 0.0f;
+    for (size_t i = 0; i < size_t(in) * outd; ++i) wmax = std::max(wmax, std::fabs(W[l][i]));
+    int e = 0;  // scale = 2^e, as large as keeps |w| * scale < 16384, at most 2^12
+    if (wmax > 0.0f && std::isfinite(wmax)) e = std::min(12, std::max(-12, int(std::floor(std::log2(16384.0f / wmax)))));
+    const float scale = std::ldexp(1.0f, e);
+    out.inv_scale[l] = std::ldexp(1.0f, -e);
+    const int rows = last ? nfb::M_LAST : H;
+    for (int m = 0; m < rows; ++m) {
+      const int src = last ? nfb::pack_last_layer_row(m) : (m < outd ? m : -1);
+      if (src >= 0 && src < outd) out.bias[size_t(l) * H + m] = B[l][src];
+    }
+    const int nb_count = last ? 1 : 2;
+    const int n_ks = slices_in_layer(l, L) / nb_count;
+    for (int ks = 0; ks < n_ks; ++ks)
+      for (int nb = 0; nb < nb_count; ++nb, ++slice) {
+        __half* dst = out.w.data() + slice * (SLICE_BYTES / 2);
+        for (int r = 0; r < SLICE_N; ++r) {
+          const int m = nb * SLICE_N + r;
+          const int src = last ? (m < nfb::M_LAST ? nfb::pack_last_layer_row(m) : -1) : (m < outd ? m : -1);
+          if (src < 0 || src >= outd) continue;
+          for (int kk = 0; kk < SLICE_K; ++kk) {
+            // layer 0: k-slices are [W_hi | W_hi | W_lo] over the same 32 (25 used) inputs
+            const int k = (l == 0) ? kk : ks * SLICE_K + kk;
+            if (k >= in) continue;
+            const float ws = W[l][size_t(src) * in + k] * scale;
+            const __half hi = __float2half_rn(ws);
+            __half v = hi;
+            if (l == 0 && ks == 2) v = __float2half_rn(ws - __half2float(hi));
+            dst[(r / 8) * 256 + (kk / 8) * 64 + (r % 8) * 8 + (kk % 8)] = v;
+          }
+        }
+      }
+  }
+  return out;
+}
+
 template <class Cfg>
 int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
   static thread_local int configured_device = -1;
@@ -124,7 +184,12 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   if (!ctx->models[model_id].loaded) return fail(NFB_ERR_NOT_LOADED, "model slot %d is empty", model_id);
   if (!ctx->have_distribution)
     return fail(NFB_ERR_NOT_LOADED, "nfb_set_distribution has not been called");
-  if (variant != NFB_VARIANT_FP32_FFMA) return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
+  if (variant != NFB_VARIANT_FP32_FFMA && variant != NFB_VARIANT_TENSOR_FP16)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
+  if (variant == NFB_VARIANT_TENSOR_FP16 && !ctx->models[model_id].tc_w)
+    return fail(NFB_ERR_UNSUPPORTED_MODEL,
+                "the tensor-core variant exists for 512-wide models with at most %d layers only; model slot %d is not one",
+                nfb::tc::MAX_TC_LAYERS, model_id);
   if (n < 0) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld is negative", (long long)n);
   if ((in_dtype != NFB_F32 && in_dtype != NFB_F64) || (out_dtype != NFB_F32 && out_dtype != NFB_F64))
     return fail(NFB_ERR_INVALID_ARGUMENT, "dtype must be NFB_F32 or NFB_F64");
@@ -138,7 +203,7 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   return NFB_OK;
 }
 
-int eval_device_impl(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
                      const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
                      cudaStream_t stream) {
   const Model& m = ctx->models[model_id];
@@ -154,6 +219,25 @@ int eval_device_impl(nfb_context* ctx, int model_id, int64_t n, const void* cons
   p.n_layers = m.n_layers;
   p.in_f64 = (in_dtype == NFB_F64);
   p.out_f64 = (out_dtype == NFB_F64);
+  if (variant == NFB_VARIANT_TENSOR_FP16) {
+    static thread_local int tc_configured_device = -1;
+    if (tc_configured_device != ctx->device) {
+      NFB_CUDA(cudaFuncSetAttribute(nfb::tc::nfb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(nfb::tc::SMEM_BYTES)));
+      tc_configured_device = ctx->device;
+    }
+    nfb::tc::TcParams tp;
+    tp.ev = p;
+    tp.wblob = m.tc_w;
+    tp.bias = m.tc_bias;
+    tp.inv_scale = m.tc_inv_scale;
+    const long long tiles = (n + nfb::tc::NQT - 1) / nfb::tc::NQT;
+    const int grid = int(std::min<long long>(tiles, ctx->sm_count));
+    nfb::tc::nfb_tc_kernel<<<grid, nfb::tc::THREADS, nfb::tc::SMEM_BYTES, stream>>>(tp);
+    NFB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return NFB_OK;
+  }
   switch (m.h_pad) {
     case 64: return launch_ffma<Cfg64>(ctx, p, stream);
     case 128: return launch_ffma<Cfg128>(ctx, p, stream);
@@ -182,7 +266,7 @@ int ensure(void** ptr, size_t* have, size_t need, bool pinned_host) {
 
 extern "C" {
 
-const char* nfb_version(void) { return "neuralfoil_b200 0.1 (sm_100a; fp32 FFMA fused evaluator)"; }
+const char* nfb_version(void) { return "neuralfoil_b200 0.2 (sm_100a; fused evaluator: fp32 FFMA2 + tcgen05 fp16-operand variants)"; }
 
 const char* nfb_last_error(void) { return g_err; }
 
@@ -221,8 +305,12 @@ int nfb_create(int device, nfb_context** out_ctx) {
 void nfb_destroy(nfb_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  for (auto& m : ctx->models)
+  for (auto& m : ctx->models) {
     if (m.blob) cudaFree(m.blob);
+    if (m.tc_w) cudaFree(m.tc_w);
+    if (m.tc_bias) cudaFree(m.tc_bias);
+    if (m.tc_inv_scale) cudaFree(m.tc_inv_scale);
+  }
   for (auto& s : ctx->slots) {
     if (s.stream) {
       cudaStreamSynchronize(s.stream);
@@ -290,10 +378,22 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
   if (m.blob) {
     NFB_CUDA(cudaDeviceSynchronize());
     NFB_CUDA(cudaFree(m.blob));
+    if (m.tc_w) NFB_CUDA(cudaFree(m.tc_w));
+    if (m.tc_bias) NFB_CUDA(cudaFree(m.tc_bias));
+    if (m.tc_inv_scale) NFB_CUDA(cudaFree(m.tc_inv_scale));
     m = Model();
   }
   NFB_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
   NFB_CUDA(cudaMemcpy(m.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (h_pad == 512 && n_layers <= nfb::tc::MAX_TC_LAYERS) {
+    const TcPack tcp = pack_model_tc(n_layers, dims, weights, biases);
+    NFB_CUDA(cudaMalloc(&m.tc_w, tcp.w.size() * sizeof(__half)));
+    NFB_CUDA(cudaMalloc(&m.tc_bias, tcp.bias.size() * sizeof(float)));
+    NFB_CUDA(cudaMalloc(&m.tc_inv_scale, tcp.inv_scale.size() * sizeof(float)));
+    NFB_CUDA(cudaMemcpy(m.tc_w, tcp.w.data(), tcp.w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    NFB_CUDA(cudaMemcpy(m.tc_bias, tcp.bias.data(), tcp.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    NFB_CUDA(cudaMemcpy(m.tc_inv_scale, tcp.inv_scale.data(), tcp.inv_scale.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   m.loaded = true;
   m.n_layers = n_layers;
   m.h_pad = h_pad;
@@ -307,7 +407,7 @@ int nfb_eval_device(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   int rc = check_eval_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype);
   if (rc != NFB_OK || n == 0) return rc;
   NFB_CUDA(cudaSetDevice(ctx->device));
-  return eval_device_impl(ctx, model_id, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype,
+  return eval_device_impl(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype,
                           static_cast<cudaStream_t>(stream));
 }
 
@@ -372,7 +472,7 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
         d_rows[r] = dst;
       }
     }
-    rc = eval_device_impl(ctx, model_id, cn, d_rows, d_strides, in_dtype, s.d_out, chunk, out_dtype, s.stream);
+    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype, s.d_out, chunk, out_dtype, s.stream);
     if (rc != NFB_OK) return rc;
     char* out_c = static_cast<char*>(out) + size_t(c0) * osz;
     if (small) {

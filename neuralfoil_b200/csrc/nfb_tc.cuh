@@ -1,0 +1,384 @@
+// Tensor-core (tcgen05) variant of the fused evaluator, for the 512-wide model (xxxlarge).
+//
+// Same per-tile pipeline as nfb_ffma.cuh -- featurise + Mahalanobis in fp64, every layer on chip, fused
+// un-flip / average / decode epilogue -- but each layer is a tcgen05.mma (kind::f16) GEMM:
+//
+//   D[128 batch rows][features] (fp32, TMEM)  +=  A[128 batch rows][K] (fp16, smem)  x  B[features][K] (fp16, smem)
+//
+//   * A = the activation tile: 64 queries + their 64 flipped twins, K-major, SWIZZLE_128B atoms (8 rows x 128 B),
+//     written by the epilogue warps themselves (thread = batch row, 16-byte conflict-free stores).
+//   * B = weights, fp16, pre-packed on the host as K-major no-swizzle core matrices, 256 output features x 32 k
+//     per 16 KB slice, streamed L2 -> smem by a producer thread through a 4-deep TMA ring (cp.async.bulk + mbarrier).
+//   * D = 128 lanes x 512 columns = the whole tensor memory; one elected thread issues the MMAs (N = 256, K = 16).
+//
+// Why this orientation and this precision (measured with scripts/umma_probe.cu on B200):
+// a tcgen05.mma with M = 128 costs ~111-124 cycles however small N is, so N must be large (256 features), which
+// puts the batch on the TMEM lanes; 128 rows x 512 features of activations only fit in shared memory at 2 bytes
+// per element.  fp16 (round to nearest, saturating) has TF32's 10-bit mantissa; the first layer, whose inputs are
+// the physical features, is made fp32-exact by K-concatenation: [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo].
+// Accuracy is therefore "TF32 class" (latent error median 3e-4, CL p99.9 4e-3); the fp32 FFMA kernel stays the
+// correctness reference.  Weights carry a per-layer power-of-two scale (keeps small weights out of fp16
+// subnormals), undone exactly in the epilogue.
+//
+// Roles (320 threads): warp 0 lane 0 = TMA producer; warp 1 = TMEM allocator, lane 0 = MMA issuer; warps 2..9 =
+// epilogue (thread = batch row 32 * (warp % 4) + lane, feature half (warp - 2) / 4).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "nfb_ffma.cuh"  // featurise maths, decode_and_store, PTX helpers
+
+namespace nfb {
+namespace tc {
+
+constexpr int H = 512;                 // hidden width this variant is built for
+constexpr int NT = 128;                // batch rows per tile (MMA M)
+constexpr int NQT = 64;                // queries per tile
+constexpr int K0 = 96;                 // first layer's K after [hi | lo | hi] concatenation (3 x 32)
+constexpr int SLICE_K = 32;            // k per streamed weight slice
+constexpr int SLICE_N = 256;           // output features per slice (MMA N)
+constexpr uint32_t SLICE_BYTES = SLICE_N * SLICE_K * 2;   // 16 KB
+constexpr int STAGES = 4;
+constexpr int ATOM_K = 64;             // fp16 per 128-byte swizzle row
+constexpr uint32_t ATOM_BYTES = NT * 128;                  // 16 KB: 16 row groups x 1024 B
+constexpr uint32_t ACT_BYTES = (H / ATOM_K) * ATOM_BYTES;  // 128 KB
+constexpr int THREADS = 320;
+constexpr int EPI_WARPS = 8, EPI_THREADS = 256;
+constexpr int MAX_BIAS = NFB_MAX_LAYERS_K * H;
+
+// shared-memory map (bytes from a 1024-aligned base)
+constexpr uint32_t OFF_ACT = 0;
+constexpr uint32_t OFF_RING = OFF_ACT + ACT_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_RING + STAGES * SLICE_BYTES;     // fp32 [L][512] (+ scales [L])
+constexpr uint32_t BIAS_FLOATS = 7 * H + 16;                       // up to 7 layers (the shipped xxxlarge) + scales
+constexpr uint32_t OFF_MAHA = OFF_BIAS + BIAS_FLOATS * 4;          // fp32 [128]
+constexpr uint32_t OFF_RE = OFF_MAHA + NT * 4;                     // fp32 [64]
+constexpr uint32_t OFF_BARS = OFF_RE + NQT * 4;                    // mbarriers
+constexpr uint32_t OFF_TMEM = OFF_BARS + 16 * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
+constexpr int MAX_TC_LAYERS = 7;
+
+struct TcParams {
+  EvalParams ev;            // inputs / outputs / n / n_layers (blob unused)
+  const __half* wblob;      // slices in streaming order, 16 KB each
+  const float* bias;        // [L][512] fp32, last layer in packed row order (224 used)
+  const float* inv_scale;   // [L]
+};
+
+__host__ __device__ constexpr int slices_in_layer(int l, int L) {
+  return l == 0 ? (K0 / SLICE_K) * 2 : (l == L - 1 ? (H / SLICE_K) : (H / SLICE_K) * 2);
+}
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// two fp32 -> packed fp16x2 (lo = first argument), round to nearest, saturate to +-65504
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// SiLU for the fp16-operand path: x * sigmoid(x) = h + h * tanh(h), h = x / 2; one MUFU (tanh.approx, rel. error 2^-11,
+// the precision the result is about to be rounded to anyway)
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// byte offset of the 16-byte chunk holding k..k+7 of batch row n in the activation tile (SWIZZLE_128B K-major atoms)
+__device__ __forceinline__ uint32_t act_chunk_offset(int n, int k) {
+  const int atom = k >> 6, chunk = (k & 63) >> 3;
+  return uint32_t(atom) * ATOM_BYTES + uint32_t(n >> 3) * 1024 + uint32_t(n & 7) * 128 + uint32_t((chunk ^ (n & 7)) << 4);
+}
+
+// ---- featurise one batch row: fp64 features + Mahalanobis (as nfb::featurise_column), then the first layer's
+//      [x_hi | x_lo | x_hi] fp16 row ----------------------------------------------------------------------------
+__device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, bool valid, bool twin, int n,
+                                              unsigned char* act, float* maha, float* re_s) {
+  double r[N_RAW];
+  if (valid) {
+    if (p.in_f64) {
+#pragma unroll
+      for (int i = 0; i < N_RAW; ++i) r[i] = __ldg(static_cast<const double*>(p.in[i]) + q * p.in_stride[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N_RAW; ++i)
+        r[i] = static_cast<double>(__ldg(static_cast<const float*>(p.in[i]) + q * p.in_stride[i]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N_RAW; ++i) r[i] = 0.0;
+    r[19] = 1.0e6; r[20] = 9.0; r[21] = 1.0; r[22] = 1.0;
+  }
+  double x[N_IN];
+#pragma unroll
+  for (int i = 0; i < 17; ++i) x[i] = r[i];
+  x[17] = r[17] * 50.0;
+  constexpr double kPi = 3.141592653589793238462643383279502884;
+  x[18] = sin((2.0 * r[18]) * kPi / 180.0);
+  const double c = cos(r[18] * kPi / 180.0);
+  x[19] = c;
+  x[20] = __dsub_rn(1.0, __dmul_rn(c, c));
+  x[21] = (log(r[19]) - 12.5) / 3.5;
+  x[22] = (r[20] - 9.0) / 4.5;
+  x[23] = r[21];
+  x[24] = r[22];
+  if (twin) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double u = x[i], l = x[8 + i];
+      x[i] = -l;
+      x[8 + i] = -u;
+    }
+    x[16] = -x[16];
+    x[18] = -x[18];
+    const double t = x[23];
+    x[23] = x[24];
+    x[24] = t;
+  }
+  double d2 = 0.0;
+  {
+    double d[N_IN];
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) d[i] = x[i] - c_mean[i];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < N_IN; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int j = i; j < N_IN; ++j) t = fma(c_quad[idx++], d[j], t);
+      d2 = fma(d[i], t, d2);
+    }
+  }
+  maha[n] = static_cast<float>(d2 / (2.0 * N_IN));
+  if (!twin) re_s[n] = static_cast<float>(r[19]);
+
+  // hi / lo split in fp16 (22 significant bits together), 32 values each (25 used)
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float f0 = (2 * i < N_IN) ? static_cast<float>(x[2 * i]) : 0.0f;
+    float f1 = (2 * i + 1 < N_IN) ? static_cast<float>(x[2 * i + 1]) : 0.0f;
+    const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+    hi[i] = uint32_t(__half_as_ushort(h0)) | (uint32_t(__half_as_ushort(h1)) << 16);
+    const float l0 = (2 * i < N_IN) ? static_cast<float>(x[2 * i] - double(__half2float(h0))) : 0.0f;
+    const float l1 = (2 * i + 1 < N_IN) ? static_cast<float>(x[2 * i + 1] - double(__half2float(h1))) : 0.0f;
+    lo[i] = pack_f16x2(l0, l1);
+  }
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {  // k = 0..31 hi, 32..63 lo, 64..95 hi
+    const uint4 vh = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);
+    const uint4 vl = make_uint4(lo[4 * c8], lo[4 * c8 + 1], lo[4 * c8 + 2], lo[4 * c8 + 3]);
+    *reinterpret_cast<uint4*>(act + act_chunk_offset(n, 8 * c8)) = vh;
+    *reinterpret_cast<uint4*>(act + act_chunk_offset(n, 32 + 8 * c8)) = vl;
+    *reinterpret_cast<uint4*>(act + act_chunk_offset(n, 64 + 8 * c8)) = vh;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
+  const EvalParams& p = tp.ev;
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char* const smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
+  unsigned char* const act = smem + OFF_ACT;
+  unsigned char* const ring = smem + OFF_RING;
+  float* const bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+  float* const maha = reinterpret_cast<float*>(smem + OFF_MAHA);
+  float* const re_s = reinterpret_cast<float*>(smem + OFF_RE);
+  const uint32_t bar_full = smem_u32(smem + OFF_BARS), bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_act = bar_empty + 8 * STAGES;  // epilogue -> MMA: layer input is in smem, TMEM is drained
+  const uint32_t bar_d = bar_act + 8;               // MMA -> epilogue: the layer's accumulators are complete
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = p.n_layers;
+  const long long n_tiles = (p.n + NQT - 1) / NQT;
+  const uint32_t my_tiles = uint32_t((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  int slices_per_tile = 0;
+  for (int l = 0; l < L; ++l) slices_per_tile += slices_in_layer(l, L);
+
+  for (int i = tid; i < L * H; i += THREADS) bias_s[i] = tp.bias[i];
+  if (tid < L) bias_s[7 * H + tid] = tp.inv_scale[tid];
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_act, EPI_WARPS);
+    mbar_init(bar_d, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ weight producer ============================
+    if (lane == 0) {
+      const uint32_t total = my_tiles * uint32_t(slices_per_tile);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(tp.wblob);
+      for (uint32_t it = 0, j = 0; it < total; ++it) {
+        const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_arrive_expect_tx(bar_full + 8 * s, SLICE_BYTES);
+        bulk_copy_g2s(smem_u32(ring + s * SLICE_BYTES), src + size_t(j) * SLICE_BYTES, SLICE_BYTES, bar_full + 8 * s);
+        if (++j == uint32_t(slices_per_tile)) j = 0;
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (uint32_t(SLICE_N >> 3) << 17) | (uint32_t(NT >> 4) << 24);  // f16 x f16 -> f32
+      uint32_t it = 0, act_phase = 0;
+      for (uint32_t t = 0; t < my_tiles; ++t)
+        for (int l = 0; l < L; ++l) {
+          mbar_wait(bar_act, act_phase);
+          act_phase ^= 1;
+          tc_fence_after();
+          const int n_sl = slices_in_layer(l, L);
+          const int nb_count = (l == L - 1) ? 1 : 2;
+          for (int sl = 0; sl < n_sl; ++sl, ++it) {
+            const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
+            const int ks = sl / nb_count, nb = sl % nb_count;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(act) + uint32_t(ks >> 1) * ATOM_BYTES + uint32_t(ks & 1) * 64;
+            const uint32_t b_base = smem_u32(ring + s * SLICE_BYTES);
+#pragma unroll
+            for (int j = 0; j < SLICE_K / 16; ++j)
+              umma_f16(tmem + nb * SLICE_N, smem_desc(a_base + j * 32, 16, 1024, 2), smem_desc(b_base + j * 256, 128, 512, 0),
+                       idesc, (ks | j) != 0);
+            umma_commit(bar_empty + 8 * s);  // slot is free once these MMAs have read it
+          }
+          umma_commit(bar_d);
+        }
+    }
+  } else {
+    // ============================ epilogue warps ============================
+    const int e = warp - 2, q = warp & 3, half = e >> 2;
+    const int n = 32 * q + lane;             // batch row == TMEM lane
+    const int et = (e << 5) | lane;          // 0..255
+    const uint32_t t_lane = tmem + (uint32_t(32 * q) << 16);
+    const bool vec_ok =
+        p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
+                  : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    uint32_t d_phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long tile_q0 = tile * NQT;
+      if (half == 0) {  // 128 threads featurise the 128 rows (row n: query n, row 64 + n: its twin)
+        const bool twin = n >= NQT;
+        const long long qi = tile_q0 + (twin ? n - NQT : n);
+        featurise_row(p, qi, qi < p.n, twin, n, act, maha, re_s);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_act);
+
+      for (int l = 0; l < L - 1; ++l) {
+        mbar_wait(bar_d, d_phase);
+        d_phase ^= 1;
+        tc_fence_after();
+        const float inv_s = bias_s[7 * H + l];
+        const float* b = bias_s + l * H + half * 256;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + uint32_t(half * 256 + c0), v);
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = silu_fast(fmaf(__uint_as_float(v[2 * i]), inv_s, b[c0 + 2 * i]));
+            const float a1 = silu_fast(fmaf(__uint_as_float(v[2 * i + 1]), inv_s, b[c0 + 2 * i + 1]));
+            w[i] = pack_f16x2(a0, a1);
+          }
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            *reinterpret_cast<uint4*>(act + act_chunk_offset(n, half * 256 + c0 + 8 * c8)) =
+                make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
+        }
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_act);
+      }
+
+      // ---- last layer: latents -> fp32 staging [224 packed rows][128 batch] in the (now idle) activation tile ----
+      mbar_wait(bar_d, d_phase);
+      d_phase ^= 1;
+      tc_fence_after();
+      {
+        float* stage = reinterpret_cast<float*>(act);
+        const float inv_s = bias_s[7 * H + (L - 1)];
+        const float* b = bias_s + (L - 1) * H;
+        // feature ranges: half 0 -> [0, 128), half 1 -> [128, 224)
+        const int f_begin = half * 128, f_end = half ? M_LAST : 128;
+#pragma unroll 1
+        for (int c0 = f_begin; c0 < f_end; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + uint32_t(c0), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stage[(c0 + i) * NT + n] = fmaf(__uint_as_float(v[i]), inv_s, b[c0 + i]);
+        }
+        tc_fence_before();
+        named_bar_sync(1, EPI_THREADS);
+        for (int item = et; item < (M_LAST / 4) * (NQT / 4); item += EPI_THREADS) {
+          const int g = item / (NQT / 4), qb = (item % (NQT / 4)) * 4;
+          float acc[4][8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 y = *reinterpret_cast<const float4*>(stage + (4 * g + i) * NT + qb);
+            const float4 f = *reinterpret_cast<const float4*>(stage + (4 * g + i) * NT + NQT + qb);
+            acc[i][0] = y.x; acc[i][1] = y.y; acc[i][2] = y.z; acc[i][3] = y.w;
+            acc[i][4] = f.x; acc[i][5] = f.y; acc[i][6] = f.z; acc[i][7] = f.w;
+          }
+          const long long q0 = tile_q0 + qb;
+          const long long left = p.n - q0;
+          const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
+          decode_and_store(p, g, q0, nvalid, vec_ok, acc, maha + qb, maha + NQT + qb, re_s + qb);
+        }
+        named_bar_sync(1, EPI_THREADS);  // staging (and maha / re) fully consumed before the next tile overwrites them
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace tc
+}  // namespace nfb

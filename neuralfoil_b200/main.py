@@ -177,6 +177,14 @@ class Evaluator:
         self._model_ids[name] = model_id
         self.model_dims[name] = dims
 
+    @staticmethod
+    def _variant(variant: str) -> int:
+        """"fp32" = FFMA kernel (reference accuracy); "tensor" = tcgen05 fp16-operand kernel (512-wide models only)."""
+        try:
+            return _lib.VARIANTS[variant]
+        except KeyError:
+            raise ValueError(f"Invalid {variant=}. Must be one of {set(_lib.VARIANTS)}.") from None
+
     def _model_id(self, model_size: str) -> int:
         if model_size not in self._model_ids:
             raise ValueError(f"Invalid {model_size=}. Must be one of {self.allowable_model_sizes}.")
@@ -184,16 +192,18 @@ class Evaluator:
 
     # -- the drop-in call --------------------------------------------------------------------------
     def get_aero_from_kulfan_parameters(
-        self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"
+        self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge",
+        variant: str = "fp32",
     ) -> dict[str, np.ndarray]:
         model_id = self._model_id(model_size)  # main.py:154-157
         rows, n_cases = prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower)
-        block = self._evaluate_host_rows(model_id, rows, n_cases, np.float64)
+        block = self._evaluate_host_rows(model_id, rows, n_cases, np.float64, variant=variant)
         # Row views of one (198, ld) block: each value is a contiguous (N,) float64 array, as in the
         # reference, where the keys are views of a shared Fortran-ordered block.
         return {key: block[i, :n_cases] for i, key in enumerate(_OUTPUT_KEYS)}
 
-    def evaluate_host(self, raw: np.ndarray, model_size: str = "xlarge", out_dtype=np.float32, chunk: int = 0):
+    def evaluate_host(self, raw: np.ndarray, model_size: str = "xlarge", out_dtype=np.float32, chunk: int = 0,
+                      variant: str = "fp32"):
         """raw (23, N) float32/float64 host array -> (198, N) host array (rows are contiguous)."""
         raw = np.asarray(raw)
         if raw.ndim != 2 or raw.shape[0] != _lib.N_RAW_ROWS:
@@ -201,10 +211,11 @@ class Evaluator:
         if raw.dtype not in (np.float32, np.float64):
             raw = raw.astype(np.float64)
         rows = [np.ascontiguousarray(raw[i]) for i in range(_lib.N_RAW_ROWS)]
-        block = self._evaluate_host_rows(self._model_id(model_size), rows, raw.shape[1], out_dtype, chunk)
+        block = self._evaluate_host_rows(self._model_id(model_size), rows, raw.shape[1], out_dtype, chunk, variant)
         return block[:, : raw.shape[1]]
 
-    def evaluate_host_into(self, raw: np.ndarray, model_size: str, out: np.ndarray, chunk: int = 0) -> np.ndarray:
+    def evaluate_host_into(self, raw: np.ndarray, model_size: str, out: np.ndarray, chunk: int = 0,
+                           variant: str = "fp32") -> np.ndarray:
         """
         Like `evaluate_host`, but writes into a caller-owned (ideally pinned) block `out` of shape
         (198, ld >= N) with contiguous rows, and reads `raw` (23, N) in place: no host allocation
@@ -222,7 +233,7 @@ class Evaluator:
         strides = (C.c_int64 * _lib.N_RAW_ROWS)(*([1] * _lib.N_RAW_ROWS))
         _lib.check(
             self._lib.nfb_eval_host(
-                self._ctx, self._model_id(model_size), _lib.VARIANT_FP32_FFMA, n, ptrs, strides,
+                self._ctx, self._model_id(model_size), self._variant(variant), n, ptrs, strides,
                 _lib.F64 if raw.dtype == np.float64 else _lib.F32,
                 out.ctypes.data_as(C.c_void_p), out.strides[0] // out.itemsize,
                 _lib.F64 if out.dtype == np.float64 else _lib.F32, chunk,
@@ -230,7 +241,7 @@ class Evaluator:
         )
         return out[:, :n]
 
-    def _evaluate_host_rows(self, model_id: int, rows, n: int, out_dtype, chunk: int = 0):
+    def _evaluate_host_rows(self, model_id: int, rows, n: int, out_dtype, chunk: int = 0, variant: str = "fp32"):
         in_dtype = rows[0].dtype
         if any(r.dtype != in_dtype for r in rows):
             rows = [r.astype(np.float64) for r in rows]
@@ -241,7 +252,7 @@ class Evaluator:
         strides = (C.c_int64 * _lib.N_RAW_ROWS)(*[0 if r.size == 1 and n > 1 else 1 for r in rows])
         _lib.check(
             self._lib.nfb_eval_host(
-                self._ctx, model_id, _lib.VARIANT_FP32_FFMA, n, ptrs, strides,
+                self._ctx, model_id, self._variant(variant), n, ptrs, strides,
                 _lib.F64 if in_dtype == np.float64 else _lib.F32,
                 block.ctypes.data_as(C.c_void_p), ld,
                 _lib.F64 if np.dtype(out_dtype) == np.float64 else _lib.F32, chunk,
@@ -250,7 +261,7 @@ class Evaluator:
         return block
 
     # -- device-resident call ----------------------------------------------------------------------
-    def evaluate_device(self, raw, model_size: str = "xlarge", out=None, out_dtype=None):
+    def evaluate_device(self, raw, model_size: str = "xlarge", out=None, out_dtype=None, variant: str = "fp32"):
         """
         raw: torch CUDA tensor (23, N), float32 or float64, rows contiguous -- or a list of 23 1-D CUDA
         tensors of length N or 1 (length-1 rows are broadcast).  Returns a (198, N) CUDA tensor view
@@ -295,7 +306,7 @@ class Evaluator:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(
             self._lib.nfb_eval_device(
-                self._ctx, model_id, _lib.VARIANT_FP32_FFMA, n, ptrs, c_strides,
+                self._ctx, model_id, self._variant(variant), n, ptrs, c_strides,
                 _lib.F64 if dtype == torch.float64 else _lib.F32,
                 C.c_void_p(out.data_ptr()), ld, _lib.F64 if out.dtype == torch.float64 else _lib.F32,
                 C.c_void_p(stream),
