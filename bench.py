@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--model-size", default="xxxlarge")
+    ap.add_argument("--variant", choices=("fp32", "tensor"), default="fp32",
+                    help="kernel behind value/e2e: fp32 FFMA (reference accuracy) or tcgen05 fp16-operand (xxxlarge only)")
+    ap.add_argument("--no-tensor-extra", action="store_true", help="skip the extra tensor-variant measurement")
     ap.add_argument("--queries-per-gpu", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -75,6 +78,7 @@ def workload_config(args, weights_note: str) -> dict:
     return {
         "workload": "BASELINE.json configs[2]: random Kulfan airfoils over the training distribution, full BL outputs",
         "model_size": args.model_size,
+        "variant": getattr(args, "variant", "fp32"),
         "queries_per_gpu": args.queries_per_gpu,
         "weights": weights_note if args.model_size == "xxxlarge" else "shipped .npz",
         "layout": "SoA fp32: 23 input rows, 198 output rows",
@@ -234,8 +238,9 @@ def main():
     fp32_peak = ev.measure_fp32_peak_tflops(5) if rank == 0 else 0.0
 
     # ---- device-resident throughput ----
+    variant = args.variant
     for _ in range(max(args.warmup, 3)):
-        ev.evaluate_device(raw_dev, size, out=out_dev)
+        ev.evaluate_device(raw_dev, size, out=out_dev, variant=variant)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -248,7 +253,7 @@ def main():
     t_begin.record()
     for i in range(args.steps):
         starts[i].record()
-        ev.evaluate_device(raw_dev, size, out=out_dev)
+        ev.evaluate_device(raw_dev, size, out=out_dev, variant=variant)
         stops[i].record()
     t_end.record()
     barrier()
@@ -265,12 +270,12 @@ def main():
     if not args.no_e2e:
         out_host = torch.empty((198, ld), dtype=torch.float32).pin_memory()
         for _ in range(1):
-            ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy())
+            ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant=variant)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
         for _ in range(e2e_steps):
-            ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy())
+            ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant=variant)
             _ = float(out_host[1, 0])  # read a result on the host
         torch.cuda.synchronize()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
@@ -280,6 +285,21 @@ def main():
         host_check = float(out_host[:6, :1000].double().sum().item())
         assert abs(host_check - checksum) <= 1e-6 * max(1.0, abs(checksum)), (host_check, checksum)
 
+    # ---- the other variant, briefly (xxxlarge only): reported beside the headline, never mixed into it ----
+    tensor_extra = None
+    if size == "xxxlarge" and variant == "fp32" and not args.no_tensor_extra:
+        for _ in range(3):
+            ev.evaluate_device(raw_dev, size, out=out_dev, variant="tensor")
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(args.steps):
+            ev.evaluate_device(raw_dev, size, out=out_dev, variant="tensor")
+        t1e.record()
+        barrier()
+        t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
+        tensor_extra = {"ms_per_step": t_ms, "value": world * n / (t_ms * 1e-3)}
+
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -288,6 +308,16 @@ def main():
         k_ms = float(np.mean(kernel_ms))
         achieved_tflops = FLOP_PER_QUERY[size] * n / (k_ms * 1e-3) / 1e12
         achieved_gbs = BYTES_PER_QUERY * n / (k_ms * 1e-3) / 1e9
+        bf16_peak, bf16_src = 1590.0, "fallback (B200_PROFILING.md)"
+        if peaks_path.exists():
+            bf16_peak, bf16_src = float(json.loads(peaks_path.read_text())["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
+        if tensor_extra is not None:
+            tf = FLOP_PER_QUERY[size] * n / (tensor_extra["ms_per_step"] * 1e-3) / 1e12 / world
+            tensor_extra.update({
+                "unit": UNIT, "kernel": "nfb_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM)",
+                "accuracy": "TF32-class: latent error median 3e-4; see DESIGN.md section 5 and tests/parity.py (tensor tolerance)",
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
+                             "peak_source": bf16_src}})
         roofline = {
             "bound": "fp32",
             "kernel": "nfb_ffma_kernel",
@@ -301,6 +331,10 @@ def main():
                     "peak_source": hbm_src},
             "traffic": None,
         }
+        if variant == "tensor":
+            roofline.update({"bound": "tensor", "kernel": "nfb_tc_kernel", "peak": bf16_peak, "peak_source": bf16_src,
+                             "frac": achieved_tflops / bf16_peak})
+            roofline.pop("frac_of_nominal_74.4", None)
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample or auto_cpu_sample(size)
@@ -311,10 +345,10 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, weights_note),
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if variant == "fp32" else "f16 operands / f32 accumulate",
+            "data": "synthetic", "config": workload_config(args, weights_note),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "tensor_variant": tensor_extra,
             "checksum_first_1000": checksum,
         }
         print(json.dumps(line), flush=True)

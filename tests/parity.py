@@ -45,8 +45,19 @@ def _tau(out: np.ndarray, Re: np.ndarray) -> np.ndarray:
     return out[ROW_THETA] * np.abs(out[ROW_UE]) * Re[None, :]
 
 
-def error_report(got: np.ndarray, want: np.ndarray, Re: np.ndarray) -> dict:
+# The tensor-core variant (tcgen05, fp16 operands = TF32's 10-bit mantissa, fp32 accumulation, first layer exact):
+# BASELINE.json allows "a stated looser bound on CL/CD/CM and the BL arrays for the tensor-core path".  Stated here:
+# the same criterion with a latent-space atol of 3e-2 (emulation on the trained xlarge / xxlarge networks gives
+# latent errors of median 3e-4, p99.9 1.4e-2; measured on B200 with the synthetic xxxlarge: max 9e-3), i.e.
+# |dCL| <= 1.5e-2, CD within 6 %, |dCM| <= 1.5e-3 in the worst case, plus the distribution checks
+# median relative error <= 2e-3 and p99.9 |dCL| <= 5e-3, |dCM| <= 1e-3, CD within 2 %.
+# (For scale: the networks' own mean error against XFoil is CL 0.012, ln CD 0.020, CM 0.002 -- reference README.md:127.)
+TENSOR_LATENT_ATOL = 3e-2
+
+
+def error_report(got: np.ndarray, want: np.ndarray, Re: np.ndarray, latent_atol: float = LATENT_ATOL) -> dict:
     """Element-wise error statistics of a (198, N) block against the oracle's."""
+    LATENT_ATOL = latent_atol  # noqa: N806 (shadows the module constant on purpose)
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     err = np.abs(got - want)
@@ -79,11 +90,22 @@ def error_report(got: np.ndarray, want: np.ndarray, Re: np.ndarray) -> dict:
         "median_rel": float(np.median(rel[well_posed])),
         "frac_rel_le_1e-5": float((rel[well_posed] <= 1e-5).mean()),
         "max_abs_scalars": [float(np.nanmax(np.abs(got[i] - want[i]))) for i in range(6)],
+        "p999_abs_CL": float(np.nanquantile(np.abs(got[1] - want[1]), 0.999)),
+        "p999_abs_CM": float(np.nanquantile(np.abs(got[3] - want[3]), 0.999)),
+        "p999_rel_CD": float(np.nanquantile(np.abs(got[2] - want[2]) / np.maximum(np.abs(want[2]), 1e-300), 0.999)),
     }
 
 
-def assert_parity(got, want, Re, check_distribution: bool = True, label: str = "") -> dict:
-    rep = error_report(got, want, np.broadcast_to(np.asarray(Re, dtype=np.float64), (np.shape(want)[1],)))
+def assert_parity(got, want, Re, check_distribution: bool = True, label: str = "", variant: str = "fp32") -> dict:
+    re = np.broadcast_to(np.asarray(Re, dtype=np.float64), (np.shape(want)[1],))
+    if variant == "tensor":
+        rep = error_report(got, want, re, latent_atol=TENSOR_LATENT_ATOL)
+        assert rep["n_bad"] == 0, f"{label}: {rep}"
+        if check_distribution:
+            assert rep["median_rel"] <= 2e-3, f"{label}: {rep}"
+            assert rep["p999_abs_CL"] <= 5e-3 and rep["p999_abs_CM"] <= 1e-3 and rep["p999_rel_CD"] <= 2e-2, f"{label}: {rep}"
+        return rep
+    rep = error_report(got, want, re)
     assert rep["n_bad"] == 0, f"{label}: {rep}"
     if check_distribution:
         assert rep["median_rel"] <= 2e-6, f"{label}: {rep}"
