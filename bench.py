@@ -299,6 +299,17 @@ def main():
         barrier()
         t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
         tensor_extra = {"ms_per_step": t_ms, "value": world * n / (t_ms * 1e-3)}
+        if not args.no_e2e:
+            ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant="tensor")
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant="tensor")
+                _ = float(out_host[1, 0])
+            torch.cuda.synchronize()
+            te = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+            tensor_extra["e2e"] = {"value": world * n / te, "unit": UNIT, "ms_per_step": te * 1e3,
+                                   "note": "same nfb_eval_host path; bound by the PCIe device->host copy of 792 B/query"}
 
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
@@ -312,7 +323,7 @@ def main():
         if peaks_path.exists():
             bf16_peak, bf16_src = float(json.loads(peaks_path.read_text())["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
         if tensor_extra is not None:
-            tf = FLOP_PER_QUERY[size] * n / (tensor_extra["ms_per_step"] * 1e-3) / 1e12 / world
+            tf = FLOP_PER_QUERY[size] * n / (tensor_extra["ms_per_step"] * 1e-3) / 1e12  # per GPU: n is per rank
             tensor_extra.update({
                 "unit": UNIT, "kernel": "nfb_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM)",
                 "accuracy": "TF32-class: latent error median 3e-4; see DESIGN.md section 5 and tests/parity.py (tensor tolerance)",

@@ -111,6 +111,10 @@ int nfb_host_free(void* ptr);
 /* Number of kernel launches this context has enqueued so far (bench.py's `gpu_launches`). */
 int64_t nfb_launch_count(const nfb_context* ctx);
 
+/* Developer aid: when enabled, CTA 0 of the tensor-core kernel records clock64 stamps of its second tile's phases
+ * (featurise, each layer's MMA span, each epilogue) into a 64-entry buffer; `out64` (may be NULL) receives a copy. */
+int nfb_debug_tc_stamps(nfb_context* ctx, int enable, long long* out64);
+
 /* Measure the device's fp32 FFMA throughput with a register-resident outer-product loop
  * (the roofline denominator for the FFMA variant; MEASURED_PEAKS.json has no fp32 figure).
  * Runs `iters` timed launches and returns the best rate in TFLOP/s. */

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "nfb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "nfb_host_free": (C.c_int, [C.c_void_p]),
     "nfb_launch_count": (C.c_int64, [C.c_void_p]),
+    "nfb_debug_tc_stamps": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
     "nfb_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
 }
 

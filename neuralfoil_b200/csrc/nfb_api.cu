@@ -80,6 +80,7 @@ struct nfb_context {
   Model models[NFB_MAX_MODELS];
   HostSlot slots[2];
   int64_t launches = 0;
+  long long* tc_debug = nullptr;  // device buffer for nfb_debug_tc_stamps (64 x clock64), normally NULL
 };
 
 namespace {
@@ -231,6 +232,7 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
     tp.wblob = m.tc_w;
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
+    tp.dbg = ctx->tc_debug;
     const long long tiles = (n + nfb::tc::NQT - 1) / nfb::tc::NQT;
     const int grid = int(std::min<long long>(tiles, ctx->sm_count));
     nfb::tc::nfb_tc_kernel<<<grid, nfb::tc::THREADS, nfb::tc::SMEM_BYTES, stream>>>(tp);
@@ -320,6 +322,7 @@ void nfb_destroy(nfb_context* ctx) {
     if (s.d_out) cudaFree(s.d_out);
     if (s.h_stage) cudaFreeHost(s.h_stage);
   }
+  if (ctx->tc_debug) cudaFree(ctx->tc_debug);
   delete ctx;
 }
 
@@ -506,6 +509,24 @@ int nfb_host_free(void* ptr) {
 }
 
 int64_t nfb_launch_count(const nfb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int nfb_debug_tc_stamps(nfb_context* ctx, int enable, long long* out64) {
+  if (!ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  if (enable && !ctx->tc_debug) {
+    NFB_CUDA(cudaMalloc(&ctx->tc_debug, 64 * sizeof(long long)));
+    NFB_CUDA(cudaMemset(ctx->tc_debug, 0, 64 * sizeof(long long)));
+  }
+  if (out64 && ctx->tc_debug) {
+    NFB_CUDA(cudaDeviceSynchronize());
+    NFB_CUDA(cudaMemcpy(out64, ctx->tc_debug, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  if (!enable && ctx->tc_debug) {
+    NFB_CUDA(cudaFree(ctx->tc_debug));
+    ctx->tc_debug = nullptr;
+  }
+  return NFB_OK;
+}
 
 int nfb_measure_fp32_peak(nfb_context* ctx, int iters, double* out_tflops) {
   if (!ctx || !out_tflops) return fail(NFB_ERR_INVALID_ARGUMENT, "NULL argument");

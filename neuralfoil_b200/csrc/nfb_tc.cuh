@@ -62,6 +62,7 @@ struct TcParams {
   const __half* wblob;      // slices in streaming order, 16 KB each
   const float* bias;        // [L][512] fp32, last layer in packed row order (224 used)
   const float* inv_scale;   // [L]
+  long long* dbg;           // optional: clock64 stamps of CTA 0's second tile (scripts/gpu_debug_tc.py), else NULL
 };
 
 __host__ __device__ constexpr int slices_in_layer(int l, int L) {
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
           mbar_wait(bar_act, act_phase);
           act_phase ^= 1;
           tc_fence_after();
+          if (tp.dbg && blockIdx.x == 0 && t == 1) tp.dbg[32 + 2 * l] = clock64();
           const int n_sl = slices_in_layer(l, L);
           const int nb_count = (l == L - 1) ? 1 : 2;
           for (int sl = 0; sl < n_sl; ++sl, ++it) {
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
             umma_commit(bar_empty + 8 * s);  // slot is free once these MMAs have read it
           }
           umma_commit(bar_d);
+          if (tp.dbg && blockIdx.x == 0 && t == 1) tp.dbg[32 + 2 * l + 1] = clock64();
         }
     }
   } else {
@@ -297,6 +300,8 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
     uint32_t d_phase = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long tile_q0 = tile * NQT;
+      const bool stamp = tp.dbg && blockIdx.x == 0 && tile == blockIdx.x + gridDim.x && e == 0 && lane == 0;
+      if (stamp) tp.dbg[0] = clock64();
       if (half == 0) {  // 128 threads featurise the 128 rows (row n: query n, row 64 + n: its twin)
         const bool twin = n >= NQT;
         const long long qi = tile_q0 + (twin ? n - NQT : n);
@@ -305,11 +310,13 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_act);
+      if (stamp) tp.dbg[1] = clock64();
 
       for (int l = 0; l < L - 1; ++l) {
         mbar_wait(bar_d, d_phase);
         d_phase ^= 1;
         tc_fence_after();
+        if (stamp) tp.dbg[2 + 2 * l] = clock64();
         const float inv_s = bias_s[7 * H + l];
         const float* b = bias_s + l * H + half * 256;
 #pragma unroll 1
@@ -332,12 +339,14 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_act);
+        if (stamp) tp.dbg[3 + 2 * l] = clock64();
       }
 
       // ---- last layer: latents -> fp32 staging [224 packed rows][128 batch] in the (now idle) activation tile ----
       mbar_wait(bar_d, d_phase);
       d_phase ^= 1;
       tc_fence_after();
+      if (stamp) tp.dbg[20] = clock64();
       {
         float* stage = reinterpret_cast<float*>(act);
         const float inv_s = bias_s[7 * H + (L - 1)];
@@ -353,6 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
         }
         tc_fence_before();
         named_bar_sync(1, EPI_THREADS);
+        if (stamp) tp.dbg[21] = clock64();
         for (int item = et; item < (M_LAST / 4) * (NQT / 4); item += EPI_THREADS) {
           const int g = item / (NQT / 4), qb = (item % (NQT / 4)) * 4;
           float acc[4][8];
@@ -369,6 +379,7 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
           decode_and_store(p, g, q0, nvalid, vec_ok, acc, maha + qb, maha + NQT + qb, re_s + qb);
         }
         named_bar_sync(1, EPI_THREADS);  // staging (and maha / re) fully consumed before the next tile overwrites them
+        if (stamp) tp.dbg[22] = clock64();
       }
     }
   }

@@ -39,3 +39,19 @@ for variant in ("tensor", "fp32"):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     print(f"{variant}: n={n} {ms:.2f} ms -> {n / ms / 1e3:.2f} M q/s", flush=True)
+
+# phase stamps of CTA 0's second tile
+import ctypes as C
+buf = (C.c_longlong * 64)()
+ev._lib.nfb_debug_tc_stamps(ev._ctx, 1, None)
+r = torch.from_numpy(synthetic.sample_training_distribution(64 * 148 * 4, seed=1, dtype=np.float32)).cuda()
+ev.evaluate_device(r, "xxxlarge", variant="tensor"); torch.cuda.synchronize()
+ev._lib.nfb_debug_tc_stamps(ev._ctx, 0, buf)
+st = list(buf)
+t0 = st[0]
+print("epilogue-warp stamps (cycles from tile start): featurise done", st[1] - t0)
+for l in range(6):
+    print(f"  layer {l}: D ready at {st[2 + 2 * l] - t0}, epilogue done at {st[3 + 2 * l] - t0}  (epilogue {st[3 + 2 * l] - st[2 + 2 * l]})")
+print("  last layer D ready", st[20] - t0, "staged", st[21] - t0, "decoded+stored", st[22] - t0)
+for l in range(7):
+    print(f"  MMA layer {l}: start {st[32 + 2 * l] - t0} issue-end {st[33 + 2 * l] - t0} (span {st[33 + 2 * l] - st[32 + 2 * l]})")
