@@ -234,7 +234,7 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
     tp.inv_scale = m.tc_inv_scale;
     tp.dbg = ctx->tc_debug;
     const long long tiles = (n + nfb::tc::NQT - 1) / nfb::tc::NQT;
-    const int grid = int(std::min<long long>(tiles, ctx->sm_count));
+    const int grid = int(std::min<long long>((tiles + 1) & ~1LL, ctx->sm_count & ~1));  // whole CTA pairs
     nfb::tc::nfb_tc_kernel<<<grid, nfb::tc::THREADS, nfb::tc::SMEM_BYTES, stream>>>(tp);
     NFB_CUDA(cudaGetLastError());
     ctx->launches += 1;

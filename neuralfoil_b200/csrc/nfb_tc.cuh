@@ -84,6 +84,30 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// commit that arrives on the same-offset mbarrier of every CTA in `mask` (weight slices are shared by the CTA pair)
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA bulk copy global -> the same smem offset of every CTA in `mask`, completing on each one's mbarrier
+__device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -203,7 +227,12 @@ __device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, 
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
+// Launched as clusters of two CTAs (two SMs of one TPC).  The pair walks the same slice sequence; each CTA's
+// producer fetches HALF of every weight slice and multicasts it into both CTAs' rings, which halves the L2 -> SM
+// weight traffic (measured: with one CTA per slice stream the MMA phase ran at the 41 B/clk/SM L2 limit, 200 cycles
+// per MMA instead of 128).  Every CTA runs the same number of tiles (surplus tiles are all-padding), so the two
+// rings never diverge.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
   const EvalParams& p = tp.ev;
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* const smem =
@@ -221,7 +250,8 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.n_layers;
   const long long n_tiles = (p.n + NQT - 1) / NQT;
-  const uint32_t my_tiles = uint32_t((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const uint32_t my_tiles = uint32_t((n_tiles + gridDim.x - 1) / gridDim.x);  // same for every CTA
+  const uint32_t cta_rank = cluster_ctarank();
   int slices_per_tile = 0;
   for (int l = 0; l < L; ++l) slices_per_tile += slices_in_layer(l, L);
 
@@ -230,7 +260,7 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 2);  // both CTAs of the pair have consumed the slot
     }
     mbar_init(bar_act, EPI_WARPS);
     mbar_init(bar_d, 1);
@@ -244,6 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
 
   if (warp == 0) {
     // ============================ weight producer ============================
@@ -253,41 +284,51 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
       for (uint32_t it = 0, j = 0; it < total; ++it) {
         const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        mbar_arrive_expect_tx(bar_full + 8 * s, SLICE_BYTES);
-        bulk_copy_g2s(smem_u32(ring + s * SLICE_BYTES), src + size_t(j) * SLICE_BYTES, SLICE_BYTES, bar_full + 8 * s);
+        mbar_arrive_expect_tx(bar_full + 8 * s, SLICE_BYTES);  // my half + the peer's half
+        bulk_copy_g2s_multicast(smem_u32(ring + s * SLICE_BYTES) + cta_rank * (SLICE_BYTES / 2),
+                                src + size_t(j) * SLICE_BYTES + cta_rank * (SLICE_BYTES / 2), SLICE_BYTES / 2,
+                                bar_full + 8 * s, uint16_t(3));
         if (++j == uint32_t(slices_per_tile)) j = 0;
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (uint32_t(SLICE_N >> 3) << 17) | (uint32_t(NT >> 4) << 24);  // f16 x f16 -> f32
-      uint32_t it = 0, act_phase = 0;
-      for (uint32_t t = 0; t < my_tiles; ++t)
-        for (int l = 0; l < L; ++l) {
-          mbar_wait(bar_act, act_phase);
-          act_phase ^= 1;
+    // The whole warp runs this loop converged and one elected lane issues: descriptors then live in uniform
+    // registers.  (Issuing from a lone `if (lane == 0)` thread costs ~220 cycles per MMA in address arithmetic,
+    // R2UR moves and election loops -- measured with scripts/umma_probe_f16.cu -- against 128 for the MMA itself.)
+    const uint32_t idesc = (1u << 4) | (uint32_t(SLICE_N >> 3) << 17) | (uint32_t(NT >> 4) << 24);  // f16 x f16 -> f32
+    // descriptor high words: A = SWIZZLE_128B K-major (SBO 1024 B), B = no-swizzle core matrices (LBO 128 B, SBO 512 B)
+    const uint64_t a_hi = (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    const uint64_t b_hi = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
+    // (14-bit start-address field; in a cluster the 32-bit shared address carries the CTA rank in its top bits)
+    const uint32_t a0 = (smem_u32(act) >> 4) & 0x3FFF, b0 = (smem_u32(ring) >> 4) & 0x3FFF;
+    uint32_t it = 0, act_phase = 0;
+    for (uint32_t t = 0; t < my_tiles; ++t)
+      for (int l = 0; l < L; ++l) {
+        mbar_wait(bar_act, act_phase);
+        act_phase ^= 1;
+        tc_fence_after();
+        if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[32 + 2 * l] = clock64();
+        const int n_sl = slices_in_layer(l, L);
+        const bool one_block = (l == L - 1);
+        for (int sl = 0; sl < n_sl; ++sl, ++it) {
+          const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
+          const int ks = one_block ? sl : (sl >> 1), nb = one_block ? 0 : (sl & 1);
+          mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          if (tp.dbg && blockIdx.x == 0 && t == 1) tp.dbg[32 + 2 * l] = clock64();
-          const int n_sl = slices_in_layer(l, L);
-          const int nb_count = (l == L - 1) ? 1 : 2;
-          for (int sl = 0; sl < n_sl; ++sl, ++it) {
-            const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
-            const int ks = sl / nb_count, nb = sl % nb_count;
-            mbar_wait(bar_full + 8 * s, ph);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(act) + uint32_t(ks >> 1) * ATOM_BYTES + uint32_t(ks & 1) * 64;
-            const uint32_t b_base = smem_u32(ring + s * SLICE_BYTES);
-#pragma unroll
-            for (int j = 0; j < SLICE_K / 16; ++j)
-              umma_f16(tmem + nb * SLICE_N, smem_desc(a_base + j * 32, 16, 1024, 2), smem_desc(b_base + j * 256, 128, 512, 0),
-                       idesc, (ks | j) != 0);
-            umma_commit(bar_empty + 8 * s);  // slot is free once these MMAs have read it
+          const uint32_t a_lo = a0 + uint32_t(ks >> 1) * (ATOM_BYTES >> 4) + uint32_t(ks & 1) * 4;  // 64 B per 32 k
+          const uint32_t b_lo = b0 + s * (SLICE_BYTES >> 4);
+          if (elect_one_sync()) {
+            umma_f16(tmem + nb * SLICE_N, a_hi | a_lo, b_hi | b_lo, idesc, ks != 0);
+            umma_f16(tmem + nb * SLICE_N, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
+            umma_commit_multicast(bar_empty + 8 * s, uint16_t(3));  // slot is free once BOTH CTAs' MMAs have read it
           }
-          umma_commit(bar_d);
-          if (tp.dbg && blockIdx.x == 0 && t == 1) tp.dbg[32 + 2 * l + 1] = clock64();
+          __syncwarp();
         }
-    }
+        if (elect_one_sync()) umma_commit(bar_d);
+        __syncwarp();
+        if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[32 + 2 * l + 1] = clock64();
+      }
   } else {
     // ============================ epilogue warps ============================
     const int e = warp - 2, q = warp & 3, half = e >> 2;
@@ -298,9 +339,10 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
         p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
                   : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     uint32_t d_phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t t = 0; t < my_tiles; ++t) {
+      const long long tile = blockIdx.x + (long long)t * gridDim.x;  // may be past the end: an all-padding tile
       const long long tile_q0 = tile * NQT;
-      const bool stamp = tp.dbg && blockIdx.x == 0 && tile == blockIdx.x + gridDim.x && e == 0 && lane == 0;
+      const bool stamp = tp.dbg && blockIdx.x == 0 && t == 1 && e == 0 && lane == 0;
       if (stamp) tp.dbg[0] = clock64();
       if (half == 0) {  // 128 threads featurise the 128 rows (row n: query n, row 64 + n: its twin)
         const bool twin = n >= NQT;
@@ -385,6 +427,7 @@ __global__ void __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer can still multicast into this CTA
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
