@@ -6,10 +6,12 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "nfb_ffma.cuh"
+#include "nfb_small.cuh"
 #include "nfb_tc.cuh"
 
 namespace {
@@ -177,6 +179,23 @@ int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream)
   return NFB_OK;
 }
 
+// Batches up to this size go to the small-batch kernel (4 queries per CTA); measured crossover, DESIGN.md section 6.
+int64_t small_batch_limit(int h_pad) {
+  static const char* env = getenv("NFB_SMALL_MAX");  // tuning experiments only
+  if (env) return atoll(env);
+  return h_pad >= 512 ? 512 : h_pad >= 256 ? 1024 : 2048;
+}
+
+template <int H>
+int launch_small(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
+  using Cfg = nfb::SmallCfg<H>;
+  const int grid = int((p.n + nfb::SMALL_QUERIES - 1) / nfb::SMALL_QUERIES);
+  nfb::nfb_small_kernel<H><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
 int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
                     const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype) {
   if (!ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "ctx is NULL");
@@ -239,6 +258,14 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
     NFB_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return NFB_OK;
+  }
+  if (n <= small_batch_limit(m.h_pad)) {
+    switch (m.h_pad) {
+      case 64: return launch_small<64>(ctx, p, stream);
+      case 128: return launch_small<128>(ctx, p, stream);
+      case 256: return launch_small<256>(ctx, p, stream);
+      case 512: return launch_small<512>(ctx, p, stream);
+    }
   }
   switch (m.h_pad) {
     case 64: return launch_ffma<Cfg64>(ctx, p, stream);

@@ -42,6 +42,7 @@ def output_keys() -> list[str]:
 
 
 _OUTPUT_KEYS = output_keys()
+_ONES_23 = (C.c_int64 * 23)(*([1] * 23))
 
 
 def _length(x) -> int:
@@ -200,7 +201,7 @@ class Evaluator:
         block = self._evaluate_host_rows(model_id, rows, n_cases, np.float64, variant=variant)
         # Row views of one (198, ld) block: each value is a contiguous (N,) float64 array, as in the
         # reference, where the keys are views of a shared Fortran-ordered block.
-        return {key: block[i, :n_cases] for i, key in enumerate(_OUTPUT_KEYS)}
+        return dict(zip(_OUTPUT_KEYS, block[:, :n_cases]))  # iterating a 2-D array yields its row views
 
     def evaluate_host(self, raw: np.ndarray, model_size: str = "xlarge", out_dtype=np.float32, chunk: int = 0,
                       variant: str = "fp32"):
@@ -242,22 +243,34 @@ class Evaluator:
         return out[:, :n]
 
     def _evaluate_host_rows(self, model_id: int, rows, n: int, out_dtype, chunk: int = 0, variant: str = "fp32"):
-        in_dtype = rows[0].dtype
-        if any(r.dtype != in_dtype for r in rows):
-            rows = [r.astype(np.float64) for r in rows]
-            in_dtype = np.dtype(np.float64)
         ld = (n + 3) & ~3
         block = np.empty((_lib.N_OUTPUT_ROWS, ld), dtype=out_dtype)
-        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[r.ctypes.data for r in rows])
-        strides = (C.c_int64 * _lib.N_RAW_ROWS)(*[0 if r.size == 1 and n > 1 else 1 for r in rows])
+        if n <= 4096:
+            # Small batches (an optimiser's per-iteration call): gather the rows into one (23, n) float64 block so
+            # that the pointer table is plain integer arithmetic -- numpy's `.ctypes` accessors cost ~1 us apiece.
+            buf = np.empty((_lib.N_RAW_ROWS, n), dtype=np.float64)
+            for i, r in enumerate(rows):
+                buf[i] = r
+            base, step = buf.__array_interface__["data"][0], n * 8
+            ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*range(base, base + _lib.N_RAW_ROWS * step, step))
+            strides, in_code = _ONES_23, _lib.F64
+        else:
+            in_dtype = rows[0].dtype
+            if any(r.dtype != in_dtype for r in rows):
+                rows = [r.astype(np.float64) for r in rows]
+                in_dtype = np.dtype(np.float64)
+            buf = rows  # keeps the arrays alive across the call
+            ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[r.__array_interface__["data"][0] for r in rows])
+            strides = (C.c_int64 * _lib.N_RAW_ROWS)(*[0 if r.size == 1 and n > 1 else 1 for r in rows])
+            in_code = _lib.F64 if in_dtype == np.float64 else _lib.F32
         _lib.check(
             self._lib.nfb_eval_host(
-                self._ctx, model_id, self._variant(variant), n, ptrs, strides,
-                _lib.F64 if in_dtype == np.float64 else _lib.F32,
-                block.ctypes.data_as(C.c_void_p), ld,
-                _lib.F64 if np.dtype(out_dtype) == np.float64 else _lib.F32, chunk,
+                self._ctx, model_id, self._variant(variant), n, ptrs, strides, in_code,
+                block.__array_interface__["data"][0], ld,
+                _lib.F64 if block.dtype == np.float64 else _lib.F32, chunk,
             )
         )
+        del buf
         return block
 
     # -- device-resident call ----------------------------------------------------------------------

@@ -365,3 +365,16 @@ def test_tensor_variant_refuses_other_models(evaluator):
         evaluator.evaluate_host(raw, "xlarge", variant="tensor")
     with pytest.raises(ValueError, match="variant"):
         evaluator.evaluate_host(raw, "xxxlarge", variant="bf16")
+
+
+# ---------------------------------------------------------------------------------------------
+# Small-batch (latency) kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", MODEL_SIZES)
+def test_small_and_large_kernels_agree(evaluator, size):
+    """A query gets bit-identical results from the 4-queries-per-CTA kernel (small batches) and the tiled kernel."""
+    raw = synthetic.sample_training_distribution(6000, seed=17).astype(np.float32)
+    big = evaluator.evaluate_host(raw, size, out_dtype=np.float32)           # 6000 > every small-batch limit
+    for n in (1, 5, 37, 256):
+        small = evaluator.evaluate_host(np.ascontiguousarray(raw[:, :n]), size, out_dtype=np.float32)
+        np.testing.assert_array_equal(small, big[:, :n])
