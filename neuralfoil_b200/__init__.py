@@ -1,16 +1,20 @@
 """
 neuralfoil_b200 -- B200-native (sm_100a) evaluation of NeuralFoil's learned core.
 
-Drop-in surface for the path (reference neuralfoil/__init__.py:1-15): `get_aero_from_kulfan_parameters`
-and `bl_x_points`.  Importing the package needs no GPU; the first evaluation creates the CUDA context
+Drop-in surface (reference neuralfoil/__init__.py:1-15): `get_aero_from_kulfan_parameters` -- the hot path --
+plus its three geometry front doors and `bl_x_points`.  Importing the package needs no GPU; the first evaluation creates the CUDA context
 and raises if the library or a B200 is missing (there is no CPU fallback).
 """
 
+from .geometry import Airfoil  # noqa: F401
 from .main import (  # noqa: F401
     MODEL_SIZES,
     Evaluator,
     bl_x_points,
     default_evaluator,
+    get_aero_from_airfoil,
+    get_aero_from_coordinates,
+    get_aero_from_dat_file,
     get_aero_from_kulfan_parameters,
     output_keys,
 )

@@ -353,6 +353,48 @@ class Evaluator:
             pass
 
 
+    # -- the reference's higher-level entry points (main.py:335-468) -----------------------------------
+    def get_aero_from_airfoil(self, airfoil, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0,
+                              model_size="xlarge", variant: str = "fp32") -> dict[str, np.ndarray]:
+        """
+        `airfoil`: anything with a `.coordinates` (N_points, 2) array in Selig order -- `geometry.Airfoil`, or an
+        `aerosandbox.Airfoil` if the caller has that package.  Normalise, fit 8 + 8 + 1 + 1 Kulfan parameters, call
+        the learned core at (alpha + rotation, Re / scale), move the moment reference back (main.py:360-387).
+        """
+        from . import geometry
+
+        if hasattr(airfoil, "kulfan_parameters") and not hasattr(airfoil, "coordinates"):
+            raise ValueError("pass Kulfan parameters to get_aero_from_kulfan_parameters directly")
+        nrm = geometry.normalize(np.asarray(airfoil.coordinates, dtype=np.float64))
+        kulfan = geometry.kulfan_parameters_from_coordinates(nrm["coordinates"])
+        delta_alpha, scale = nrm["rotation_angle"], nrm["scale_factor"]
+        x_qc = -nrm["x_translation"] + 0.25 * (1.0 / scale * np.cos(np.radians(delta_alpha))) - 0.25
+        y_qc = -nrm["y_translation"] + 0.25 * (1.0 / scale * np.sin(np.radians(-delta_alpha)))
+        aero = self.get_aero_from_kulfan_parameters(
+            kulfan, alpha=np.asarray(alpha, dtype=np.float64) + delta_alpha, Re=np.asarray(Re, dtype=np.float64) / scale,
+            n_crit=n_crit, xtr_upper=xtr_upper, xtr_lower=xtr_lower, model_size=model_size, variant=variant,
+        )
+        aero["CM"] = aero["CM"] + (-aero["CL"] * x_qc + aero["CD"] * y_qc)  # main.py:386-387
+        return aero
+
+    def get_aero_from_coordinates(self, coordinates, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0,
+                                  model_size="xlarge", variant: str = "fp32") -> dict[str, np.ndarray]:
+        """main.py:392-426"""
+        from . import geometry
+
+        return self.get_aero_from_airfoil(geometry.Airfoil(coordinates=coordinates), alpha, Re, n_crit, xtr_upper,
+                                          xtr_lower, model_size, variant)
+
+    def get_aero_from_dat_file(self, filename, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0,
+                               model_size="xlarge", variant: str = "fp32") -> dict[str, np.ndarray]:
+        """main.py:429-468"""
+        from . import geometry
+
+        with open(filename, "r") as f:
+            coordinates = geometry.coordinates_from_raw_dat(f.readlines())
+        return self.get_aero_from_coordinates(coordinates, alpha, Re, n_crit, xtr_upper, xtr_lower, model_size, variant)
+
+
 _default: Evaluator | None = None
 
 
@@ -376,3 +418,18 @@ def get_aero_from_kulfan_parameters(
     return default_evaluator().get_aero_from_kulfan_parameters(
         kulfan_parameters, alpha, Re, n_crit=n_crit, xtr_upper=xtr_upper, xtr_lower=xtr_lower, model_size=model_size
     )
+
+
+def get_aero_from_airfoil(airfoil, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"):
+    """Drop-in for the reference's `get_aero_from_airfoil` (main.py:335-389); geometry by `neuralfoil_b200.geometry`."""
+    return default_evaluator().get_aero_from_airfoil(airfoil, alpha, Re, n_crit, xtr_upper, xtr_lower, model_size)
+
+
+def get_aero_from_coordinates(coordinates, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"):
+    """Drop-in for the reference's `get_aero_from_coordinates` (main.py:392-426)."""
+    return default_evaluator().get_aero_from_coordinates(coordinates, alpha, Re, n_crit, xtr_upper, xtr_lower, model_size)
+
+
+def get_aero_from_dat_file(filename, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"):
+    """Drop-in for the reference's `get_aero_from_dat_file` (main.py:429-468)."""
+    return default_evaluator().get_aero_from_dat_file(filename, alpha, Re, n_crit, xtr_upper, xtr_lower, model_size)

@@ -378,3 +378,35 @@ def test_small_and_large_kernels_agree(evaluator, size):
     for n in (1, 5, 37, 256):
         small = evaluator.evaluate_host(np.ascontiguousarray(raw[:, :n]), size, out_dtype=np.float32)
         np.testing.assert_array_equal(small, big[:, :n])
+
+
+# ---------------------------------------------------------------------------------------------
+# Geometry front doors (reference main.py:335-468) on the CUDA path
+# ---------------------------------------------------------------------------------------------
+def test_golden_airfoil_pipeline_on_gpu(evaluator):
+    """reference tests/test_golden_values.py:48-55, 70-79 (rel 1e-6 there, for float64; fp32 bound of tests/parity.py here)"""
+    from neuralfoil_b200 import Airfoil
+
+    golden = {"analysis_confidence": 0.968356999039, "CL": 1.02508809111, "CD": 0.00791137686241,
+              "CM": -0.0992982374935, "Top_Xtr": 0.402283708087, "Bot_Xtr": 1.0}
+    aero = evaluator.get_aero_from_airfoil(Airfoil("naca4412"), alpha=5.0, Re=1e6, model_size="xlarge")
+    assert list(aero) == output_keys()
+    for key, want in golden.items():
+        assert float(aero[key][0]) == pytest.approx(want, rel=1e-5, abs=6e-5), key
+
+
+def test_entry_points_agree_on_gpu(evaluator, tmp_path):
+    """reference tests/test_entry_points.py:22-48"""
+    from neuralfoil_b200 import Airfoil
+
+    af = Airfoil("naca4412")
+    a = evaluator.get_aero_from_airfoil(af, alpha=4.0, Re=2e6)
+    c = evaluator.get_aero_from_coordinates(af.coordinates, alpha=4.0, Re=2e6)
+    dat = tmp_path / "naca4412.dat"
+    dat.write_text(af.name + "\n" + "\n".join(f"{x:.16f} {y:.16f}" for x, y in af.coordinates))
+    d = evaluator.get_aero_from_dat_file(dat, alpha=4.0, Re=2e6)
+    for key in SCALARS:
+        np.testing.assert_allclose(a[key], c[key], rtol=1e-10, err_msg=key)
+        np.testing.assert_allclose(a[key], d[key], rtol=1e-5, atol=1e-6, err_msg=key)
+    sweep = evaluator.get_aero_from_airfoil(af, alpha=np.linspace(-5, 10, 31), Re=2e6)
+    assert sweep["CL"].shape == (31,) and np.all(np.diff(sweep["CL"][:20]) > 0)
