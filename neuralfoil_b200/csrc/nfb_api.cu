@@ -143,8 +143,8 @@ TcPack pack_model_tc(int L, const int* dims, const float* const* W, const float*
     }
     const int nb_count = last ? 1 : 2;
     const int n_ks = slices_in_layer(l, L) / nb_count;
-    for (int ks = 0; ks < n_ks; ++ks)
-      for (int nb = 0; nb < nb_count; ++nb, ++slice) {
+    for (int nb = 0; nb < nb_count; ++nb)  // streaming order of nfb_tc_kernel: N-block major, K-slices inside
+      for (int ks = 0; ks < n_ks; ++ks, ++slice) {
         __half* dst = out.w.data() + slice * (SLICE_BYTES / 2);
         for (int r = 0; r < SLICE_N; ++r) {
           const int m = nb * SLICE_N + r;

@@ -10,6 +10,9 @@
 //   * B = weights, fp16, pre-packed on the host as K-major no-swizzle core matrices, 256 output features x 32 k
 //     per 16 KB slice, streamed L2 -> smem by a producer thread through a 4-deep TMA ring (cp.async.bulk + mbarrier).
 //   * D = 128 lanes x 512 columns = the whole tensor memory; one elected thread issues the MMAs (N = 256, K = 16).
+//   * Layers are software-pipelined in halves of 256 features (see the barrier comment in the kernel): the epilogue
+//     of a layer's first half runs under the MMAs of its second half, and the next layer's first MMAs run under the
+//     epilogue of the second half; the activation tile stays single-buffered.
 //
 // Why this orientation and this precision (measured with scripts/umma_probe.cu on B200):
 // a tcgen05.mma with M = 128 costs ~111-124 cycles however small N is, so N must be large (256 features), which
@@ -21,7 +24,7 @@
 // subnormals), undone exactly in the epilogue.
 //
 // Roles (320 threads): warp 0 lane 0 = TMA producer; warp 1 = TMEM allocator, lane 0 = MMA issuer; warps 2..9 =
-// epilogue (thread = batch row 32 * (warp % 4) + lane, feature half (warp - 2) / 4).
+// epilogue (thread = batch row 32 * (warp % 4) + lane; the two warps of a row quarter split each half's 256 features).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -243,8 +246,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
   float* const maha = reinterpret_cast<float*>(smem + OFF_MAHA);
   float* const re_s = reinterpret_cast<float*>(smem + OFF_RE);
   const uint32_t bar_full = smem_u32(smem + OFF_BARS), bar_empty = bar_full + 8 * STAGES;
-  const uint32_t bar_act = bar_empty + 8 * STAGES;  // epilogue -> MMA: layer input is in smem, TMEM is drained
-  const uint32_t bar_d = bar_act + 8;               // MMA -> epilogue: the layer's accumulators are complete
+  // Layer pipeline barriers.  "Half" h = features [256 h, 256 h + 256) = TMEM columns of N-block h = K region h
+  // (activation atoms 4 h .. 4 h + 3) of the next layer.  The MMA warp walks a layer as four quarters
+  //   q1 = (N-block 0, K region 0), q2 = (N-block 0, K region 1), q3 = (N-block 1, K region 0), q4 = (N-block 1, K region 1)
+  // so that the epilogue of half 0 overlaps q3/q4 and the next layer's q1 overlaps the epilogue of half 1.
+  const uint32_t bar_a0 = bar_empty + 8 * STAGES;   // epilogue -> MMA: K region 0 of the layer input is in smem, TMEM cols 0..255 drained
+  const uint32_t bar_a1 = bar_a0 + 8;               // ... K region 1, TMEM cols 256..511
+  const uint32_t bar_d0 = bar_a1 + 8;               // MMA -> epilogue: N-block 0 complete (after q2)
+  const uint32_t bar_k0 = bar_d0 + 8;               // MMA -> epilogue: K region 0 no longer read (after q3)
+  const uint32_t bar_d1 = bar_k0 + 8;               // MMA -> epilogue: N-block 1 complete, K region 1 no longer read (after q4)
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -262,8 +272,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 2);  // both CTAs of the pair have consumed the slot
     }
-    mbar_init(bar_act, EPI_WARPS);
-    mbar_init(bar_d, 1);
+    mbar_init(bar_a0, EPI_WARPS);
+    mbar_init(bar_a1, EPI_WARPS);
+    mbar_init(bar_d0, 1);
+    mbar_init(bar_k0, 1);
+    mbar_init(bar_d1, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -302,99 +315,145 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
     const uint64_t b_hi = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
     // (14-bit start-address field; in a cluster the 32-bit shared address carries the CTA rank in its top bits)
     const uint32_t a0 = (smem_u32(act) >> 4) & 0x3FFF, b0 = (smem_u32(ring) >> 4) & 0x3FFF;
-    uint32_t it = 0, act_phase = 0;
+    uint32_t it = 0, ph_a0 = 0, ph_a1 = 0;
+    auto issue = [&](int nb, int ks_begin, int ks_end) {  // K-slices [ks_begin, ks_end) of N-block nb, in streaming order
+      for (int ks = ks_begin; ks < ks_end; ++ks, ++it) {
+        const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a_lo = a0 + uint32_t(ks >> 1) * (ATOM_BYTES >> 4) + uint32_t(ks & 1) * 4;  // 64 B per 32 k
+        const uint32_t b_lo = b0 + s * (SLICE_BYTES >> 4);
+        if (elect_one_sync()) {
+          umma_f16(tmem + nb * SLICE_N, a_hi | a_lo, b_hi | b_lo, idesc, ks != 0);
+          umma_f16(tmem + nb * SLICE_N, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
+          umma_commit_multicast(bar_empty + 8 * s, uint16_t(3));  // slot is free once BOTH CTAs' MMAs have read it
+        }
+        __syncwarp();
+      }
+    };
+    auto commit = [&](uint32_t bar) {
+      if (elect_one_sync()) umma_commit(bar);
+      __syncwarp();
+    };
     for (uint32_t t = 0; t < my_tiles; ++t)
       for (int l = 0; l < L; ++l) {
-        mbar_wait(bar_act, act_phase);
-        act_phase ^= 1;
+        const int kt = (l == 0) ? K0 / SLICE_K : H / SLICE_K;  // K-slices of the layer
+        const int kh = (l == 0) ? kt : kt / 2;                 // of which in K region 0 (the first layer's 96 inputs all are)
+        mbar_wait(bar_a0, ph_a0);
+        ph_a0 ^= 1;
         tc_fence_after();
         if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[32 + 2 * l] = clock64();
-        const int n_sl = slices_in_layer(l, L);
-        const bool one_block = (l == L - 1);
-        for (int sl = 0; sl < n_sl; ++sl, ++it) {
-          const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
-          const int ks = one_block ? sl : (sl >> 1), nb = one_block ? 0 : (sl & 1);
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t a_lo = a0 + uint32_t(ks >> 1) * (ATOM_BYTES >> 4) + uint32_t(ks & 1) * 4;  // 64 B per 32 k
-          const uint32_t b_lo = b0 + s * (SLICE_BYTES >> 4);
-          if (elect_one_sync()) {
-            umma_f16(tmem + nb * SLICE_N, a_hi | a_lo, b_hi | b_lo, idesc, ks != 0);
-            umma_f16(tmem + nb * SLICE_N, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
-            umma_commit_multicast(bar_empty + 8 * s, uint16_t(3));  // slot is free once BOTH CTAs' MMAs have read it
-          }
-          __syncwarp();
+        issue(0, 0, kh);                                       // q1
+        mbar_wait(bar_a1, ph_a1);
+        ph_a1 ^= 1;
+        tc_fence_after();
+        issue(0, kh, kt);                                      // q2
+        commit(bar_d0);
+        if (l != L - 1) {
+          issue(1, 0, kh);                                     // q3
+          commit(bar_k0);
+          issue(1, kh, kt);                                    // q4
+          commit(bar_d1);
         }
-        if (elect_one_sync()) umma_commit(bar_d);
-        __syncwarp();
         if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[32 + 2 * l + 1] = clock64();
       }
   } else {
     // ============================ epilogue warps ============================
-    const int e = warp - 2, q = warp & 3, half = e >> 2;
+    const int e = warp - 2, q = warp & 3, part = e >> 2;  // part: which 128 of a half's 256 features this warp takes
     const int n = 32 * q + lane;             // batch row == TMEM lane
     const int et = (e << 5) | lane;          // 0..255
     const uint32_t t_lane = tmem + (uint32_t(32 * q) << 16);
     const bool vec_ok =
         p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
                   : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    uint32_t d_phase = 0;
+    uint32_t ph_d0 = 0, ph_k0 = 0, ph_d1 = 0;
+    // scale, bias, SiLU and fp16 packing of 32 accumulators
+    auto activate = [&](const uint32_t (&v)[32], const float* b, float inv_s, uint32_t (&w)[16]) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x0 = silu_fast(fmaf(__uint_as_float(v[2 * i]), inv_s, b[2 * i]));
+        const float x1 = silu_fast(fmaf(__uint_as_float(v[2 * i + 1]), inv_s, b[2 * i + 1]));
+        w[i] = pack_f16x2(x0, x1);
+      }
+    };
+    auto store32 = [&](int k, const uint32_t (&w)[16]) {  // 32 consecutive features k..k+31 of row n
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8)
+        *reinterpret_cast<uint4*>(act + act_chunk_offset(n, k + 8 * c8)) =
+            make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
+    };
+    auto publish = [&](uint32_t bar) {  // my smem writes -> async proxy, my TMEM reads are done; tell the MMA warp
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
     for (uint32_t t = 0; t < my_tiles; ++t) {
       const long long tile = blockIdx.x + (long long)t * gridDim.x;  // may be past the end: an all-padding tile
       const long long tile_q0 = tile * NQT;
       const bool stamp = tp.dbg && blockIdx.x == 0 && t == 1 && e == 0 && lane == 0;
       if (stamp) tp.dbg[0] = clock64();
-      if (half == 0) {  // 128 threads featurise the 128 rows (row n: query n, row 64 + n: its twin)
+      if (part == 0) {  // 128 threads featurise the 128 rows (row n: query n, row 64 + n: its twin)
         const bool twin = n >= NQT;
         const long long qi = tile_q0 + (twin ? n - NQT : n);
         featurise_row(p, qi, qi < p.n, twin, n, act, maha, re_s);
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_act);
+      if (lane == 0) {
+        mbar_arrive(bar_a0);
+        mbar_arrive(bar_a1);
+      }
       if (stamp) tp.dbg[1] = clock64();
 
       for (int l = 0; l < L - 1; ++l) {
-        mbar_wait(bar_d, d_phase);
-        d_phase ^= 1;
+        const float inv_s = bias_s[7 * H + l];
+        const float* b = bias_s + l * H + part * 128;
+        // ---- half 0: N-block 0 is complete after q2; its outputs may only land in K region 0 after q3 ----
+        mbar_wait(bar_d0, ph_d0);
+        ph_d0 ^= 1;
         tc_fence_after();
         if (stamp) tp.dbg[2 + 2 * l] = clock64();
-        const float inv_s = bias_s[7 * H + l];
-        const float* b = bias_s + l * H + half * 256;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + uint32_t(half * 256 + c0), v);
-          uint32_t w[16];
+        {
+          uint32_t w[4][16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a0 = silu_fast(fmaf(__uint_as_float(v[2 * i]), inv_s, b[c0 + 2 * i]));
-            const float a1 = silu_fast(fmaf(__uint_as_float(v[2 * i + 1]), inv_s, b[c0 + 2 * i + 1]));
-            w[i] = pack_f16x2(a0, a1);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + uint32_t(part * 128 + 32 * c), v);
+            activate(v, b + 32 * c, inv_s, w[c]);
           }
+          mbar_wait(bar_k0, ph_k0);
+          ph_k0 ^= 1;
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8)
-            *reinterpret_cast<uint4*>(act + act_chunk_offset(n, half * 256 + c0 + 8 * c8)) =
-                make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
+          for (int c = 0; c < 4; ++c) store32(part * 128 + 32 * c, w[c]);
         }
-        tc_fence_before();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_act);
+        publish(bar_a0);
+        // ---- half 1: N-block 1 complete (and K region 1 free) after q4; overlaps the next layer's q1 ----
+        mbar_wait(bar_d1, ph_d1);
+        ph_d1 ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32], w[16];
+          tmem_ld32(t_lane + uint32_t(256 + part * 128 + 32 * c), v);
+          activate(v, b + 256 + 32 * c, inv_s, w);
+          store32(256 + part * 128 + 32 * c, w);
+        }
+        publish(bar_a1);
         if (stamp) tp.dbg[3 + 2 * l] = clock64();
       }
 
       // ---- last layer: latents -> fp32 staging [224 packed rows][128 batch] in the (now idle) activation tile ----
-      mbar_wait(bar_d, d_phase);
-      d_phase ^= 1;
+      mbar_wait(bar_d0, ph_d0);
+      ph_d0 ^= 1;
       tc_fence_after();
       if (stamp) tp.dbg[20] = clock64();
       {
         float* stage = reinterpret_cast<float*>(act);
         const float inv_s = bias_s[7 * H + (L - 1)];
         const float* b = bias_s + (L - 1) * H;
-        // feature ranges: half 0 -> [0, 128), half 1 -> [128, 224)
-        const int f_begin = half * 128, f_end = half ? M_LAST : 128;
+        // feature ranges: part 0 -> [0, 128), part 1 -> [128, 224)
+        const int f_begin = part * 128, f_end = part ? M_LAST : 128;
 #pragma unroll 1
         for (int c0 = f_begin; c0 < f_end; c0 += 32) {
           uint32_t v[32];
