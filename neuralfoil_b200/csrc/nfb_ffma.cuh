@@ -126,11 +126,11 @@ __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const fl
   }
 }
 
-// ---- step 1: featurisation + Mahalanobis, one thread per tile column --------------------------
-template <int NC>
-__device__ __forceinline__ void featurise_column(const EvalParams& p, long long q, bool valid,
-                                                 bool twin, int col, float* __restrict__ act,
-                                                 float* __restrict__ maha, float* __restrict__ re_s) {
+// ---- step 1: featurisation + Mahalanobis (shared by every kernel) -----------------------------------
+// One query (or its flipped twin): 23 raw scalars -> the 25 latent inputs x (fp64) [main.py:171-184, 253-265],
+// d2 / 50 of the Mahalanobis correction [main.py:47-61, 244-246] and Re.  fp64 throughout: cond(S^-1) ~ 7e7.
+__device__ __forceinline__ void featurise_query(const EvalParams& p, long long q, bool valid, bool twin,
+                                                double (&x)[N_IN], float& maha, float& re) {
   double r[N_RAW];
   if (valid) {
     if (p.in_f64) {
@@ -148,7 +148,6 @@ __device__ __forceinline__ void featurise_column(const EvalParams& p, long long 
     r[19] = 1.0e6; r[20] = 9.0; r[21] = 1.0; r[22] = 1.0;
   }
 
-  double x[N_IN];
 #pragma unroll
   for (int i = 0; i < 17; ++i) x[i] = r[i];
   x[17] = r[17] * 50.0;
@@ -178,7 +177,7 @@ __device__ __forceinline__ void featurise_column(const EvalParams& p, long long 
     x[24] = t;
   }
 
-  // (x - mu)^T S^-1 (x - mu) with the packed symmetric form (fp64: cond(S^-1) ~ 7e7).
+  // (x - mu)^T S^-1 (x - mu) with the packed symmetric form
   double d[N_IN];
 #pragma unroll
   for (int i = 0; i < N_IN; ++i) d[i] = x[i] - c_mean[i];
@@ -191,9 +190,20 @@ __device__ __forceinline__ void featurise_column(const EvalParams& p, long long 
     for (int j = i; j < N_IN; ++j) t = fma(c_quad[idx++], d[j], t);
     d2 = fma(d[i], t, d2);
   }
-  maha[col] = static_cast<float>(d2 / (2.0 * N_IN));  // main.py:244-246
-  if (!twin) re_s[col] = static_cast<float>(r[19]);
+  maha = static_cast<float>(d2 / (2.0 * N_IN));  // main.py:244-246
+  re = static_cast<float>(r[19]);
+}
 
+// fp32 kernels: one thread per tile column; the 25 inputs go, rounded to fp32, into rows 0..31 of the activation tile
+template <int NC>
+__device__ __forceinline__ void featurise_column(const EvalParams& p, long long q, bool valid,
+                                                 bool twin, int col, float* __restrict__ act,
+                                                 float* __restrict__ maha, float* __restrict__ re_s) {
+  double x[N_IN];
+  float m, re;
+  featurise_query(p, q, valid, twin, x, m, re);
+  maha[col] = m;
+  if (!twin) re_s[col] = re;
 #pragma unroll
   for (int k = 0; k < N_IN; ++k) act[k * NC + col] = static_cast<float>(x[k]);
 #pragma unroll

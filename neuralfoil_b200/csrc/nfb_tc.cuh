@@ -46,7 +46,6 @@ constexpr uint32_t ATOM_BYTES = NT * 128;                  // 16 KB: 16 row grou
 constexpr uint32_t ACT_BYTES = (H / ATOM_K) * ATOM_BYTES;  // 128 KB
 constexpr int THREADS = 320;
 constexpr int EPI_WARPS = 8, EPI_THREADS = 256;
-constexpr int MAX_BIAS = NFB_MAX_LAYERS_K * H;
 
 // shared-memory map (bytes from a 1024-aligned base)
 constexpr uint32_t OFF_ACT = 0;
@@ -146,67 +145,14 @@ __device__ __forceinline__ uint32_t act_chunk_offset(int n, int k) {
   return uint32_t(atom) * ATOM_BYTES + uint32_t(n >> 3) * 1024 + uint32_t(n & 7) * 128 + uint32_t((chunk ^ (n & 7)) << 4);
 }
 
-// ---- featurise one batch row: fp64 features + Mahalanobis (as nfb::featurise_column), then the first layer's
-//      [x_hi | x_lo | x_hi] fp16 row ----------------------------------------------------------------------------
+// ---- featurise one batch row (nfb::featurise_query), then the first layer's [x_hi | x_lo | x_hi] fp16 row ----------
 __device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, bool valid, bool twin, int n,
                                               unsigned char* act, float* maha, float* re_s) {
-  double r[N_RAW];
-  if (valid) {
-    if (p.in_f64) {
-#pragma unroll
-      for (int i = 0; i < N_RAW; ++i) r[i] = __ldg(static_cast<const double*>(p.in[i]) + q * p.in_stride[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < N_RAW; ++i)
-        r[i] = static_cast<double>(__ldg(static_cast<const float*>(p.in[i]) + q * p.in_stride[i]));
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < N_RAW; ++i) r[i] = 0.0;
-    r[19] = 1.0e6; r[20] = 9.0; r[21] = 1.0; r[22] = 1.0;
-  }
   double x[N_IN];
-#pragma unroll
-  for (int i = 0; i < 17; ++i) x[i] = r[i];
-  x[17] = r[17] * 50.0;
-  constexpr double kPi = 3.141592653589793238462643383279502884;
-  x[18] = sin((2.0 * r[18]) * kPi / 180.0);
-  const double c = cos(r[18] * kPi / 180.0);
-  x[19] = c;
-  x[20] = __dsub_rn(1.0, __dmul_rn(c, c));
-  x[21] = (log(r[19]) - 12.5) / 3.5;
-  x[22] = (r[20] - 9.0) / 4.5;
-  x[23] = r[21];
-  x[24] = r[22];
-  if (twin) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double u = x[i], l = x[8 + i];
-      x[i] = -l;
-      x[8 + i] = -u;
-    }
-    x[16] = -x[16];
-    x[18] = -x[18];
-    const double t = x[23];
-    x[23] = x[24];
-    x[24] = t;
-  }
-  double d2 = 0.0;
-  {
-    double d[N_IN];
-#pragma unroll
-    for (int i = 0; i < N_IN; ++i) d[i] = x[i] - c_mean[i];
-    int idx = 0;
-#pragma unroll
-    for (int i = 0; i < N_IN; ++i) {
-      double t = 0.0;
-#pragma unroll
-      for (int j = i; j < N_IN; ++j) t = fma(c_quad[idx++], d[j], t);
-      d2 = fma(d[i], t, d2);
-    }
-  }
-  maha[n] = static_cast<float>(d2 / (2.0 * N_IN));
-  if (!twin) re_s[n] = static_cast<float>(r[19]);
+  float m, re;
+  featurise_query(p, q, valid, twin, x, m, re);
+  maha[n] = m;
+  if (!twin) re_s[n] = re;
 
   // hi / lo split in fp16 (22 significant bits together), 32 values each (25 used)
   uint32_t hi[16], lo[16];
