@@ -49,8 +49,8 @@ enum nfb_dtype { NFB_F32 = 0, NFB_F64 = 1 };
 
 /* Which kernel evaluates the network.
  *   FP32_FFMA    fp32 CUDA-core path, every model size; the correctness reference (tolerance: tests/parity.py).
- *   TENSOR_FP16  tcgen05 tensor-core path for 512-wide models (xxxlarge): fp16 operands (TF32's mantissa), fp32
- *                accumulation in tensor memory, first layer fp32-exact; looser, stated tolerance.
+ *   TENSOR_FP16  tcgen05 tensor-core path for 512- and 256-wide models (xxxlarge, xxlarge): fp16 operands (TF32's
+ *                mantissa), fp32 accumulation in tensor memory, first layer fp32-exact; looser, stated tolerance.
  *                Other models: NFB_ERR_UNSUPPORTED_MODEL. */
 enum nfb_variant { NFB_VARIANT_FP32_FFMA = 0, NFB_VARIANT_TENSOR_FP16 = 1 };
 

@@ -118,11 +118,14 @@ struct TcPack {
   std::vector<__half> w;
   std::vector<float> bias, inv_scale;
 };
+template <class Cfg>
 TcPack pack_model_tc(int L, const int* dims, const float* const* W, const float* const* B) {
   using namespace nfb::tc;
+  constexpr int H = Cfg::H, SLICE_N = Cfg::SLICE_N;
+  constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES;
   TcPack out;
   size_t n_slices = 0;
-  for (int l = 0; l < L; ++l) n_slices += slices_in_layer(l, L);
+  for (int l = 0; l < L; ++l) n_slices += Cfg::slices_in_layer(l, L);
   out.w.assign(n_slices * (SLICE_BYTES / 2), __float2half_rn(0.0f));
   out.bias.assign(size_t(L) * H, 0.0f);
   out.inv_scale.assign(L, 1.0f);
@@ -141,8 +144,8 @@ TcPack pack_model_tc(int L, const int* dims, const float* const* W, const float*
       const int src = last ? nfb::pack_last_layer_row(m) : (m < outd ? m : -1);
       if (src >= 0 && src < outd) out.bias[size_t(l) * H + m] = B[l][src];
     }
-    const int nb_count = last ? 1 : 2;
-    const int n_ks = slices_in_layer(l, L) / nb_count;
+    const int nb_count = last ? Cfg::LAST_BLOCKS : 2;
+    const int n_ks = Cfg::slices_in_layer(l, L) / nb_count;
     for (int nb = 0; nb < nb_count; ++nb)  // streaming order of nfb_tc_kernel: N-block major, K-slices inside
       for (int ks = 0; ks < n_ks; ++ks, ++slice) {
         __half* dst = out.w.data() + slice * (SLICE_BYTES / 2);
@@ -158,7 +161,7 @@ TcPack pack_model_tc(int L, const int* dims, const float* const* W, const float*
             const __half hi = __float2half_rn(ws);
             __half v = hi;
             if (l == 0 && ks == 2) v = __float2half_rn(ws - __half2float(hi));
-            dst[(r / 8) * 256 + (kk / 8) * 64 + (r % 8) * 8 + (kk % 8)] = v;
+            dst[(r / 8) * 256 + (kk / 8) * 64 + (r % 8) * 8 + (kk % 8)] = v;  // 8-row group: 4 k-chunks x 128 B
           }
         }
       }
@@ -189,6 +192,21 @@ int64_t small_batch_limit(int h_pad) {
   return h_pad >= 512 ? 512 : h_pad >= 256 ? 1024 : 2048;
 }
 
+template <class Cfg>
+int launch_tc(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream) {
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    NFB_CUDA(cudaFuncSetAttribute(nfb::tc::nfb_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    configured_device = ctx->device;
+  }
+  const long long tiles = (tp.ev.n + nfb::tc::NQT - 1) / nfb::tc::NQT;
+  const int grid = int(std::min<long long>((tiles + 1) & ~1LL, ctx->sm_count & ~1));  // whole CTA pairs
+  nfb::tc::nfb_tc_kernel<Cfg><<<grid, nfb::tc::THREADS, Cfg::SMEM_BYTES, stream>>>(tp);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
 template <int H>
 int launch_small(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
   using Cfg = nfb::SmallCfg<H>;
@@ -211,7 +229,7 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
     return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
   if (variant == NFB_VARIANT_TENSOR_FP16 && !ctx->models[model_id].tc_w)
     return fail(NFB_ERR_UNSUPPORTED_MODEL,
-                "the tensor-core variant exists for 512-wide models with at most %d layers only; model slot %d is not one",
+                "the tensor-core variant exists for 256- and 512-wide models with at most %d layers only; model slot %d is not one",
                 nfb::tc::MAX_TC_LAYERS, model_id);
   if (n < 0) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld is negative", (long long)n);
   if ((in_dtype != NFB_F32 && in_dtype != NFB_F64) || (out_dtype != NFB_F32 && out_dtype != NFB_F64))
@@ -243,24 +261,13 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
   p.in_f64 = (in_dtype == NFB_F64);
   p.out_f64 = (out_dtype == NFB_F64);
   if (variant == NFB_VARIANT_TENSOR_FP16) {
-    static thread_local int tc_configured_device = -1;
-    if (tc_configured_device != ctx->device) {
-      NFB_CUDA(cudaFuncSetAttribute(nfb::tc::nfb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    int(nfb::tc::SMEM_BYTES)));
-      tc_configured_device = ctx->device;
-    }
     nfb::tc::TcParams tp;
     tp.ev = p;
     tp.wblob = m.tc_w;
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
     tp.dbg = ctx->tc_debug;
-    const long long tiles = (n + nfb::tc::NQT - 1) / nfb::tc::NQT;
-    const int grid = int(std::min<long long>((tiles + 1) & ~1LL, ctx->sm_count & ~1));  // whole CTA pairs
-    nfb::tc::nfb_tc_kernel<<<grid, nfb::tc::THREADS, nfb::tc::SMEM_BYTES, stream>>>(tp);
-    NFB_CUDA(cudaGetLastError());
-    ctx->launches += 1;
-    return NFB_OK;
+    return m.h_pad == 512 ? launch_tc<nfb::tc::TcCfg<512>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<256>>(ctx, tp, stream);
   }
   if (n <= small_batch_limit(m.h_pad)) {
     switch (m.h_pad) {
@@ -418,8 +425,9 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
   }
   NFB_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
   NFB_CUDA(cudaMemcpy(m.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (h_pad == 512 && n_layers <= nfb::tc::MAX_TC_LAYERS) {
-    const TcPack tcp = pack_model_tc(n_layers, dims, weights, biases);
+  if ((h_pad == 512 || h_pad == 256) && n_layers <= nfb::tc::MAX_TC_LAYERS) {
+    const TcPack tcp = h_pad == 512 ? pack_model_tc<nfb::tc::TcCfg<512>>(n_layers, dims, weights, biases)
+                                    : pack_model_tc<nfb::tc::TcCfg<256>>(n_layers, dims, weights, biases);
     NFB_CUDA(cudaMalloc(&m.tc_w, tcp.w.size() * sizeof(__half)));
     NFB_CUDA(cudaMalloc(&m.tc_bias, tcp.bias.size() * sizeof(float)));
     NFB_CUDA(cudaMalloc(&m.tc_inv_scale, tcp.inv_scale.size() * sizeof(float)));

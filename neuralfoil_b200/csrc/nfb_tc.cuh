@@ -1,4 +1,5 @@
-// Tensor-core (tcgen05) variant of the fused evaluator, for the 512-wide model (xxxlarge).
+// Tensor-core (tcgen05) variant of the fused evaluator, for the 512-wide (xxxlarge) and 256-wide (xxlarge) models.
+// (Numbers in this header are for H = 512; H = 256 halves N, the activation tile and the tensor-memory columns.)
 //
 // Same per-tile pipeline as nfb_ffma.cuh -- featurise + Mahalanobis in fp64, every layer on chip, fused
 // un-flip / average / decode epilogue -- but each layer is a tcgen05.mma (kind::f16) GEMM:
@@ -33,43 +34,56 @@
 namespace nfb {
 namespace tc {
 
-constexpr int H = 512;                 // hidden width this variant is built for
 constexpr int NT = 128;                // batch rows per tile (MMA M)
 constexpr int NQT = 64;                // queries per tile
 constexpr int K0 = 96;                 // first layer's K after [hi | lo | hi] concatenation (3 x 32)
 constexpr int SLICE_K = 32;            // k per streamed weight slice
-constexpr int SLICE_N = 256;           // output features per slice (MMA N)
-constexpr uint32_t SLICE_BYTES = SLICE_N * SLICE_K * 2;   // 16 KB
 constexpr int STAGES = 4;
 constexpr int ATOM_K = 64;             // fp16 per 128-byte swizzle row
 constexpr uint32_t ATOM_BYTES = NT * 128;                  // 16 KB: 16 row groups x 1024 B
-constexpr uint32_t ACT_BYTES = (H / ATOM_K) * ATOM_BYTES;  // 128 KB
 constexpr int THREADS = 320;
 constexpr int EPI_WARPS = 8, EPI_THREADS = 256;
-
-// shared-memory map (bytes from a 1024-aligned base)
-constexpr uint32_t OFF_ACT = 0;
-constexpr uint32_t OFF_RING = OFF_ACT + ACT_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_RING + STAGES * SLICE_BYTES;     // fp32 [L][512] (+ scales [L])
-constexpr uint32_t BIAS_FLOATS = 7 * H + 16;                       // up to 7 layers (the shipped xxxlarge) + scales
-constexpr uint32_t OFF_MAHA = OFF_BIAS + BIAS_FLOATS * 4;          // fp32 [128]
-constexpr uint32_t OFF_RE = OFF_MAHA + NT * 4;                     // fp32 [64]
-constexpr uint32_t OFF_BARS = OFF_RE + NQT * 4;                    // mbarriers
-constexpr uint32_t OFF_TMEM = OFF_BARS + 16 * 8;
-constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
 constexpr int MAX_TC_LAYERS = 7;
+constexpr int LAST_ROWS = 256;         // the last layer's 224 packed rows, padded to whole N-blocks
+
+// Per hidden width (512: xxxlarge, 256: xxlarge).  A layer always has two N-blocks of H / 2 features.
+template <int H_>
+struct TcCfg {
+  static constexpr int H = H_;
+  static constexpr int SLICE_N = H / 2;                              // output features per slice == MMA N (256 or 128)
+  static constexpr uint32_t SLICE_BYTES = SLICE_N * SLICE_K * 2;     // 16 or 8 KB
+  static constexpr int LAST_BLOCKS = LAST_ROWS / SLICE_N;            // N-blocks of the last layer (1 or 2)
+  static constexpr uint32_t ACT_BYTES = (H / ATOM_K) * ATOM_BYTES;   // 128 or 64 KB
+  static constexpr uint32_t STAGE_BYTES = M_LAST * NT * 4;           // last layer's latents, fp32 [224][128] = 112 KB
+  static constexpr uint32_t TMEM_COLS = H;                           // power of two >= 32
+  static constexpr int PART = H / 4;                                 // features per epilogue warp per half (128 or 64)
+  // shared-memory map (bytes from a 1024-aligned base)
+  static constexpr uint32_t OFF_ACT = 0;
+  static constexpr uint32_t OFF_RING = OFF_ACT + ACT_BYTES;
+  static constexpr uint32_t OFF_BIAS = OFF_RING + STAGES * SLICE_BYTES;   // fp32 [L][H] (+ scales [L] at 7 H)
+  static constexpr uint32_t BIAS_FLOATS = MAX_TC_LAYERS * H + 16;
+  static constexpr uint32_t OFF_MAHA = OFF_BIAS + BIAS_FLOATS * 4;        // fp32 [128]
+  static constexpr uint32_t OFF_RE = OFF_MAHA + NT * 4;                   // fp32 [64]
+  static constexpr uint32_t OFF_BARS = OFF_RE + NQT * 4;                  // mbarriers
+  static constexpr uint32_t OFF_TMEM = OFF_BARS + 16 * 8;
+  // the staging block re-uses the idle activation tile when that is big enough (H = 512), else gets its own room
+  static constexpr uint32_t OFF_STAGE = (ACT_BYTES >= STAGE_BYTES) ? OFF_ACT : ((OFF_TMEM + 16 + 127) & ~127u);
+  static constexpr uint32_t SMEM_BYTES = ((ACT_BYTES >= STAGE_BYTES) ? OFF_TMEM + 16 : OFF_STAGE + STAGE_BYTES) + 1024;
+  static_assert(H == 512 || H == 256, "tensor-core variant: 512- or 256-wide models");
+  static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
+
+  __host__ __device__ static constexpr int slices_in_layer(int l, int L) {
+    return l == 0 ? (K0 / SLICE_K) * 2 : (l == L - 1 ? (H / SLICE_K) * LAST_BLOCKS : (H / SLICE_K) * 2);
+  }
+};
 
 struct TcParams {
   EvalParams ev;            // inputs / outputs / n / n_layers (blob unused)
-  const __half* wblob;      // slices in streaming order, 16 KB each
-  const float* bias;        // [L][512] fp32, last layer in packed row order (224 used)
+  const __half* wblob;      // slices in streaming order, Cfg::SLICE_BYTES each
+  const float* bias;        // [L][H] fp32, last layer in packed row order (224 used)
   const float* inv_scale;   // [L]
   long long* dbg;           // optional: clock64 stamps of CTA 0's second tile (scripts/gpu_debug_tc.py), else NULL
 };
-
-__host__ __device__ constexpr int slices_in_layer(int l, int L) {
-  return l == 0 ? (K0 / SLICE_K) * 2 : (l == L - 1 ? (H / SLICE_K) : (H / SLICE_K) * 2);
-}
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -181,17 +195,20 @@ __device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, 
 // weight traffic (measured: with one CTA per slice stream the MMA phase ran at the 41 B/clk/SM L2 limit, 200 cycles
 // per MMA instead of 128).  Every CTA runs the same number of tiles (surplus tiles are all-padding), so the two
 // rings never diverge.
+template <class Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
+  constexpr int H = Cfg::H, SLICE_N = Cfg::SLICE_N, PART = Cfg::PART;
+  constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES;
   const EvalParams& p = tp.ev;
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* const smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
-  unsigned char* const act = smem + OFF_ACT;
-  unsigned char* const ring = smem + OFF_RING;
-  float* const bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
-  float* const maha = reinterpret_cast<float*>(smem + OFF_MAHA);
-  float* const re_s = reinterpret_cast<float*>(smem + OFF_RE);
-  const uint32_t bar_full = smem_u32(smem + OFF_BARS), bar_empty = bar_full + 8 * STAGES;
+  unsigned char* const act = smem + Cfg::OFF_ACT;
+  unsigned char* const ring = smem + Cfg::OFF_RING;
+  float* const bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+  float* const maha = reinterpret_cast<float*>(smem + Cfg::OFF_MAHA);
+  float* const re_s = reinterpret_cast<float*>(smem + Cfg::OFF_RE);
+  const uint32_t bar_full = smem_u32(smem + Cfg::OFF_BARS), bar_empty = bar_full + 8 * STAGES;
   // Layer pipeline barriers.  "Half" h = features [256 h, 256 h + 256) = TMEM columns of N-block h = K region h
   // (activation atoms 4 h .. 4 h + 3) of the next layer.  The MMA warp walks a layer as four quarters
   //   q1 = (N-block 0, K region 0), q2 = (N-block 0, K region 1), q3 = (N-block 1, K region 0), q4 = (N-block 1, K region 1)
@@ -201,7 +218,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
   const uint32_t bar_d0 = bar_a1 + 8;               // MMA -> epilogue: N-block 0 complete (after q2)
   const uint32_t bar_k0 = bar_d0 + 8;               // MMA -> epilogue: K region 0 no longer read (after q3)
   const uint32_t bar_d1 = bar_k0 + 8;               // MMA -> epilogue: N-block 1 complete, K region 1 no longer read (after q4)
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.n_layers;
@@ -209,10 +226,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
   const uint32_t my_tiles = uint32_t((n_tiles + gridDim.x - 1) / gridDim.x);  // same for every CTA
   const uint32_t cta_rank = cluster_ctarank();
   int slices_per_tile = 0;
-  for (int l = 0; l < L; ++l) slices_per_tile += slices_in_layer(l, L);
+  for (int l = 0; l < L; ++l) slices_per_tile += Cfg::slices_in_layer(l, L);
 
   for (int i = tid; i < L * H; i += THREADS) bias_s[i] = tp.bias[i];
-  if (tid < L) bias_s[7 * H + tid] = tp.inv_scale[tid];
+  if (tid < L) bias_s[MAX_TC_LAYERS * H + tid] = tp.inv_scale[tid];
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -226,7 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
     fence_mbar_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -294,12 +311,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
         ph_a1 ^= 1;
         tc_fence_after();
         issue(0, kh, kt);                                      // q2
-        commit(bar_d0);
         if (l != L - 1) {
+          commit(bar_d0);
           issue(1, 0, kh);                                     // q3
           commit(bar_k0);
           issue(1, kh, kt);                                    // q4
           commit(bar_d1);
+        } else {                                               // last layer: 256 packed rows, one signal when all are done
+          if (Cfg::LAST_BLOCKS == 2) issue(1, 0, kt);
+          commit(bar_d0);
         }
         if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[32 + 2 * l + 1] = clock64();
       }
@@ -353,25 +373,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
       if (stamp) tp.dbg[1] = clock64();
 
       for (int l = 0; l < L - 1; ++l) {
-        const float inv_s = bias_s[7 * H + l];
-        const float* b = bias_s + l * H + part * 128;
+        const float inv_s = bias_s[MAX_TC_LAYERS * H + l];
+        const float* b = bias_s + l * H + part * PART;
         // ---- half 0: N-block 0 is complete after q2; its outputs may only land in K region 0 after q3 ----
         mbar_wait(bar_d0, ph_d0);
         ph_d0 ^= 1;
         tc_fence_after();
         if (stamp) tp.dbg[2 + 2 * l] = clock64();
         {
-          uint32_t w[4][16];
+          uint32_t w[PART / 32][16];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < PART / 32; ++c) {
             uint32_t v[32];
-            tmem_ld32(t_lane + uint32_t(part * 128 + 32 * c), v);
+            tmem_ld32(t_lane + uint32_t(part * PART + 32 * c), v);
             activate(v, b + 32 * c, inv_s, w[c]);
           }
           mbar_wait(bar_k0, ph_k0);
           ph_k0 ^= 1;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) store32(part * 128 + 32 * c, w[c]);
+          for (int c = 0; c < PART / 32; ++c) store32(part * PART + 32 * c, w[c]);
         }
         publish(bar_a0);
         // ---- half 1: N-block 1 complete (and K region 1 free) after q4; overlaps the next layer's q1 ----
@@ -379,24 +399,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
         ph_d1 ^= 1;
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PART / 32; ++c) {
           uint32_t v[32], w[16];
-          tmem_ld32(t_lane + uint32_t(256 + part * 128 + 32 * c), v);
-          activate(v, b + 256 + 32 * c, inv_s, w);
-          store32(256 + part * 128 + 32 * c, w);
+          tmem_ld32(t_lane + uint32_t(H / 2 + part * PART + 32 * c), v);
+          activate(v, b + H / 2 + 32 * c, inv_s, w);
+          store32(H / 2 + part * PART + 32 * c, w);
         }
         publish(bar_a1);
         if (stamp) tp.dbg[3 + 2 * l] = clock64();
       }
 
-      // ---- last layer: latents -> fp32 staging [224 packed rows][128 batch] in the (now idle) activation tile ----
+      // ---- last layer: latents -> fp32 staging [224 packed rows][128 batch] (the idle activation tile when it fits) ----
       mbar_wait(bar_d0, ph_d0);
       ph_d0 ^= 1;
       tc_fence_after();
       if (stamp) tp.dbg[20] = clock64();
       {
-        float* stage = reinterpret_cast<float*>(act);
-        const float inv_s = bias_s[7 * H + (L - 1)];
+        float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_STAGE);
+        const float inv_s = bias_s[MAX_TC_LAYERS * H + (L - 1)];
         const float* b = bias_s + (L - 1) * H;
         // feature ranges: part 0 -> [0, 128), part 1 -> [128, 224)
         const int f_begin = part * 128, f_end = part ? M_LAST : 128;
@@ -435,7 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
   cluster_sync_all();  // nobody leaves while the peer can still multicast into this CTA
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
   }
 }
 

@@ -10,11 +10,12 @@ from oracle.neuralfoil_oracle import Oracle
 extra = {"xxxlarge": synthetic.synthetic_xxxlarge_params()}
 ev = Evaluator(device=0, extra_models=extra)
 orc = Oracle(extra_models=extra)
-for n in (64, 1003):
+for size, n in (("xxxlarge", 64), ("xxxlarge", 1003), ("xxlarge", 64), ("xxlarge", 20000)):
     raw = synthetic.sample_training_distribution(n, seed=42)
-    want, zw = orc.evaluate_raw(raw, "xxxlarge", return_latent=True)
-    ref32 = ev.evaluate_host(raw, "xxxlarge", out_dtype=np.float64)
-    got = ev.evaluate_host(raw, "xxxlarge", out_dtype=np.float64, variant="tensor")
+    want, zw = orc.evaluate_raw(raw, size, return_latent=True)
+    ref32 = ev.evaluate_host(raw, size, out_dtype=np.float64)
+    got = ev.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor")
+    print(size, end=" ")
     d = np.abs(got - want)
     print(f"n={n}: finite {np.isfinite(got).all()}  fp32-path max|d| scalars {[float(np.abs(ref32[i]-want[i]).max()) for i in range(6)]}")
     print("   tensor max|d| scalars", [float(d[i].max()) for i in range(6)])
@@ -25,6 +26,20 @@ for n in (64, 1003):
         print("   sample CL got/want", got[1, :4], want[1, :4])
         print("   sample row 6", got[6, :3], want[6, :3], " row 197", got[197, :3], want[197, :3])
 import torch
+for size, variant in (("xxlarge", "tensor"), ("xxlarge", "fp32")):
+    n = 4_000_000
+    r = torch.from_numpy(synthetic.sample_training_distribution(n, seed=1, dtype=np.float32)).cuda()
+    out = torch.empty((198, n), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        ev.evaluate_device(r, size, out=out, variant=variant)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        ev.evaluate_device(r, size, out=out, variant=variant)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{size} {variant}: {n / (e0.elapsed_time(e1) / 3) / 1e3:.2f} M q/s", flush=True)
+    del r, out
 for variant in ("tensor", "fp32"):
     n = 4_000_000 if variant == "tensor" else 1_000_000
     r = torch.from_numpy(synthetic.sample_training_distribution(n, seed=1, dtype=np.float32)).cuda()

@@ -311,31 +311,34 @@ def test_large_batch_properties(evaluator, oracle, size, n):
 # ---------------------------------------------------------------------------------------------
 # Tensor-core variant (tcgen05, fp16 operands): stated looser tolerance, same exact invariants
 # ---------------------------------------------------------------------------------------------
-def test_tensor_variant_matches_oracle(evaluator, oracle):
-    raw = synthetic.sample_training_distribution(5003, seed=11)
-    want = oracle.evaluate_raw(raw, "xxxlarge")
-    got = evaluator.evaluate_host(raw, "xxxlarge", out_dtype=np.float64, variant="tensor")
-    rep = parity.assert_parity(got, want, raw[19], label="tensor xxxlarge", variant="tensor")
+@pytest.mark.parametrize("size", ["xxlarge", "xxxlarge"])  # xxlarge: the reference's TRAINED weights on the tensor path
+def test_tensor_variant_matches_oracle(evaluator, oracle, size):
+    raw = synthetic.sample_training_distribution(20011, seed=11)
+    want = oracle.evaluate_raw(raw, size)
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor")
+    rep = parity.assert_parity(got, want, raw[19], label=f"tensor {size}", variant="tensor")
     # and it must be a real low-precision evaluation of the same network, not something else: close to the fp32 path
-    ref = evaluator.evaluate_host(raw, "xxxlarge", out_dtype=np.float64)
-    assert np.nanmax(np.abs(got[1] - ref[1])) <= 1.5e-2 and rep["median_rel"] > 1e-6
+    ref = evaluator.evaluate_host(raw, size, out_dtype=np.float64)
+    assert np.nanmax(np.abs(got[1] - ref[1])) <= 7.5e-2 and rep["median_rel"] > 1e-6  # CL = z / 2, worst-case latent 0.15
 
 
 @pytest.mark.parametrize("n", [1, 3, 63, 64, 65, 127, 129, 1000])
-def test_tensor_variant_ragged_batch_sizes(evaluator, oracle, n):
+@pytest.mark.parametrize("size", ["xxlarge", "xxxlarge"])
+def test_tensor_variant_ragged_batch_sizes(evaluator, oracle, size, n):
     raw = synthetic.sample_training_distribution(n, seed=300 + n)
-    got = evaluator.evaluate_host(raw, "xxxlarge", out_dtype=np.float64, variant="tensor")
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor")
     assert got.shape == (198, n)
-    parity.assert_parity(got, oracle.evaluate_raw(raw, "xxxlarge"), raw[19], check_distribution=False, variant="tensor")
+    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], check_distribution=False, variant="tensor")
 
 
 def test_tensor_variant_golden_and_far_ood(evaluator, golden_dir):
     """The reference-written fixture (incl. alpha = +-90, +-180, Re = 1e2, 1e10) with the tensor tolerance; finite everywhere."""
     g = np.load(golden_dir / "golden_all_sizes.npz")
     raw = g["raw"]
-    got = evaluator.evaluate_host(raw, "xxxlarge", out_dtype=np.float64, variant="tensor")
-    assert np.isfinite(got[:6]).all()
-    parity.assert_parity(got, g["out_xxxlarge"], raw[19], check_distribution=False, variant="tensor")
+    for size in ("xxlarge", "xxxlarge"):
+        got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor")
+        assert np.isfinite(got[:6]).all(), size
+        parity.assert_parity(got, g[f"out_{size}"], raw[19], check_distribution=False, variant="tensor", label=size)
 
 
 def test_tensor_variant_invariants_are_exact(evaluator):
@@ -344,19 +347,19 @@ def test_tensor_variant_invariants_are_exact(evaluator):
 
     w = np.array([0.15, 0.20, 0.15, 0.20, 0.15, 0.20, 0.15, 0.15])
     sym = dict(upper_weights=w, lower_weights=-w, leading_edge_weight=0.0, TE_thickness=0.002)
-    aero = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size="xxxlarge", variant="tensor")
-    assert aero["CL"][0] == 0.0 and aero["CM"][0] == 0.0 and aero["Top_Xtr"][0] == aero["Bot_Xtr"][0]
-
     n = 200_000
     raw = synthetic.sample_training_distribution(n, seed=4).astype(np.float32)
     d_raw = torch.from_numpy(raw).cuda()
-    out = evaluator.evaluate_device(d_raw, "xxxlarge", variant="tensor")
-    out_m = evaluator.evaluate_device(torch.from_numpy(mirrored(raw)).cuda(), "xxxlarge", variant="tensor")
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).cuda()
-    out_p = evaluator.evaluate_device(d_raw[:, perm].contiguous(), "xxxlarge", variant="tensor")
-    torch.cuda.synchronize()
-    assert torch.equal(out_p, out[:, perm])
-    np.testing.assert_array_equal(out_m.cpu().numpy(), unmirror_outputs(out.cpu().numpy()))
+    for size in ("xxlarge", "xxxlarge"):
+        aero = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size=size, variant="tensor")
+        assert aero["CL"][0] == 0.0 and aero["CM"][0] == 0.0 and aero["Top_Xtr"][0] == aero["Bot_Xtr"][0]
+        out = evaluator.evaluate_device(d_raw, size, variant="tensor")
+        out_m = evaluator.evaluate_device(torch.from_numpy(mirrored(raw)).cuda(), size, variant="tensor")
+        out_p = evaluator.evaluate_device(d_raw[:, perm].contiguous(), size, variant="tensor")
+        torch.cuda.synchronize()
+        assert torch.equal(out_p, out[:, perm]), size
+        np.testing.assert_array_equal(out_m.cpu().numpy(), unmirror_outputs(out.cpu().numpy()))
 
 
 def test_tensor_variant_refuses_other_models(evaluator):
