@@ -37,7 +37,8 @@ def test_pth_round_trip(tmp_path):
         assert sorted(f.files) == sorted(f"net.{i}.{p}" for i in (0, 2, 4) for p in ("weight", "bias"))
         np.testing.assert_array_equal(f["net.2.weight"], model.net[2].weight.detach().numpy())
         assert f["net.4.bias"].dtype == np.float32
-    dst = weights.install(npz, weights_dir=tmp_path)
+    (tmp_path / "installed").mkdir()
+    dst = weights.install(npz, weights_dir=tmp_path / "installed")
     assert dst.name == "nn-tiny.npz" and dst.exists()
 
 
