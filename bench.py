@@ -47,6 +47,10 @@ FLOP_PER_QUERY = {  # 2 twins x 2 x sum(in * out) over the layers, unpadded
     "xxsmall": 52_032, "xsmall": 61_248, "small": 89_856, "medium": 106_240,
     "large": 310_784, "xlarge": 376_320, "xxlarge": 1_276_928, "xxxlarge": 5_699_584,
 }
+# DRAM traffic per query of the two xxxlarge kernels, from one `ncu --set full` capture each of this file's own
+# command at 10 M queries (profiles/r1_ncu_full_xxxlarge_ffma.txt / _tensor.txt: dram__bytes_read.sum + dram__bytes_write.sum
+# = 8.900 GB and 8.805 GB per launch; algorithmic 8.840 GB).  Reported as roofline.traffic, scaled to the run's n.
+NCU_TRAFFIC_BYTES_PER_QUERY = {("xxxlarge", "fp32"): 890.0, ("xxxlarge", "tensor"): 880.5}
 METRIC = "airfoil_queries_per_sec"
 UNIT = "queries/s"
 
@@ -342,6 +346,11 @@ def main():
                     "peak_source": hbm_src},
             "traffic": None,
         }
+        per_q = NCU_TRAFFIC_BYTES_PER_QUERY.get((size, variant))
+        if per_q is not None:
+            roofline["traffic"] = per_q * n
+            roofline["traffic_note"] = ("bytes per launch = ncu-measured DRAM bytes per query (10 M-query capture, profiles/) x this run's "
+                                        f"queries per launch; algorithmic {BYTES_PER_QUERY * n}")
         if variant == "tensor":
             roofline.update({"bound": "tensor", "kernel": "nfb_tc_kernel", "peak": bf16_peak, "peak_source": bf16_src,
                              "frac": achieved_tflops / bf16_peak})
