@@ -62,8 +62,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--model-size", default="xxxlarge")
-    ap.add_argument("--variant", choices=("fp32", "tensor"), default="fp32",
-                    help="kernel behind value/e2e: fp32 FFMA (reference accuracy) or tcgen05 fp16-operand (xxxlarge only)")
+    ap.add_argument("--variant", choices=("fp32", "tensor", "tensor_fp32"), default="fp32",
+                    help="kernel behind value/e2e: fp32 FFMA (reference accuracy), tcgen05 one-term fp16 (TF32 class) "
+                         "or tcgen05 three-term fp16 split (fp32 class); the tensor kernels exist for xxlarge / xxxlarge")
     ap.add_argument("--no-tensor-extra", action="store_true", help="skip the extra tensor-variant measurement")
     ap.add_argument("--queries-per-gpu", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0 = auto)")
@@ -290,30 +291,35 @@ def main():
         assert abs(host_check - checksum) <= 1e-6 * max(1.0, abs(checksum)), (host_check, checksum)
 
     # ---- the other variant, briefly (xxxlarge only): reported beside the headline, never mixed into it ----
-    tensor_extra = None
-    if size == "xxxlarge" and variant == "fp32" and not args.no_tensor_extra:
+    def measure_other(other: str) -> dict:
         for _ in range(3):
-            ev.evaluate_device(raw_dev, size, out=out_dev, variant="tensor")
+            ev.evaluate_device(raw_dev, size, out=out_dev, variant=other)
         barrier()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         for _ in range(args.steps):
-            ev.evaluate_device(raw_dev, size, out=out_dev, variant="tensor")
+            ev.evaluate_device(raw_dev, size, out=out_dev, variant=other)
         t1e.record()
         barrier()
         t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
-        tensor_extra = {"ms_per_step": t_ms, "value": world * n / (t_ms * 1e-3)}
+        extra = {"ms_per_step": t_ms, "value": world * n / (t_ms * 1e-3)}
         if not args.no_e2e:
-            ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant="tensor")
+            ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant=other)
             barrier()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant="tensor")
+                ev.evaluate_host_into(raw_host.numpy(), size, out_host.numpy(), variant=other)
                 _ = float(out_host[1, 0])
             torch.cuda.synchronize()
             te = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-            tensor_extra["e2e"] = {"value": world * n / te, "unit": UNIT, "ms_per_step": te * 1e3,
-                                   "note": "same nfb_eval_host path; bound by the PCIe device->host copy of 792 B/query"}
+            extra["e2e"] = {"value": world * n / te, "unit": UNIT, "ms_per_step": te * 1e3,
+                            "note": "same nfb_eval_host path (pinned host in/out); PCIe device->host moves 792 B/query"}
+        return extra
+
+    tensor_extra = tensor_fp32_extra = None
+    if size in ("xxxlarge", "xxlarge") and variant == "fp32" and not args.no_tensor_extra:
+        tensor_fp32_extra = measure_other("tensor_fp32")
+        tensor_extra = measure_other("tensor")
 
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
@@ -329,10 +335,19 @@ def main():
         if tensor_extra is not None:
             tf = FLOP_PER_QUERY[size] * n / (tensor_extra["ms_per_step"] * 1e-3) / 1e12  # per GPU: n is per rank
             tensor_extra.update({
-                "unit": UNIT, "kernel": "nfb_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM)",
-                "accuracy": "TF32-class: latent error median 3e-4; see DESIGN.md section 5 and tests/parity.py (tensor tolerance)",
+                "unit": UNIT, "kernel": "nfb_tc_kernel<H, 1> (tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM)",
+                "accuracy": "TF32-class: median relative error 3e-4; tests/parity.py 'tensor' tolerance",
                 "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
                              "peak_source": bf16_src}})
+        if tensor_fp32_extra is not None:
+            tf = 3 * FLOP_PER_QUERY[size] * n / (tensor_fp32_extra["ms_per_step"] * 1e-3) / 1e12
+            tensor_fp32_extra.update({
+                "unit": UNIT, "kernel": "nfb_tc_kernel<H, 3> (three fp16 MMAs per product: a_hi w_hi + a_lo w_hi + a_hi w_lo)",
+                "accuracy": "fp32-class worst case (fp32 tolerance), median relative error 2e-6 .. 4e-6; tests/parity.py 'tensor_fp32'",
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
+                             "peak_source": bf16_src,
+                             "note": "achieved counts the 3 tensor-core MACs issued per algorithmic MAC; the 512-wide tile is M = 64, "
+                                     "which the tensor core runs at half rate"}})
         roofline = {
             "bound": "fp32",
             "kernel": "nfb_ffma_kernel",
@@ -351,9 +366,11 @@ def main():
             roofline["traffic"] = per_q * n
             roofline["traffic_note"] = ("bytes per launch = ncu-measured DRAM bytes per query (10 M-query capture, profiles/) x this run's "
                                         f"queries per launch; algorithmic {BYTES_PER_QUERY * n}")
-        if variant == "tensor":
+        if variant != "fp32":
+            mult = 3 if variant == "tensor_fp32" else 1
             roofline.update({"bound": "tensor", "kernel": "nfb_tc_kernel", "peak": bf16_peak, "peak_source": bf16_src,
-                             "frac": achieved_tflops / bf16_peak})
+                             "achieved": mult * achieved_tflops, "frac": mult * achieved_tflops / bf16_peak,
+                             "tensor_macs_per_algorithmic_mac": mult})
             roofline.pop("frac_of_nominal_74.4", None)
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
@@ -365,10 +382,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if variant == "fp32" else "f16 operands / f32 accumulate",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tensor": "f16 operands / f32 accumulate",
+                                                       "tensor_fp32": "2 x f16 split operands / f32 accumulate"}[variant],
             "data": "synthetic", "config": workload_config(args, weights_note),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "tensor_variant": tensor_extra,
+            "tensor_fp32_variant": tensor_fp32_extra,
             "checksum_first_1000": checksum,
         }
         print(json.dumps(line), flush=True)

@@ -51,8 +51,11 @@ enum nfb_dtype { NFB_F32 = 0, NFB_F64 = 1 };
  *   FP32_FFMA    fp32 CUDA-core path, every model size; the correctness reference (tolerance: tests/parity.py).
  *   TENSOR_FP16  tcgen05 tensor-core path for 512- and 256-wide models (xxxlarge, xxlarge): fp16 operands (TF32's
  *                mantissa), fp32 accumulation in tensor memory, first layer fp32-exact; looser, stated tolerance.
- *                Other models: NFB_ERR_UNSUPPORTED_MODEL. */
-enum nfb_variant { NFB_VARIANT_FP32_FFMA = 0, NFB_VARIANT_TENSOR_FP16 = 1 };
+ *                Other models: NFB_ERR_UNSUPPORTED_MODEL.
+ *   TENSOR_FP16X3  the same tcgen05 kernel with every operand split into two fp16 halves and three MMAs per
+ *                product (a_hi w_hi + a_lo w_hi + a_hi w_lo), fp32 accumulation: fp32-class accuracy, held to the
+ *                FP32_FFMA tolerance.  Same model restriction. */
+enum nfb_variant { NFB_VARIANT_FP32_FFMA = 0, NFB_VARIANT_TENSOR_FP16 = 1, NFB_VARIANT_TENSOR_FP16X3 = 2 };
 
 typedef struct nfb_context nfb_context;
 

@@ -16,7 +16,8 @@ N_OUTPUT_ROWS = 198
 F32, F64 = 0, 1
 VARIANT_FP32_FFMA = 0
 VARIANT_TENSOR_FP16 = 1
-VARIANTS = {"fp32": VARIANT_FP32_FFMA, "tensor": VARIANT_TENSOR_FP16}
+VARIANT_TENSOR_FP16X3 = 2
+VARIANTS = {"fp32": VARIANT_FP32_FFMA, "tensor": VARIANT_TENSOR_FP16, "tensor_fp32": VARIANT_TENSOR_FP16X3}
 
 OK = 0
 ERR_INVALID_ARGUMENT = -1

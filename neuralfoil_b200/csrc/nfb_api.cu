@@ -40,8 +40,10 @@ struct Model {
   int h_pad = 0;  // 64 / 128 / 256 / 512
   int dims[NFB_MAX_LAYERS + 1] = {0};
   float* blob = nullptr;  // device
-  // tensor-core variant (512-wide models only): fp16 weight slices, fp32 biases, per-layer 1 / scale
+  // tensor-core variants (256- / 512-wide models): fp16 weight slices of the one-term and the three-term kernels,
+  // fp32 biases, per-layer 1 / scale
   __half* tc_w = nullptr;
+  __half* tc3_w = nullptr;
   float* tc_bias = nullptr;
   float* tc_inv_scale = nullptr;
 };
@@ -145,26 +147,27 @@ TcPack pack_model_tc(int L, const int* dims, const float* const* W, const float*
       if (src >= 0 && src < outd) out.bias[size_t(l) * H + m] = B[l][src];
     }
     const int nb_count = last ? Cfg::LAST_BLOCKS : 2;
-    const int n_ks = Cfg::slices_in_layer(l, L) / nb_count;
+    const int n_ks = Cfg::k_slices(l);
     for (int nb = 0; nb < nb_count; ++nb)  // streaming order of nfb_tc_kernel: N-block major, K-slices inside
-      for (int ks = 0; ks < n_ks; ++ks, ++slice) {
-        __half* dst = out.w.data() + slice * (SLICE_BYTES / 2);
-        for (int r = 0; r < SLICE_N; ++r) {
-          const int m = nb * SLICE_N + r;
-          const int src = last ? (m < nfb::M_LAST ? nfb::pack_last_layer_row(m) : -1) : (m < outd ? m : -1);
-          if (src < 0 || src >= outd) continue;
-          for (int kk = 0; kk < SLICE_K; ++kk) {
-            // layer 0: k-slices are [W_hi | W_hi | W_lo] over the same 32 (25 used) inputs
-            const int k = (l == 0) ? kk : ks * SLICE_K + kk;
-            if (k >= in) continue;
-            const float ws = W[l][size_t(src) * in + k] * scale;
-            const __half hi = __float2half_rn(ws);
-            __half v = hi;
-            if (l == 0 && ks == 2) v = __float2half_rn(ws - __half2float(hi));
-            dst[(r / 8) * 256 + (kk / 8) * 64 + (r % 8) * 8 + (kk % 8)] = v;  // 8-row group: 4 k-chunks x 128 B
+      for (int ks = 0; ks < n_ks; ++ks)
+        for (int part = 0; part < Cfg::SLOTS_PER_STEP; ++part, ++slice) {  // SPLIT = 3: the W_hi slice, then the W_lo slice
+          __half* dst = out.w.data() + slice * (SLICE_BYTES / 2);
+          for (int r = 0; r < SLICE_N; ++r) {
+            const int m = nb * SLICE_N + r;
+            const int src = last ? (m < nfb::M_LAST ? nfb::pack_last_layer_row(m) : -1) : (m < outd ? m : -1);
+            if (src < 0 || src >= outd) continue;
+            for (int kk = 0; kk < SLICE_K; ++kk) {
+              // SPLIT = 1, layer 0: the k-slices are [W_hi | W_hi | W_lo] over the same 32 (25 used) inputs
+              const int k = (Cfg::SPLIT == 1 && l == 0) ? kk : ks * SLICE_K + kk;
+              if (k >= in) continue;
+              const float ws = W[l][size_t(src) * in + k] * scale;
+              const __half hi = __float2half_rn(ws);
+              const bool want_lo = (Cfg::SPLIT == 3) ? (part == 1) : (l == 0 && ks == 2);
+              const __half v = want_lo ? __float2half_rn(ws - __half2float(hi)) : hi;
+              dst[(r / 8) * 256 + (kk / 8) * 64 + (r % 8) * 8 + (kk % 8)] = v;  // 8-row group: 4 k-chunks x 128 B
+            }
           }
         }
-      }
   }
   return out;
 }
@@ -199,7 +202,7 @@ int launch_tc(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream
     NFB_CUDA(cudaFuncSetAttribute(nfb::tc::nfb_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
     configured_device = ctx->device;
   }
-  const long long tiles = (tp.ev.n + nfb::tc::NQT - 1) / nfb::tc::NQT;
+  const long long tiles = (tp.ev.n + Cfg::NQT - 1) / Cfg::NQT;
   const int grid = int(std::min<long long>((tiles + 1) & ~1LL, ctx->sm_count & ~1));  // whole CTA pairs
   nfb::tc::nfb_tc_kernel<Cfg><<<grid, nfb::tc::THREADS, Cfg::SMEM_BYTES, stream>>>(tp);
   NFB_CUDA(cudaGetLastError());
@@ -225,9 +228,9 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   if (!ctx->models[model_id].loaded) return fail(NFB_ERR_NOT_LOADED, "model slot %d is empty", model_id);
   if (!ctx->have_distribution)
     return fail(NFB_ERR_NOT_LOADED, "nfb_set_distribution has not been called");
-  if (variant != NFB_VARIANT_FP32_FFMA && variant != NFB_VARIANT_TENSOR_FP16)
+  if (variant != NFB_VARIANT_FP32_FFMA && variant != NFB_VARIANT_TENSOR_FP16 && variant != NFB_VARIANT_TENSOR_FP16X3)
     return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
-  if (variant == NFB_VARIANT_TENSOR_FP16 && !ctx->models[model_id].tc_w)
+  if (variant != NFB_VARIANT_FP32_FFMA && !ctx->models[model_id].tc_w)
     return fail(NFB_ERR_UNSUPPORTED_MODEL,
                 "the tensor-core variant exists for 256- and 512-wide models with at most %d layers only; model slot %d is not one",
                 nfb::tc::MAX_TC_LAYERS, model_id);
@@ -260,14 +263,17 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
   p.n_layers = m.n_layers;
   p.in_f64 = (in_dtype == NFB_F64);
   p.out_f64 = (out_dtype == NFB_F64);
-  if (variant == NFB_VARIANT_TENSOR_FP16) {
+  if (variant == NFB_VARIANT_TENSOR_FP16 || variant == NFB_VARIANT_TENSOR_FP16X3) {
+    const bool x3 = (variant == NFB_VARIANT_TENSOR_FP16X3);
     nfb::tc::TcParams tp;
     tp.ev = p;
-    tp.wblob = m.tc_w;
+    tp.wblob = x3 ? m.tc3_w : m.tc_w;
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
     tp.dbg = ctx->tc_debug;
-    return m.h_pad == 512 ? launch_tc<nfb::tc::TcCfg<512>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<256>>(ctx, tp, stream);
+    if (m.h_pad == 512)
+      return x3 ? launch_tc<nfb::tc::TcCfg<512, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<512, 1>>(ctx, tp, stream);
+    return x3 ? launch_tc<nfb::tc::TcCfg<256, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<256, 1>>(ctx, tp, stream);
   }
   if (n <= small_batch_limit(m.h_pad)) {
     switch (m.h_pad) {
@@ -347,6 +353,7 @@ void nfb_destroy(nfb_context* ctx) {
   for (auto& m : ctx->models) {
     if (m.blob) cudaFree(m.blob);
     if (m.tc_w) cudaFree(m.tc_w);
+    if (m.tc3_w) cudaFree(m.tc3_w);
     if (m.tc_bias) cudaFree(m.tc_bias);
     if (m.tc_inv_scale) cudaFree(m.tc_inv_scale);
   }
@@ -419,6 +426,7 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
     NFB_CUDA(cudaDeviceSynchronize());
     NFB_CUDA(cudaFree(m.blob));
     if (m.tc_w) NFB_CUDA(cudaFree(m.tc_w));
+    if (m.tc3_w) NFB_CUDA(cudaFree(m.tc3_w));
     if (m.tc_bias) NFB_CUDA(cudaFree(m.tc_bias));
     if (m.tc_inv_scale) NFB_CUDA(cudaFree(m.tc_inv_scale));
     m = Model();
@@ -426,8 +434,12 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
   NFB_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
   NFB_CUDA(cudaMemcpy(m.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   if ((h_pad == 512 || h_pad == 256) && n_layers <= nfb::tc::MAX_TC_LAYERS) {
-    const TcPack tcp = h_pad == 512 ? pack_model_tc<nfb::tc::TcCfg<512>>(n_layers, dims, weights, biases)
-                                    : pack_model_tc<nfb::tc::TcCfg<256>>(n_layers, dims, weights, biases);
+    const TcPack tcp = h_pad == 512 ? pack_model_tc<nfb::tc::TcCfg<512, 1>>(n_layers, dims, weights, biases)
+                                    : pack_model_tc<nfb::tc::TcCfg<256, 1>>(n_layers, dims, weights, biases);
+    const TcPack tcp3 = h_pad == 512 ? pack_model_tc<nfb::tc::TcCfg<512, 3>>(n_layers, dims, weights, biases)
+                                     : pack_model_tc<nfb::tc::TcCfg<256, 3>>(n_layers, dims, weights, biases);
+    NFB_CUDA(cudaMalloc(&m.tc3_w, tcp3.w.size() * sizeof(__half)));
+    NFB_CUDA(cudaMemcpy(m.tc3_w, tcp3.w.data(), tcp3.w.size() * sizeof(__half), cudaMemcpyHostToDevice));
     NFB_CUDA(cudaMalloc(&m.tc_w, tcp.w.size() * sizeof(__half)));
     NFB_CUDA(cudaMalloc(&m.tc_bias, tcp.bias.size() * sizeof(float)));
     NFB_CUDA(cudaMalloc(&m.tc_inv_scale, tcp.inv_scale.size() * sizeof(float)));

@@ -1,80 +1,96 @@
-// Tensor-core (tcgen05) variant of the fused evaluator, for the 512-wide (xxxlarge) and 256-wide (xxlarge) models.
-// (Numbers in this header are for H = 512; H = 256 halves N, the activation tile and the tensor-memory columns.)
+// Tensor-core (tcgen05) variants of the fused evaluator for the 512-wide (xxxlarge) and 256-wide (xxlarge) models.
 //
 // Same per-tile pipeline as nfb_ffma.cuh -- featurise + Mahalanobis in fp64, every layer on chip, fused
 // un-flip / average / decode epilogue -- but each layer is a tcgen05.mma (kind::f16) GEMM:
 //
-//   D[128 batch rows][features] (fp32, TMEM)  +=  A[128 batch rows][K] (fp16, smem)  x  B[features][K] (fp16, smem)
+//   D[batch rows][features] (fp32, TMEM)  +=  A[batch rows][K] (fp16, smem)  x  B[features][K] (fp16, smem)
 //
-//   * A = the activation tile: 64 queries + their 64 flipped twins, K-major, SWIZZLE_128B atoms (8 rows x 128 B),
-//     written by the epilogue warps themselves (thread = batch row, 16-byte conflict-free stores).
-//   * B = weights, fp16, pre-packed on the host as K-major no-swizzle core matrices, 256 output features x 32 k
-//     per 16 KB slice, streamed L2 -> smem by a producer thread through a 4-deep TMA ring (cp.async.bulk + mbarrier).
-//   * D = 128 lanes x 512 columns = the whole tensor memory; one elected thread issues the MMAs (N = 256, K = 16).
-//   * Layers are software-pipelined in halves of 256 features (see the barrier comment in the kernel): the epilogue
-//     of a layer's first half runs under the MMAs of its second half, and the next layer's first MMAs run under the
-//     epilogue of the second half; the activation tile stays single-buffered.
+//   * A = the activation tile (queries in the first half of the rows, their flipped twins in the second), K-major,
+//     SWIZZLE_128B atoms (8 rows x 128 B), written by the epilogue warps themselves (thread = batch row, 16-byte
+//     conflict-free stores).
+//   * B = weights, fp16 with a per-layer power-of-two scale, pre-packed on the host as K-major no-swizzle core
+//     matrices, H/2 output features x 32 k per slice, streamed L2 -> smem by a producer thread through a 4-deep TMA
+//     ring; the kernel runs as clusters of two CTAs that each fetch half of every slice and multicast it to both.
+//   * D in tensor memory, two N-blocks of H/2 features; the whole MMA warp runs the issue loop, one elected lane issues.
+//   * Layers are software-pipelined in halves (see the barrier comment in the kernel); the activation tile stays
+//     single-buffered.
 //
-// Why this orientation and this precision (measured with scripts/umma_probe.cu on B200):
-// a tcgen05.mma with M = 128 costs ~111-124 cycles however small N is, so N must be large (256 features), which
-// puts the batch on the TMEM lanes; 128 rows x 512 features of activations only fit in shared memory at 2 bytes
-// per element.  fp16 (round to nearest, saturating) has TF32's 10-bit mantissa; the first layer, whose inputs are
-// the physical features, is made fp32-exact by K-concatenation: [x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo].
-// Accuracy is therefore "TF32 class" (latent error median 3e-4, CL p99.9 4e-3); the fp32 FFMA kernel stays the
-// correctness reference.  Weights carry a per-layer power-of-two scale (keeps small weights out of fp16
-// subnormals), undone exactly in the epilogue.
+// Two precisions (template parameter SPLIT):
+//   SPLIT = 1  "tensor":  operands rounded to fp16 (TF32's 10-bit mantissa), one MMA per product, 128 rows per tile,
+//              SiLU by tanh.approx.  First layer fp32-exact by K-concatenation [x_hi | x_lo | x_hi].[W_hi | W_hi | W_lo].
+//              TF32-class accuracy (latent error median 3e-4); tolerance: tests/parity.py, "tensor".
+//   SPLIT = 3  "tensor_fp32":  every operand split into two fp16 halves, a = a_hi + a_lo (22 significant bits), and
+//              each product evaluated as a_hi.w_hi + a_lo.w_hi + a_hi.w_lo with fp32 accumulation -- three MMAs.
+//              A NumPy emulation gives error statistics indistinguishable from an fp32 evaluation, so this
+//              variant is held to the fp32 tolerance.  Both activation halves must be on chip: 2 x 2 bytes per element,
+//              so a 512-wide tile is 64 rows (M = 64 MMAs: same 128 cycles as M = 128, i.e. half rate -- measured,
+//              scripts/umma_probe_m64.cu), a 256-wide tile 128 rows.  Accurate SiLU (expf), as the FFMA kernel.
 //
-// Roles (320 threads): warp 0 lane 0 = TMA producer; warp 1 = TMEM allocator, lane 0 = MMA issuer; warps 2..9 =
-// epilogue (thread = batch row 32 * (warp % 4) + lane; the two warps of a row quarter split each half's 256 features).
+// Why these shapes (measured with scripts/umma_probe*.cu on B200): with A in shared memory an
+// M = 128 MMA never takes less than ~115 cycles however small N is, so N must be large, which puts the batch on the
+// TMEM lanes; an MMA issued from a lone `if (lane == 0)` thread costs ~220 cycles in address arithmetic and election
+// loops, so the issue loop is warp-converged with uniform descriptors (128 cycles per M128 N256 K16 MMA = the peak).
+//
+// Roles (320 threads): warp 0 lane 0 = TMA producer; warp 1 = TMEM allocator + MMA issue; warps 2..9 = epilogue
+// (thread = batch row; the two warps of a TMEM lane quarter split each half's features).
 #pragma once
 #include <cuda_fp16.h>
 
-#include "nfb_ffma.cuh"  // featurise maths, decode_and_store, PTX helpers
+#include "nfb_ffma.cuh"  // featurise_query, silu, decode_and_store, PTX helpers
 
 namespace nfb {
 namespace tc {
 
-constexpr int NT = 128;                // batch rows per tile (MMA M)
-constexpr int NQT = 64;                // queries per tile
-constexpr int K0 = 96;                 // first layer's K after [hi | lo | hi] concatenation (3 x 32)
 constexpr int SLICE_K = 32;            // k per streamed weight slice
 constexpr int STAGES = 4;
 constexpr int ATOM_K = 64;             // fp16 per 128-byte swizzle row
-constexpr uint32_t ATOM_BYTES = NT * 128;                  // 16 KB: 16 row groups x 1024 B
 constexpr int THREADS = 320;
 constexpr int EPI_WARPS = 8, EPI_THREADS = 256;
 constexpr int MAX_TC_LAYERS = 7;
 constexpr int LAST_ROWS = 256;         // the last layer's 224 packed rows, padded to whole N-blocks
 
-// Per hidden width (512: xxxlarge, 256: xxlarge).  A layer always has two N-blocks of H / 2 features.
-template <int H_>
+template <int H_, int SPLIT_>
 struct TcCfg {
   static constexpr int H = H_;
+  static constexpr int SPLIT = SPLIT_;
+  static constexpr int ROWS = (SPLIT == 3 && H == 512) ? 64 : 128;   // batch rows per tile == MMA M
+  static constexpr int NQT = ROWS / 2;                               // queries per tile
+  static constexpr int K0 = (SPLIT == 3) ? 32 : 96;                  // first layer's K ([hi | lo | hi] concatenation when SPLIT = 1)
   static constexpr int SLICE_N = H / 2;                              // output features per slice == MMA N (256 or 128)
   static constexpr uint32_t SLICE_BYTES = SLICE_N * SLICE_K * 2;     // 16 or 8 KB
+  static constexpr int SLOTS_PER_STEP = (SPLIT == 3) ? 2 : 1;        // ring slots per (N-block, k-slice): W_hi then W_lo
   static constexpr int LAST_BLOCKS = LAST_ROWS / SLICE_N;            // N-blocks of the last layer (1 or 2)
-  static constexpr uint32_t ACT_BYTES = (H / ATOM_K) * ATOM_BYTES;   // 128 or 64 KB
-  static constexpr uint32_t STAGE_BYTES = M_LAST * NT * 4;           // last layer's latents, fp32 [224][128] = 112 KB
-  static constexpr uint32_t TMEM_COLS = H;                           // power of two >= 32
+  static constexpr uint32_t ATOM_BYTES = ROWS * 128;                 // ROWS/8 row groups x 1024 B
+  static constexpr uint32_t A_BYTES = (H / ATOM_K) * ATOM_BYTES;     // one fp16 copy of the activation tile
+  static constexpr uint32_t ACT_BYTES = A_BYTES * (SPLIT == 3 ? 2 : 1);  // [A_hi][A_lo]
+  static constexpr uint32_t STAGE_BYTES = M_LAST * ROWS * 4;         // last layer's latents, fp32 [224][ROWS]
+  // SPLIT = 3 keeps the two small product terms in an accumulator of their own (D_lo): the tensor core truncates
+  // (rounds toward zero) at every accumulation, so a bias of ~half an ulp of D builds up per MMA; with the ~2^-11
+  // smaller a_lo.w_hi / a_hi.w_lo blocks accumulated separately, the big accumulator sees 32 truncations per
+  // 512-long dot product instead of 96 (measured: median relative error 1.3e-5 -> see DESIGN.md).  D_lo lives in the
+  // lanes an M = 64 tile leaves free (lane + 16, "interleaved" allocation), or in the upper 256 columns (H = 256).
+  static constexpr uint32_t D_LO_OFFSET = (SPLIT != 3) ? 0u : (ROWS == 64 ? (16u << 16) : 256u);
+  static constexpr uint32_t TMEM_COLS = (SPLIT == 3 && ROWS == 128) ? 512 : H;   // power of two >= 32
   static constexpr int PART = H / 4;                                 // features per epilogue warp per half (128 or 64)
   // shared-memory map (bytes from a 1024-aligned base)
   static constexpr uint32_t OFF_ACT = 0;
   static constexpr uint32_t OFF_RING = OFF_ACT + ACT_BYTES;
-  static constexpr uint32_t OFF_BIAS = OFF_RING + STAGES * SLICE_BYTES;   // fp32 [L][H] (+ scales [L] at 7 H)
+  static constexpr uint32_t OFF_BIAS = OFF_RING + STAGES * SLICE_BYTES;   // fp32 [L][H] (+ scales [L] at MAX_TC_LAYERS * H)
   static constexpr uint32_t BIAS_FLOATS = MAX_TC_LAYERS * H + 16;
-  static constexpr uint32_t OFF_MAHA = OFF_BIAS + BIAS_FLOATS * 4;        // fp32 [128]
-  static constexpr uint32_t OFF_RE = OFF_MAHA + NT * 4;                   // fp32 [64]
+  static constexpr uint32_t OFF_MAHA = OFF_BIAS + BIAS_FLOATS * 4;        // fp32 [ROWS]
+  static constexpr uint32_t OFF_RE = OFF_MAHA + ROWS * 4;                 // fp32 [NQT]
   static constexpr uint32_t OFF_BARS = OFF_RE + NQT * 4;                  // mbarriers
   static constexpr uint32_t OFF_TMEM = OFF_BARS + 16 * 8;
-  // the staging block re-uses the idle activation tile when that is big enough (H = 512), else gets its own room
+  // the staging block re-uses the idle activation tile when that is big enough, else gets its own room
   static constexpr uint32_t OFF_STAGE = (ACT_BYTES >= STAGE_BYTES) ? OFF_ACT : ((OFF_TMEM + 16 + 127) & ~127u);
   static constexpr uint32_t SMEM_BYTES = ((ACT_BYTES >= STAGE_BYTES) ? OFF_TMEM + 16 : OFF_STAGE + STAGE_BYTES) + 1024;
-  static_assert(H == 512 || H == 256, "tensor-core variant: 512- or 256-wide models");
+  static_assert(H == 512 || H == 256, "tensor-core variants: 512- or 256-wide models");
+  static_assert(SPLIT == 1 || SPLIT == 3, "one MMA per product, or the three-term fp16 split");
   static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
 
-  __host__ __device__ static constexpr int slices_in_layer(int l, int L) {
-    return l == 0 ? (K0 / SLICE_K) * 2 : (l == L - 1 ? (H / SLICE_K) * LAST_BLOCKS : (H / SLICE_K) * 2);
-  }
+  __host__ __device__ static constexpr int k_slices(int l) { return (l == 0 ? K0 : H) / SLICE_K; }
+  __host__ __device__ static constexpr int n_blocks(int l, int L) { return l == L - 1 ? LAST_BLOCKS : 2; }
+  __host__ __device__ static constexpr int slices_in_layer(int l, int L) { return k_slices(l) * n_blocks(l, L) * SLOTS_PER_STEP; }
 };
 
 struct TcParams {
@@ -153,13 +169,16 @@ __device__ __forceinline__ float silu_fast(float x) {
   return fmaf(h, t, h);
 }
 
-// byte offset of the 16-byte chunk holding k..k+7 of batch row n in the activation tile (SWIZZLE_128B K-major atoms)
+// byte offset of the 16-byte chunk holding k..k+7 of batch row n in an activation copy (SWIZZLE_128B K-major atoms)
+template <class Cfg>
 __device__ __forceinline__ uint32_t act_chunk_offset(int n, int k) {
   const int atom = k >> 6, chunk = (k & 63) >> 3;
-  return uint32_t(atom) * ATOM_BYTES + uint32_t(n >> 3) * 1024 + uint32_t(n & 7) * 128 + uint32_t((chunk ^ (n & 7)) << 4);
+  return uint32_t(atom) * Cfg::ATOM_BYTES + uint32_t(n >> 3) * 1024 + uint32_t(n & 7) * 128 + uint32_t((chunk ^ (n & 7)) << 4);
 }
 
-// ---- featurise one batch row (nfb::featurise_query), then the first layer's [x_hi | x_lo | x_hi] fp16 row ----------
+// ---- featurise one batch row (nfb::featurise_query), then write the first layer's fp16 input row -------------------
+//   SPLIT = 1: [x_hi | x_lo | x_hi] in k = 0..95 of the single copy;  SPLIT = 3: x_hi -> A_hi, x_lo -> A_lo, k = 0..31
+template <class Cfg>
 __device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, bool valid, bool twin, int n,
                                               unsigned char* act, float* maha, float* re_s) {
   double x[N_IN];
@@ -181,40 +200,44 @@ __device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, 
     lo[i] = pack_f16x2(l0, l1);
   }
 #pragma unroll
-  for (int c8 = 0; c8 < 4; ++c8) {  // k = 0..31 hi, 32..63 lo, 64..95 hi
+  for (int c8 = 0; c8 < 4; ++c8) {
     const uint4 vh = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);
     const uint4 vl = make_uint4(lo[4 * c8], lo[4 * c8 + 1], lo[4 * c8 + 2], lo[4 * c8 + 3]);
-    *reinterpret_cast<uint4*>(act + act_chunk_offset(n, 8 * c8)) = vh;
-    *reinterpret_cast<uint4*>(act + act_chunk_offset(n, 32 + 8 * c8)) = vl;
-    *reinterpret_cast<uint4*>(act + act_chunk_offset(n, 64 + 8 * c8)) = vh;
+    if constexpr (Cfg::SPLIT == 1) {  // k = 0..31 hi, 32..63 lo, 64..95 hi
+      *reinterpret_cast<uint4*>(act + act_chunk_offset<Cfg>(n, 8 * c8)) = vh;
+      *reinterpret_cast<uint4*>(act + act_chunk_offset<Cfg>(n, 32 + 8 * c8)) = vl;
+      *reinterpret_cast<uint4*>(act + act_chunk_offset<Cfg>(n, 64 + 8 * c8)) = vh;
+    } else {
+      *reinterpret_cast<uint4*>(act + act_chunk_offset<Cfg>(n, 8 * c8)) = vh;
+      *reinterpret_cast<uint4*>(act + Cfg::A_BYTES + act_chunk_offset<Cfg>(n, 8 * c8)) = vl;
+    }
   }
 }
 
 // Launched as clusters of two CTAs (two SMs of one TPC).  The pair walks the same slice sequence; each CTA's
 // producer fetches HALF of every weight slice and multicasts it into both CTAs' rings, which halves the L2 -> SM
-// weight traffic (measured: with one CTA per slice stream the MMA phase ran at the 41 B/clk/SM L2 limit, 200 cycles
-// per MMA instead of 128).  Every CTA runs the same number of tiles (surplus tiles are all-padding), so the two
-// rings never diverge.
+// weight traffic.  Every CTA runs the same number of tiles (surplus tiles are all-padding), so the two rings never
+// diverge.
 template <class Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_kernel(const TcParams tp) {
-  constexpr int H = Cfg::H, SLICE_N = Cfg::SLICE_N, PART = Cfg::PART;
-  constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES;
+  constexpr int H = Cfg::H, SLICE_N = Cfg::SLICE_N, PART = Cfg::PART, ROWS = Cfg::ROWS, NQT = Cfg::NQT, SPLIT = Cfg::SPLIT;
+  constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES, ATOM_BYTES = Cfg::ATOM_BYTES;
   const EvalParams& p = tp.ev;
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* const smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
-  unsigned char* const act = smem + Cfg::OFF_ACT;
+  unsigned char* const act = smem + Cfg::OFF_ACT;   // A_hi (the only copy when SPLIT = 1), then A_lo
   unsigned char* const ring = smem + Cfg::OFF_RING;
   float* const bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
   float* const maha = reinterpret_cast<float*>(smem + Cfg::OFF_MAHA);
   float* const re_s = reinterpret_cast<float*>(smem + Cfg::OFF_RE);
   const uint32_t bar_full = smem_u32(smem + Cfg::OFF_BARS), bar_empty = bar_full + 8 * STAGES;
-  // Layer pipeline barriers.  "Half" h = features [256 h, 256 h + 256) = TMEM columns of N-block h = K region h
-  // (activation atoms 4 h .. 4 h + 3) of the next layer.  The MMA warp walks a layer as four quarters
+  // Layer pipeline barriers.  "Half" h = features [H/2 h, H/2 h + H/2) = TMEM columns of N-block h = K region h
+  // (the second half of the activation atoms when h = 1) of the next layer.  The MMA warp walks a layer as four quarters
   //   q1 = (N-block 0, K region 0), q2 = (N-block 0, K region 1), q3 = (N-block 1, K region 0), q4 = (N-block 1, K region 1)
   // so that the epilogue of half 0 overlaps q3/q4 and the next layer's q1 overlaps the epilogue of half 1.
-  const uint32_t bar_a0 = bar_empty + 8 * STAGES;   // epilogue -> MMA: K region 0 of the layer input is in smem, TMEM cols 0..255 drained
-  const uint32_t bar_a1 = bar_a0 + 8;               // ... K region 1, TMEM cols 256..511
+  const uint32_t bar_a0 = bar_empty + 8 * STAGES;   // epilogue -> MMA: K region 0 of the layer input is in smem, N-block 0's TMEM drained
+  const uint32_t bar_a1 = bar_a0 + 8;               // ... K region 1, N-block 1's TMEM
   const uint32_t bar_d0 = bar_a1 + 8;               // MMA -> epilogue: N-block 0 complete (after q2)
   const uint32_t bar_k0 = bar_d0 + 8;               // MMA -> epilogue: K region 0 no longer read (after q3)
   const uint32_t bar_d1 = bar_k0 + 8;               // MMA -> epilogue: N-block 1 complete, K region 1 no longer read (after q4)
@@ -269,10 +292,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    // The whole warp runs this loop converged and one elected lane issues: descriptors then live in uniform
-    // registers.  (Issuing from a lone `if (lane == 0)` thread costs ~220 cycles per MMA in address arithmetic,
-    // R2UR moves and election loops -- measured with scripts/umma_probe_f16.cu -- against 128 for the MMA itself.)
-    const uint32_t idesc = (1u << 4) | (uint32_t(SLICE_N >> 3) << 17) | (uint32_t(NT >> 4) << 24);  // f16 x f16 -> f32
+    // The whole warp runs this loop converged and one elected lane issues: descriptors then live in uniform registers.
+    const uint32_t idesc = (1u << 4) | (uint32_t(SLICE_N >> 3) << 17) | (uint32_t(ROWS >> 4) << 24);  // f16 x f16 -> f32
     // descriptor high words: A = SWIZZLE_128B K-major (SBO 1024 B), B = no-swizzle core matrices (LBO 128 B, SBO 512 B)
     const uint64_t a_hi = (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
     const uint64_t b_hi = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
@@ -280,18 +301,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
     const uint32_t a0 = (smem_u32(act) >> 4) & 0x3FFF, b0 = (smem_u32(ring) >> 4) & 0x3FFF;
     uint32_t it = 0, ph_a0 = 0, ph_a1 = 0;
     auto issue = [&](int nb, int ks_begin, int ks_end) {  // K-slices [ks_begin, ks_end) of N-block nb, in streaming order
-      for (int ks = ks_begin; ks < ks_end; ++ks, ++it) {
-        const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
-        tc_fence_after();
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
         const uint32_t a_lo = a0 + uint32_t(ks >> 1) * (ATOM_BYTES >> 4) + uint32_t(ks & 1) * 4;  // 64 B per 32 k
-        const uint32_t b_lo = b0 + s * (SLICE_BYTES >> 4);
-        if (elect_one_sync()) {
-          umma_f16(tmem + nb * SLICE_N, a_hi | a_lo, b_hi | b_lo, idesc, ks != 0);
-          umma_f16(tmem + nb * SLICE_N, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
-          umma_commit_multicast(bar_empty + 8 * s, uint16_t(3));  // slot is free once BOTH CTAs' MMAs have read it
+#pragma unroll
+        for (int half = 0; half < Cfg::SLOTS_PER_STEP; ++half, ++it) {  // SPLIT = 3: the W_hi slot, then the W_lo slot
+          const uint32_t s = it & (STAGES - 1), ph = (it / STAGES) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t b_lo = b0 + s * (SLICE_BYTES >> 4);
+          const uint32_t d = tmem + nb * SLICE_N, d_small = d + Cfg::D_LO_OFFSET;
+          if (elect_one_sync()) {
+            if (SPLIT == 1 || half == 0) {
+              umma_f16(d, a_hi | a_lo, b_hi | b_lo, idesc, ks != 0);
+              umma_f16(d, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
+              if (SPLIT == 3) {  // a_lo . w_hi -> D_lo
+                constexpr uint32_t LO = Cfg::A_BYTES >> 4;
+                umma_f16(d_small, a_hi | (a_lo + LO), b_hi | b_lo, idesc, ks != 0);
+                umma_f16(d_small, a_hi | (a_lo + LO + 2), b_hi | (b_lo + 16), idesc, 1u);
+              }
+            } else {             // a_hi . w_lo -> D_lo
+              umma_f16(d_small, a_hi | a_lo, b_hi | b_lo, idesc, 1u);
+              umma_f16(d_small, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
+            }
+            umma_commit_multicast(bar_empty + 8 * s, uint16_t(3));  // slot is free once BOTH CTAs' MMAs have read it
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     };
     auto commit = [&](uint32_t bar) {
@@ -300,8 +335,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
     };
     for (uint32_t t = 0; t < my_tiles; ++t)
       for (int l = 0; l < L; ++l) {
-        const int kt = (l == 0) ? K0 / SLICE_K : H / SLICE_K;  // K-slices of the layer
-        const int kh = (l == 0) ? kt : kt / 2;                 // of which in K region 0 (the first layer's 96 inputs all are)
+        const int kt = Cfg::k_slices(l);                       // K-slices of the layer
+        const int kh = (l == 0) ? kt : kt / 2;                 // of which in K region 0 (the first layer's inputs all are)
         mbar_wait(bar_a0, ph_a0);
         ph_a0 ^= 1;
         tc_fence_after();
@@ -325,28 +360,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
       }
   } else {
     // ============================ epilogue warps ============================
-    const int e = warp - 2, q = warp & 3, part = e >> 2;  // part: which 128 of a half's 256 features this warp takes
-    const int n = 32 * q + lane;             // batch row == TMEM lane
+    const int e = warp - 2, q = warp & 3, part = e >> 2;  // part: which PART of a half's features this warp takes
+    // batch row of this thread == TMEM lane 32 q + lane.  M = 64 tiles only occupy lanes 0..15 of each quarter.
+    const bool has_row = (ROWS == 128) || lane < 16;
+    const int n = (ROWS == 128) ? 32 * q + lane : 16 * q + (lane & 15);
     const int et = (e << 5) | lane;          // 0..255
     const uint32_t t_lane = tmem + (uint32_t(32 * q) << 16);
     const bool vec_ok =
         p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
                   : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     uint32_t ph_d0 = 0, ph_k0 = 0, ph_d1 = 0;
-    // scale, bias, SiLU and fp16 packing of 32 accumulators
-    auto activate = [&](const uint32_t (&v)[32], const float* b, float inv_s, uint32_t (&w)[16]) {
+    // scale, bias, SiLU and fp16 packing of 32 accumulators: w = the fp16 activations (the hi halves when SPLIT = 3),
+    // wl = their fp16 remainders (SPLIT = 3 only)
+    auto activate = [&](const uint32_t (&v)[32], const float* b, float inv_s, uint32_t (&w)[16], uint32_t (&wl)[16]) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float x0 = silu_fast(fmaf(__uint_as_float(v[2 * i]), inv_s, b[2 * i]));
-        const float x1 = silu_fast(fmaf(__uint_as_float(v[2 * i + 1]), inv_s, b[2 * i + 1]));
-        w[i] = pack_f16x2(x0, x1);
+        const float y0 = fmaf(__uint_as_float(v[2 * i]), inv_s, b[2 * i]);
+        const float y1 = fmaf(__uint_as_float(v[2 * i + 1]), inv_s, b[2 * i + 1]);
+        if constexpr (SPLIT == 1) {
+          w[i] = pack_f16x2(silu_fast(y0), silu_fast(y1));
+        } else {
+          const float x0 = silu(y0), x1 = silu(y1);
+          w[i] = pack_f16x2(x0, x1);
+          const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+          wl[i] = pack_f16x2(x0 - back.x, x1 - back.y);
+        }
       }
     };
-    auto store32 = [&](int k, const uint32_t (&w)[16]) {  // 32 consecutive features k..k+31 of row n
+    // 32 accumulator columns of this thread's row; SPLIT = 3 adds the separately accumulated small terms (D_lo)
+    auto load_acc = [&](uint32_t col, uint32_t (&v)[32]) {
+      tmem_ld32(t_lane + col, v);
+      if constexpr (SPLIT == 3) {
+        if constexpr (ROWS == 64) {  // lanes 16..31 of the quarter hold D_lo of rows lane - 16
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8)
-        *reinterpret_cast<uint4*>(act + act_chunk_offset(n, k + 8 * c8)) =
-            make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
+          for (int i = 0; i < 32; ++i)
+            v[i] = __float_as_uint(__uint_as_float(v[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), 16));
+        } else {
+          uint32_t u[32];
+          tmem_ld32(t_lane + col + Cfg::D_LO_OFFSET, u);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+        }
+      }
+    };
+    auto store32 = [&](int k, const uint32_t (&w)[16], const uint32_t (&wl)[16]) {  // 32 consecutive features k..k+31 of row n
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const uint32_t off = act_chunk_offset<Cfg>(n, k + 8 * c8);
+        *reinterpret_cast<uint4*>(act + off) = make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
+        if constexpr (SPLIT == 3)
+          *reinterpret_cast<uint4*>(act + Cfg::A_BYTES + off) = make_uint4(wl[4 * c8], wl[4 * c8 + 1], wl[4 * c8 + 2], wl[4 * c8 + 3]);
+      }
     };
     auto publish = [&](uint32_t bar) {  // my smem writes -> async proxy, my TMEM reads are done; tell the MMA warp
       tc_fence_before();
@@ -359,10 +423,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
       const long long tile_q0 = tile * NQT;
       const bool stamp = tp.dbg && blockIdx.x == 0 && t == 1 && e == 0 && lane == 0;
       if (stamp) tp.dbg[0] = clock64();
-      if (part == 0) {  // 128 threads featurise the 128 rows (row n: query n, row 64 + n: its twin)
+      if (part == 0 && has_row) {  // one thread per batch row (row n: query n, row NQT + n: its twin)
         const bool twin = n >= NQT;
         const long long qi = tile_q0 + (twin ? n - NQT : n);
-        featurise_row(p, qi, qi < p.n, twin, n, act, maha, re_s);
+        featurise_row<Cfg>(p, qi, qi < p.n, twin, n, act, maha, re_s);
       }
       fence_async_smem();
       __syncwarp();
@@ -380,18 +444,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
         ph_d0 ^= 1;
         tc_fence_after();
         if (stamp) tp.dbg[2 + 2 * l] = clock64();
-        {
-          uint32_t w[PART / 32][16];
+        if constexpr (SPLIT == 1) {
+          uint32_t w[PART / 32][16], unused[16];
 #pragma unroll
           for (int c = 0; c < PART / 32; ++c) {
             uint32_t v[32];
-            tmem_ld32(t_lane + uint32_t(part * PART + 32 * c), v);
-            activate(v, b + 32 * c, inv_s, w[c]);
+            load_acc(uint32_t(part * PART + 32 * c), v);
+            activate(v, b + 32 * c, inv_s, w[c], unused);
           }
           mbar_wait(bar_k0, ph_k0);
           ph_k0 ^= 1;
 #pragma unroll
-          for (int c = 0; c < PART / 32; ++c) store32(part * PART + 32 * c, w[c]);
+          for (int c = 0; c < PART / 32; ++c) store32(part * PART + 32 * c, w[c], unused);
+        } else {
+          // (hi and lo halves of a whole PART do not fit in registers: keep the first chunk, then stream)
+          uint32_t w0[16], wl0[16];
+          {
+            uint32_t v[32];
+            load_acc(uint32_t(part * PART), v);
+            activate(v, b, inv_s, w0, wl0);
+          }
+          mbar_wait(bar_k0, ph_k0);
+          ph_k0 ^= 1;
+          if (has_row) store32(part * PART, w0, wl0);
+#pragma unroll 1
+          for (int c = 1; c < PART / 32; ++c) {
+            uint32_t v[32], w[16], wl[16];
+            load_acc(uint32_t(part * PART + 32 * c), v);
+            activate(v, b + 32 * c, inv_s, w, wl);
+            if (has_row) store32(part * PART + 32 * c, w, wl);
+          }
         }
         publish(bar_a0);
         // ---- half 1: N-block 1 complete (and K region 1 free) after q4; overlaps the next layer's q1 ----
@@ -400,16 +482,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < PART / 32; ++c) {
-          uint32_t v[32], w[16];
-          tmem_ld32(t_lane + uint32_t(H / 2 + part * PART + 32 * c), v);
-          activate(v, b + H / 2 + 32 * c, inv_s, w);
-          store32(H / 2 + part * PART + 32 * c, w);
+          uint32_t v[32], w[16], wl[16];
+          load_acc(uint32_t(H / 2 + part * PART + 32 * c), v);
+          activate(v, b + H / 2 + 32 * c, inv_s, w, wl);
+          if (has_row) store32(H / 2 + part * PART + 32 * c, w, wl);
         }
         publish(bar_a1);
         if (stamp) tp.dbg[3 + 2 * l] = clock64();
       }
 
-      // ---- last layer: latents -> fp32 staging [224 packed rows][128 batch] (the idle activation tile when it fits) ----
+      // ---- last layer: latents -> fp32 staging [224 packed rows][ROWS] (the idle activation tile when it fits) ----
       mbar_wait(bar_d0, ph_d0);
       ph_d0 ^= 1;
       tc_fence_after();
@@ -423,9 +505,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
 #pragma unroll 1
         for (int c0 = f_begin; c0 < f_end; c0 += 32) {
           uint32_t v[32];
-          tmem_ld32(t_lane + uint32_t(c0), v);
+          load_acc(uint32_t(c0), v);
+          if (has_row) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) stage[(c0 + i) * NT + n] = fmaf(__uint_as_float(v[i]), inv_s, b[c0 + i]);
+            for (int i = 0; i < 32; ++i) stage[(c0 + i) * ROWS + n] = fmaf(__uint_as_float(v[i]), inv_s, b[c0 + i]);
+          }
         }
         tc_fence_before();
         named_bar_sync(1, EPI_THREADS);
@@ -435,8 +519,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
           float acc[4][8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 y = *reinterpret_cast<const float4*>(stage + (4 * g + i) * NT + qb);
-            const float4 f = *reinterpret_cast<const float4*>(stage + (4 * g + i) * NT + NQT + qb);
+            const float4 y = *reinterpret_cast<const float4*>(stage + (4 * g + i) * ROWS + qb);
+            const float4 f = *reinterpret_cast<const float4*>(stage + (4 * g + i) * ROWS + NQT + qb);
             acc[i][0] = y.x; acc[i][1] = y.y; acc[i][2] = y.z; acc[i][3] = y.w;
             acc[i][4] = f.x; acc[i][5] = f.y; acc[i][6] = f.z; acc[i][7] = f.w;
           }

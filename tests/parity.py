@@ -56,6 +56,15 @@ def _tau(out: np.ndarray, Re: np.ndarray) -> np.ndarray:
 #   * worst case: no element is off by more than a latent error of 0.15 (measured 0.10; these are far-from-training
 #     queries whose pre-activations reach the hundreds, where 10 mantissa bits lose the most).
 # (For scale: the networks' own mean error against XFoil is CL 0.012, ln CD 0.020, CM 0.002 -- reference README.md:127.)
+# The three-term tensor variant ("tensor_fp32": a_hi w_hi + a_lo w_hi + a_hi w_lo, fp16 halves, fp32 accumulation) is
+# held to the fp32 criterion's WORST-CASE bound unchanged (LATENT_ATOL = 2.5e-4; measured worst error / tolerance 0.08 ..
+# 0.53).  Its typical error is ~4x the FFMA kernel's, because the tensor core truncates (rounds toward zero) at each of
+# the 32 accumulation steps of a 512-long dot product where FFMA rounds to nearest: measured median relative error
+# 1.6e-6 (trained xxlarge) .. 4.1e-6 (synthetic xxxlarge), 84 .. 92 % of elements within rtol 1e-5.  Stated distribution
+# bound for this variant: median relative error <= 1e-5 (BASELINE.json's figure), >= 75 % of elements within rtol 1e-5.
+TENSOR_FP32_MEDIAN_REL = 1e-5
+TENSOR_FP32_FRAC_1E5 = 0.75
+
 TENSOR_LATENT_ATOL = 3e-2
 TENSOR_WORST_FACTOR = 5.0   # worst case = TENSOR_WORST_FACTOR * TENSOR_LATENT_ATOL = 0.15 in latent space
 TENSOR_BULK_FRACTION = 1e-4
@@ -115,6 +124,11 @@ def assert_parity(got, want, Re, check_distribution: bool = True, label: str = "
         return rep
     rep = error_report(got, want, re)
     assert rep["n_bad"] == 0, f"{label}: {rep}"
+    if variant == "tensor_fp32":
+        if check_distribution:
+            assert rep["median_rel"] <= TENSOR_FP32_MEDIAN_REL, f"{label}: {rep}"
+            assert rep["frac_rel_le_1e-5"] >= TENSOR_FP32_FRAC_1E5, f"{label}: {rep}"
+        return rep
     if check_distribution:
         assert rep["median_rel"] <= 2e-6, f"{label}: {rep}"
         assert rep["frac_rel_le_1e-5"] >= 0.92, f"{label}: {rep}"

@@ -413,3 +413,49 @@ def test_entry_points_agree_on_gpu(evaluator, tmp_path):
         np.testing.assert_allclose(a[key], d[key], rtol=1e-5, atol=1e-6, err_msg=key)
     sweep = evaluator.get_aero_from_airfoil(af, alpha=np.linspace(-5, 10, 31), Re=2e6)
     assert sweep["CL"].shape == (31,) and np.all(np.diff(sweep["CL"][:20]) > 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# Three-term tensor variant ("tensor_fp32"): the fp32 worst-case tolerance, its own distribution bound
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", ["xxlarge", "xxxlarge"])
+def test_tensor_fp32_variant_matches_oracle(evaluator, oracle, size):
+    raw = synthetic.sample_training_distribution(20011, seed=11)
+    want = oracle.evaluate_raw(raw, size)
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor_fp32")
+    rep = parity.assert_parity(got, want, raw[19], label=f"tensor_fp32 {size}", variant="tensor_fp32")
+    x1 = parity.error_report(evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor"), want, raw[19])
+    assert rep["median_rel"] < 0.1 * x1["median_rel"]  # two orders of magnitude tighter than the one-term variant
+
+
+@pytest.mark.parametrize("n", [1, 3, 31, 32, 33, 63, 64, 65, 129, 1000])
+@pytest.mark.parametrize("size", ["xxlarge", "xxxlarge"])
+def test_tensor_fp32_variant_ragged_batch_sizes(evaluator, oracle, size, n):
+    raw = synthetic.sample_training_distribution(n, seed=500 + n)
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor_fp32")
+    assert got.shape == (198, n)
+    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], check_distribution=False, variant="tensor_fp32")
+
+
+def test_tensor_fp32_variant_golden_and_invariants(evaluator, golden_dir):
+    import torch
+
+    g = np.load(golden_dir / "golden_all_sizes.npz")
+    raw = g["raw"]
+    w = np.array([0.15, 0.20, 0.15, 0.20, 0.15, 0.20, 0.15, 0.15])
+    sym = dict(upper_weights=w, lower_weights=-w, leading_edge_weight=0.0, TE_thickness=0.002)
+    n = 100_000
+    big = synthetic.sample_training_distribution(n, seed=6).astype(np.float32)
+    d_big = torch.from_numpy(big).cuda()
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(2)).cuda()
+    for size in ("xxlarge", "xxxlarge"):
+        got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor_fp32")
+        parity.assert_parity(got, g[f"out_{size}"], raw[19], check_distribution=False, variant="tensor_fp32", label=size)
+        aero = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size=size, variant="tensor_fp32")
+        assert aero["CL"][0] == 0.0 and aero["CM"][0] == 0.0 and aero["Top_Xtr"][0] == aero["Bot_Xtr"][0]
+        out = evaluator.evaluate_device(d_big, size, variant="tensor_fp32")
+        out_m = evaluator.evaluate_device(torch.from_numpy(mirrored(big)).cuda(), size, variant="tensor_fp32")
+        out_p = evaluator.evaluate_device(d_big[:, perm].contiguous(), size, variant="tensor_fp32")
+        torch.cuda.synchronize()
+        assert torch.equal(out_p, out[:, perm]), size
+        np.testing.assert_array_equal(out_m.cpu().numpy(), unmirror_outputs(out.cpu().numpy()))
