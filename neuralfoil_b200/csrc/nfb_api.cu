@@ -13,6 +13,7 @@
 #include "nfb_ffma.cuh"
 #include "nfb_small.cuh"
 #include "nfb_tc.cuh"
+#include "nfb_tc2.cuh"
 
 namespace {
 
@@ -210,6 +211,24 @@ int launch_tc(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream
   return NFB_OK;
 }
 
+// the three-term kernel on CTA pairs (nfb_tc2.cuh)
+template <class Cfg>
+int launch_tc2(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream) {
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    NFB_CUDA(cudaFuncSetAttribute(nfb::tc2::nfb_tc2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    configured_device = ctx->device;
+  }
+  const long long tiles = (tp.ev.n + Cfg::NQT - 1) / Cfg::NQT;
+  static const char* grid_env = getenv("NFB_TC2_GRID");  // contention experiments only
+  const int max_grid = grid_env ? atoi(grid_env) : ctx->sm_count;
+  const int grid = int(std::min<long long>((tiles + 1) & ~1LL, max_grid & ~1));  // whole CTA pairs
+  nfb::tc2::nfb_tc2_kernel<Cfg><<<grid, nfb::tc::THREADS, Cfg::SMEM_BYTES, stream>>>(tp);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
 template <int H>
 int launch_small(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
   using Cfg = nfb::SmallCfg<H>;
@@ -271,8 +290,11 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
     tp.dbg = ctx->tc_debug;
-    if (m.h_pad == 512)
+    if (m.h_pad == 512) {
+      static const bool one_sm = getenv("NFB_TC3_ONE_SM") != nullptr;  // A/B experiments: the M = 64 one-SM kernel
+      if (x3 && !one_sm) return launch_tc2<nfb::tc2::Tc2Cfg<512>>(ctx, tp, stream);
       return x3 ? launch_tc<nfb::tc::TcCfg<512, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<512, 1>>(ctx, tp, stream);
+    }
     return x3 ? launch_tc<nfb::tc::TcCfg<256, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<256, 1>>(ctx, tp, stream);
   }
   if (n <= small_batch_limit(m.h_pad)) {
