@@ -335,19 +335,19 @@ def main():
         if tensor_extra is not None:
             tf = FLOP_PER_QUERY[size] * n / (tensor_extra["ms_per_step"] * 1e-3) / 1e12  # per GPU: n is per rank
             tensor_extra.update({
-                "unit": UNIT, "kernel": "nfb_tc_kernel<H, 1> (tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM)",
+                "unit": UNIT, "kernel": "nfb_tc2_kernel<H, 1> (tcgen05 cta_group::2 kind::f16 on CTA pairs, fp16 operands, fp32 accumulate in TMEM)",
                 "accuracy": "TF32-class: median relative error 3e-4; tests/parity.py 'tensor' tolerance",
                 "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
                              "peak_source": bf16_src}})
         if tensor_fp32_extra is not None:
             tf = 3 * FLOP_PER_QUERY[size] * n / (tensor_fp32_extra["ms_per_step"] * 1e-3) / 1e12
             tensor_fp32_extra.update({
-                "unit": UNIT, "kernel": "nfb_tc_kernel<H, 3> (three fp16 MMAs per product: a_hi w_hi + a_lo w_hi + a_hi w_lo)",
+                "unit": UNIT, "kernel": "nfb_tc2_kernel<H, 3> (tcgen05 cta_group::2 on CTA pairs; three fp16 MMAs per product: a_hi w_hi + a_lo w_hi + a_hi w_lo)",
                 "accuracy": "fp32-class worst case (fp32 tolerance), median relative error 2e-6 .. 4e-6; tests/parity.py 'tensor_fp32'",
                 "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tf / bf16_peak,
                              "peak_source": bf16_src,
-                             "note": "achieved counts the 3 tensor-core MACs issued per algorithmic MAC; the 512-wide tile is M = 64, "
-                                     "which the tensor core runs at half rate"}})
+                             "note": "achieved counts the 3 tensor-core MACs issued per algorithmic MAC; the 512-wide tile is 64 rows per CTA, "
+                                     "run at full rate as half of a pair-wide M = 128 MMA"}})
         roofline = {
             "bound": "fp32",
             "kernel": "nfb_ffma_kernel",
@@ -368,7 +368,7 @@ def main():
                                         f"queries per launch; algorithmic {BYTES_PER_QUERY * n}")
         if variant != "fp32":
             mult = 3 if variant == "tensor_fp32" else 1
-            roofline.update({"bound": "tensor", "kernel": "nfb_tc_kernel", "peak": bf16_peak, "peak_source": bf16_src,
+            roofline.update({"bound": "tensor", "kernel": "nfb_tc2_kernel", "peak": bf16_peak, "peak_source": bf16_src,
                              "achieved": mult * achieved_tflops, "frac": mult * achieved_tflops / bf16_peak,
                              "tensor_macs_per_algorithmic_mac": mult})
             roofline.pop("frac_of_nominal_74.4", None)

@@ -211,7 +211,7 @@ int launch_tc(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream
   return NFB_OK;
 }
 
-// the three-term kernel on CTA pairs (nfb_tc2.cuh)
+// the tensor-core kernels on CTA pairs (nfb_tc2.cuh)
 template <class Cfg>
 int launch_tc2(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream) {
   static thread_local int configured_device = -1;
@@ -290,11 +290,14 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
     tp.dbg = ctx->tc_debug;
-    if (m.h_pad == 512) {
-      static const bool one_sm = getenv("NFB_TC3_ONE_SM") != nullptr;  // A/B experiments: the M = 64 one-SM kernel
-      if (x3 && !one_sm) return launch_tc2<nfb::tc2::Tc2Cfg<512>>(ctx, tp, stream);
-      return x3 ? launch_tc<nfb::tc::TcCfg<512, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<512, 1>>(ctx, tp, stream);
+    static const bool one_sm = getenv("NFB_TC_ONE_SM") != nullptr;  // A/B experiments: the one-SM kernels of nfb_tc.cuh
+    if (!one_sm) {
+      if (m.h_pad == 512)
+        return x3 ? launch_tc2<nfb::tc2::Tc2Cfg<512, 3>>(ctx, tp, stream) : launch_tc2<nfb::tc2::Tc2Cfg<512, 1>>(ctx, tp, stream);
+      return x3 ? launch_tc2<nfb::tc2::Tc2Cfg<256, 3>>(ctx, tp, stream) : launch_tc2<nfb::tc2::Tc2Cfg<256, 1>>(ctx, tp, stream);
     }
+    if (m.h_pad == 512)
+      return x3 ? launch_tc<nfb::tc::TcCfg<512, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<512, 1>>(ctx, tp, stream);
     return x3 ? launch_tc<nfb::tc::TcCfg<256, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<256, 1>>(ctx, tp, stream);
   }
   if (n <= small_batch_limit(m.h_pad)) {
