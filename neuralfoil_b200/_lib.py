@@ -7,9 +7,12 @@ present, the calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libneuralfoil_b200.so"
+if os.environ.get("NFB_LIB_PATH"):  # A/B experiments only: another build of the same library
+    LIB_PATH = Path(os.environ["NFB_LIB_PATH"])
 
 N_RAW_ROWS = 23
 N_OUTPUT_ROWS = 198

@@ -45,6 +45,8 @@ struct Model {
   // fp32 biases, per-layer 1 / scale
   __half* tc_w = nullptr;
   __half* tc3_w = nullptr;
+  __half* tc2_w = nullptr;   // the CTA-pair kernels' streams (nfb_tc2.cuh): one-term, three-term
+  __half* tc2_w3 = nullptr;
   float* tc_bias = nullptr;
   float* tc_inv_scale = nullptr;
 };
@@ -173,6 +175,59 @@ TcPack pack_model_tc(int L, const int* dims, const float* const* W, const float*
   return out;
 }
 
+// Weight streams of the CTA-pair kernels (nfb_tc2.cuh): for each CTA rank, the ring slots of one tile in the order the
+// kernel consumes them -- layer, N-block, K sweep position (Cfg::k_slice_at) -- each position this rank's HALF_N rows of
+// the W_hi slice (and of the W_lo slice when SPLIT = 3), K-major no-swizzle core matrices as above.  Same per-layer
+// scale as pack_model_tc (whose biases and 1 / scale the kernels share).
+template <class Cfg>
+std::vector<__half> pack_model_tc2(int L, const int* dims, const float* const* W) {
+  using nfb::tc::SLICE_K;
+  constexpr int HALF_N = Cfg::HALF_N, BLOCK_N = Cfg::BLOCK_N, PARTS = (Cfg::SPLIT == 3) ? 2 : 1;
+  size_t slots = 0;
+  for (int l = 0; l < L; ++l) slots += Cfg::slots_in_layer(l, L);
+  std::vector<__half> out(2 * slots * (Cfg::SLOT_BYTES / 2), __float2half_rn(0.0f));
+  for (int rank = 0; rank < 2; ++rank) {
+    size_t slot = 0;
+    for (int l = 0; l < L; ++l) {
+      const int in = dims[l], outd = dims[l + 1];
+      const bool last = (l == L - 1);
+      float wmax = 0.0f;
+      for (size_t i = 0; i < size_t(in) * outd; ++i) wmax = std::max(wmax, std::fabs(W[l][i]));
+      int e = 0;
+      if (wmax > 0.0f && std::isfinite(wmax)) e = std::min(12, std::max(-12, int(std::floor(std::log2(16384.0f / wmax)))));
+      const float scale = std::ldexp(1.0f, e);
+      const int kt = Cfg::k_slices(l);
+      for (int nb = 0; nb < Cfg::n_blocks(l, L); ++nb)
+        for (int pos0 = 0; pos0 < kt; pos0 += Cfg::SPS, ++slot) {
+          __half* const dst_slot = out.data() + (size_t(rank) * slots + slot) * (Cfg::SLOT_BYTES / 2);
+          for (int u = 0; u < Cfg::SPS; ++u) {
+            const int ks = Cfg::k_slice_at(pos0 + u, kt);
+            for (int part = 0; part < PARTS; ++part) {
+              __half* const dst = dst_slot + u * (Cfg::POS_BYTES / 2) + part * (Cfg::PIECE_BYTES / 2);
+              for (int r = 0; r < HALF_N; ++r) {
+                const int m = nb * BLOCK_N + rank * HALF_N + r;
+                const int src = last ? (m < nfb::M_LAST ? nfb::pack_last_layer_row(m) : -1) : (m < outd ? m : -1);
+                if (src < 0 || src >= outd) continue;
+                for (int kk = 0; kk < SLICE_K; ++kk) {
+                  // SPLIT = 1, layer 0: the four k-slices are [W_hi | W_hi | W_lo | 0] over the same 32 (25 used) inputs
+                  const bool first_x1 = (Cfg::SPLIT == 1 && l == 0);
+                  if (first_x1 && ks == 3) continue;
+                  const int k = first_x1 ? kk : ks * SLICE_K + kk;
+                  if (k >= in) continue;
+                  const float ws = W[l][size_t(src) * in + k] * scale;
+                  const __half hi = __float2half_rn(ws);
+                  const bool want_lo = first_x1 ? (ks == 2) : (part == 1);
+                  dst[(r / 8) * 256 + (kk / 8) * 64 + (r % 8) * 8 + (kk % 8)] = want_lo ? __float2half_rn(ws - __half2float(hi)) : hi;
+                }
+              }
+            }
+          }
+        }
+    }
+  }
+  return out;
+}
+
 template <class Cfg>
 int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
   static thread_local int configured_device = -1;
@@ -223,7 +278,7 @@ int launch_tc2(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t strea
   static const char* grid_env = getenv("NFB_TC2_GRID");  // contention experiments only
   const int max_grid = grid_env ? atoi(grid_env) : ctx->sm_count;
   const int grid = int(std::min<long long>((tiles + 1) & ~1LL, max_grid & ~1));  // whole CTA pairs
-  nfb::tc2::nfb_tc2_kernel<Cfg><<<grid, nfb::tc::THREADS, Cfg::SMEM_BYTES, stream>>>(tp);
+  nfb::tc2::nfb_tc2_kernel<Cfg><<<grid, nfb::tc2::THREADS2, Cfg::SMEM_BYTES, stream>>>(tp);
   NFB_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return NFB_OK;
@@ -286,11 +341,11 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
     const bool x3 = (variant == NFB_VARIANT_TENSOR_FP16X3);
     nfb::tc::TcParams tp;
     tp.ev = p;
-    tp.wblob = x3 ? m.tc3_w : m.tc_w;
+    static const bool one_sm = getenv("NFB_TC_ONE_SM") != nullptr;  // A/B experiments: the one-SM kernels of nfb_tc.cuh
+    tp.wblob = one_sm ? (x3 ? m.tc3_w : m.tc_w) : (x3 ? m.tc2_w3 : m.tc2_w);
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
     tp.dbg = ctx->tc_debug;
-    static const bool one_sm = getenv("NFB_TC_ONE_SM") != nullptr;  // A/B experiments: the one-SM kernels of nfb_tc.cuh
     if (!one_sm) {
       if (m.h_pad == 512)
         return x3 ? launch_tc2<nfb::tc2::Tc2Cfg<512, 3>>(ctx, tp, stream) : launch_tc2<nfb::tc2::Tc2Cfg<512, 1>>(ctx, tp, stream);
@@ -379,6 +434,8 @@ void nfb_destroy(nfb_context* ctx) {
     if (m.blob) cudaFree(m.blob);
     if (m.tc_w) cudaFree(m.tc_w);
     if (m.tc3_w) cudaFree(m.tc3_w);
+    if (m.tc2_w) cudaFree(m.tc2_w);
+    if (m.tc2_w3) cudaFree(m.tc2_w3);
     if (m.tc_bias) cudaFree(m.tc_bias);
     if (m.tc_inv_scale) cudaFree(m.tc_inv_scale);
   }
@@ -452,6 +509,8 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
     NFB_CUDA(cudaFree(m.blob));
     if (m.tc_w) NFB_CUDA(cudaFree(m.tc_w));
     if (m.tc3_w) NFB_CUDA(cudaFree(m.tc3_w));
+    if (m.tc2_w) NFB_CUDA(cudaFree(m.tc2_w));
+    if (m.tc2_w3) NFB_CUDA(cudaFree(m.tc2_w3));
     if (m.tc_bias) NFB_CUDA(cudaFree(m.tc_bias));
     if (m.tc_inv_scale) NFB_CUDA(cudaFree(m.tc_inv_scale));
     m = Model();
@@ -463,6 +522,14 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
                                     : pack_model_tc<nfb::tc::TcCfg<256, 1>>(n_layers, dims, weights, biases);
     const TcPack tcp3 = h_pad == 512 ? pack_model_tc<nfb::tc::TcCfg<512, 3>>(n_layers, dims, weights, biases)
                                      : pack_model_tc<nfb::tc::TcCfg<256, 3>>(n_layers, dims, weights, biases);
+    const std::vector<__half> p2 = h_pad == 512 ? pack_model_tc2<nfb::tc2::Tc2Cfg<512, 1>>(n_layers, dims, weights)
+                                                : pack_model_tc2<nfb::tc2::Tc2Cfg<256, 1>>(n_layers, dims, weights);
+    const std::vector<__half> p23 = h_pad == 512 ? pack_model_tc2<nfb::tc2::Tc2Cfg<512, 3>>(n_layers, dims, weights)
+                                                 : pack_model_tc2<nfb::tc2::Tc2Cfg<256, 3>>(n_layers, dims, weights);
+    NFB_CUDA(cudaMalloc(&m.tc2_w, p2.size() * sizeof(__half)));
+    NFB_CUDA(cudaMemcpy(m.tc2_w, p2.data(), p2.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    NFB_CUDA(cudaMalloc(&m.tc2_w3, p23.size() * sizeof(__half)));
+    NFB_CUDA(cudaMemcpy(m.tc2_w3, p23.data(), p23.size() * sizeof(__half), cudaMemcpyHostToDevice));
     NFB_CUDA(cudaMalloc(&m.tc3_w, tcp3.w.size() * sizeof(__half)));
     NFB_CUDA(cudaMemcpy(m.tc3_w, tcp3.w.data(), tcp3.w.size() * sizeof(__half), cudaMemcpyHostToDevice));
     NFB_CUDA(cudaMalloc(&m.tc_w, tcp.w.size() * sizeof(__half)));

@@ -176,19 +176,12 @@ __device__ __forceinline__ uint32_t act_chunk_offset(int n, int k) {
   return uint32_t(atom) * Cfg::ATOM_BYTES + uint32_t(n >> 3) * 1024 + uint32_t(n & 7) * 128 + uint32_t((chunk ^ (n & 7)) << 4);
 }
 
-// ---- featurise one batch row (nfb::featurise_query), then write the first layer's fp16 input row -------------------
-//   SPLIT = 1: [x_hi | x_lo | x_hi] in k = 0..95 of the single copy;  SPLIT = 3: x_hi -> A_hi, x_lo -> A_lo, k = 0..31
-template <class Cfg>
-__device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, bool valid, bool twin, int n,
-                                              unsigned char* act, float* maha, float* re_s) {
+// ---- featurise one batch row (nfb::featurise_query) -> fp16 hi / lo halves of its 32 (25 used) first-layer inputs ----
+__device__ __forceinline__ void featurise_pack(const EvalParams& p, long long q, bool valid, bool twin,
+                                               uint32_t (&hi)[16], uint32_t (&lo)[16], float& m, float& re) {
   double x[N_IN];
-  float m, re;
   featurise_query(p, q, valid, twin, x, m, re);
-  maha[n] = m;
-  if (!twin) re_s[n] = re;
-
-  // hi / lo split in fp16 (22 significant bits together), 32 values each (25 used)
-  uint32_t hi[16], lo[16];
+  // hi / lo split in fp16 (22 significant bits together)
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float f0 = (2 * i < N_IN) ? static_cast<float>(x[2 * i]) : 0.0f;
@@ -199,6 +192,18 @@ __device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, 
     const float l1 = (2 * i + 1 < N_IN) ? static_cast<float>(x[2 * i + 1] - double(__half2float(h1))) : 0.0f;
     lo[i] = pack_f16x2(l0, l1);
   }
+}
+
+// ... and write the first layer's fp16 input row n into the activation tile:
+//   SPLIT = 1: [x_hi | x_lo | x_hi] in k = 0..95 of the single copy;  SPLIT = 3: x_hi -> A_hi, x_lo -> A_lo, k = 0..31
+template <class Cfg>
+__device__ __forceinline__ void featurise_row(const EvalParams& p, long long q, bool valid, bool twin, int n,
+                                              unsigned char* act, float* maha, float* re_s) {
+  uint32_t hi[16], lo[16];
+  float m, re;
+  featurise_pack(p, q, valid, twin, hi, lo, m, re);
+  maha[n] = m;
+  if (!twin) re_s[n] = re;
 #pragma unroll
   for (int c8 = 0; c8 < 4; ++c8) {
     const uint4 vh = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);

@@ -21,6 +21,10 @@
 //     by multicast commits.  K region 1 of a layer is swept chunk-major (k_slice_at) and its readiness is signalled in
 //     two steps (a1a, a1b), so q2 starts while the second half of the previous layer's N-block 1 is still being
 //     activated.
+//   * Featurisation runs ahead: two extra warps compute the NEXT tile's 25 inputs and Mahalanobis terms (fp64, ~7,000
+//     latency-bound cycles per tile) while the current tile's layers run, and drop them into a small first-layer input
+//     buffer of their own as soon as layer 0 of the current tile has consumed it.  The next tile's layer 0 then starts
+//     the moment the last layer's accumulators are staged, overlapping the decode.
 //   * All barriers use default (CTA-scope) semantics: a cluster-scope release compiles to MEMBAR.ALL.GPU and a
 //     cluster-scope acquiring wait to CCTL.IVALL (an L1 invalidate) per wait -- measured 3x slower MMA issue.  Nothing
 //     is handed over through the generic proxy across CTAs: the data these barriers order is written to the writer's own
@@ -32,7 +36,11 @@
 namespace nfb {
 namespace tc2 {
 
-using namespace nfb::tc;  // PTX wrappers, SLICE_K, ATOM_K, THREADS, EPI_WARPS, MAX_TC_LAYERS, LAST_ROWS
+using namespace nfb::tc;  // PTX wrappers, SLICE_K, ATOM_K, EPI_WARPS, MAX_TC_LAYERS, LAST_ROWS
+
+constexpr int THREADS2 = 384;   // warp 0 producer, warp 1 MMA issue / relay, warps 2..9 epilogue, warps 10..11 featurise-ahead
+constexpr int FW_WARP0 = 10, FW_WARPS = 2;
+constexpr int N_BARS = 40;
 
 template <int H_, int SPLIT_>
 struct Tc2Cfg {
@@ -40,18 +48,30 @@ struct Tc2Cfg {
   static constexpr int SPLIT = SPLIT_;
   static constexpr int ROWS = (SPLIT == 3 && H == 512) ? 64 : 128;   // batch rows per CTA; the MMA's M = 2 ROWS spans the pair
   static constexpr int NQT = ROWS / 2;                               // queries per CTA tile (rows NQT.. are the twins)
-  static constexpr int K0 = (SPLIT == 3) ? 32 : 96;                  // first layer's K ([hi | lo | hi] concatenation when SPLIT = 1)
+  static constexpr int K0 = (SPLIT == 3) ? 32 : 128;                 // first layer's K (SPLIT = 1: [x_hi | x_lo | x_hi | -] . [W_hi | W_hi | W_lo | 0])
   static constexpr int BLOCK_N = H / 2;                              // MMA N = features per N-block
   static constexpr int HALF_N = BLOCK_N / 2;                         // B rows held by each CTA
-  static constexpr int SLOTS_PER_STEP = (SPLIT == 3) ? 2 : 1;        // slices per (N-block, k-slice) in the blob: W_hi, W_lo
-  static constexpr uint32_t SLICE_BYTES = BLOCK_N * SLICE_K * 2;     // a packed slice in the blob
-  static constexpr uint32_t PIECE_BYTES = SLICE_BYTES / 2;           // one CTA's share of a slice
-  static constexpr uint32_t SLOT_BYTES = SLOTS_PER_STEP * PIECE_BYTES;   // ring slot: my W_hi piece (, my W_lo piece)
-  static constexpr int RING = (SLOT_BYTES >= 16384) ? 5 : (SPLIT == 1 && H == 256) ? 8 : 10;   // weight ring depth (what fits)
+  // Weight stream (pack_model_tc2 in nfb_api.cu): per CTA rank, the ring slots of one tile in the order the kernel
+  // consumes them.  A slot = SPS consecutive positions of a K sweep, each position my half (HALF_N rows x 32 k, K-major
+  // no-swizzle core matrices) of the W_hi slice and, when SPLIT = 3, of the W_lo slice.  One bulk copy per slot: issuing
+  // a copy costs the producer ~260 cycles whatever its size (scripts/tma_mma_probe.cu), more than a one-term position's
+  // MMAs last, hence two positions per slot there.
+  static constexpr int SPS = (SPLIT == 3) ? 1 : 2;
+  static constexpr uint32_t PIECE_BYTES = HALF_N * SLICE_K * 2;      // my rows of one slice
+  static constexpr uint32_t POS_BYTES = (SPLIT == 3 ? 2 : 1) * PIECE_BYTES;
+  static constexpr uint32_t SLOT_BYTES = SPS * POS_BYTES;
   static constexpr uint32_t ATOM_BYTES = ROWS * 128;
   static constexpr uint32_t A_BYTES = (H / ATOM_K) * ATOM_BYTES;
   static constexpr uint32_t ACT_BYTES = A_BYTES * (SPLIT == 3 ? 2 : 1);  // [A_hi][A_lo]
   static constexpr uint32_t STAGE_BYTES = M_LAST * ROWS * 4;         // last layer's latents, fp32 [224][ROWS]
+  static constexpr uint32_t REGION_BYTES = ACT_BYTES >= STAGE_BYTES ? ACT_BYTES : STAGE_BYTES;  // the idle activation tile doubles as the staging block
+  // first-layer input rows [x_hi | x_lo] at k = 0..63 of one atom, outside the activation tile so that they can be
+  // written a tile ahead.  (SPLIT = 1 reads them as the K = 96 concatenation [x_hi | x_lo | x_hi]: its third k-slice
+  // points at the first again.)
+  static constexpr uint32_t IN_BYTES = ATOM_BYTES;
+  // (Measured: reading the 512-wide models' 14 KB of biases through L1 instead, to buy weight-ring slots, loses 5 %:
+  //  with 227 KB of shared memory carved out the L1 is too small to keep them.)
+  static constexpr bool BIAS_IN_SMEM = true;
   // TMEM: D_hi of N-block nb at column nb * TILE_COLS; SPLIT = 3 keeps the two small product terms in accumulators of
   // their own (the tensor core truncates at every accumulation, see nfb_tc.cuh) at + 256
   static constexpr uint32_t TILE_COLS = (ROWS == 64) ? BLOCK_N / 2 : BLOCK_N;
@@ -60,32 +80,35 @@ struct Tc2Cfg {
   // epilogue geometry: G thread groups along the features of an N-block, each thread NCH chunks of 32 features per half
   static constexpr int G = (ROWS == 64) ? 4 : 2;
   static constexpr int NCH = BLOCK_N / (32 * G);
+  static constexpr uint32_t BIAS_FLOATS = (BIAS_IN_SMEM ? MAX_TC_LAYERS * H : 0) + 16;   // biases [L][H], then 1 / scale [L]
+  static constexpr uint32_t FIXED_BYTES = REGION_BYTES + IN_BYTES + BIAS_FLOATS * 4 + 2 * ROWS * 4 + 2 * NQT * 4 + N_BARS * 8 + 16 + 1024;
+  static constexpr int RING_FIT = int((232448 - FIXED_BYTES) / SLOT_BYTES);
+  static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;          // weight ring depth: what fits, at most 10
   static constexpr uint32_t OFF_ACT = 0;
-  static constexpr uint32_t OFF_RING = OFF_ACT + ACT_BYTES;
+  static constexpr uint32_t OFF_STAGE = 0;
+  static constexpr uint32_t OFF_IN = REGION_BYTES;
+  static constexpr uint32_t OFF_RING = OFF_IN + IN_BYTES;
   static constexpr uint32_t OFF_BIAS = OFF_RING + RING * SLOT_BYTES;
-  static constexpr uint32_t BIAS_FLOATS = MAX_TC_LAYERS * H + 16;
-  static constexpr uint32_t OFF_MAHA = OFF_BIAS + BIAS_FLOATS * 4;
-  static constexpr uint32_t OFF_RE = OFF_MAHA + ROWS * 4;
-  static constexpr uint32_t OFF_BARS = OFF_RE + NQT * 4;
-  static constexpr uint32_t OFF_TMEM = OFF_BARS + 32 * 8;
-  // the staging block re-uses the idle activation tile when that is big enough, else gets its own room
-  static constexpr uint32_t OFF_STAGE = (ACT_BYTES >= STAGE_BYTES) ? OFF_ACT : ((OFF_TMEM + 16 + 127) & ~127u);
-  static constexpr uint32_t SMEM_BYTES = ((ACT_BYTES >= STAGE_BYTES) ? OFF_TMEM + 16 : OFF_STAGE + STAGE_BYTES) + 1024;
+  static constexpr uint32_t OFF_MAHA = OFF_BIAS + BIAS_FLOATS * 4;    // fp32 [2][ROWS], by tile parity
+  static constexpr uint32_t OFF_RE = OFF_MAHA + 2 * ROWS * 4;         // fp32 [2][NQT]
+  static constexpr uint32_t OFF_BARS = OFF_RE + 2 * NQT * 4;
+  static constexpr uint32_t OFF_TMEM = OFF_BARS + N_BARS * 8;
+  static constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
   static_assert(H == 512 || H == 256, "tensor-core variants: 512- or 256-wide models");
   static_assert(SPLIT == 1 || SPLIT == 3, "one MMA per product, or the three-term fp16 split");
   static_assert(NCH == 2 || NCH == 4, "chunks per thread per half");
-  static_assert(2 * RING + 6 <= 32, "barrier block");
+  static_assert(RING >= 3 && 2 * RING + 10 <= N_BARS, "weight ring / barrier block");
   static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
 
   __host__ __device__ static constexpr int k_slices(int l) { return (l == 0 ? K0 : H) / SLICE_K; }
   __host__ __device__ static constexpr int n_blocks(int l, int L) { return l == L - 1 ? LAST_ROWS / BLOCK_N : 2; }
-  __host__ __device__ static constexpr int steps_in_layer(int l, int L) { return k_slices(l) * n_blocks(l, L); }
+  __host__ __device__ static constexpr int slots_in_layer(int l, int L) { return k_slices(l) * n_blocks(l, L) / SPS; }
   // Position in a layer's K sweep -> k-slice.  K region 1 (the second half of the inputs) is swept chunk-major: first the
   // slices that hold the chunks every epilogue thread of the previous layer writes in its first NCH / 2 rounds, then the
   // others, so the sweep can start on the former while the latter are still being activated (barriers a1a / a1b).
   // Thread group g writes slices g NCH .. g NCH + NCH - 1 of the region, one per round.
   __host__ __device__ static constexpr int k_slice_at(int pos, int kt) {
-    if (kt < 4 || pos < kt / 2) return pos;  // (the first layer's few slices all count as region 0)
+    if (kt != H / SLICE_K || pos < kt / 2) return pos;  // (the first layer's few slices all count as region 0)
     const int R = kt / 2, hn = NCH / 2, j = pos - R;
     const int phase = j / (R / 2), jj = j % (R / 2);
     return R + (jj / hn) * NCH + phase * hn + jj % hn;
@@ -122,7 +145,7 @@ __device__ __forceinline__ float silu_ex2(float h) {
 }
 
 template <class Cfg>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_kernel(const TcParams tp) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2_kernel(const TcParams tp) {
   constexpr int H = Cfg::H, ROWS = Cfg::ROWS, NQT = Cfg::NQT, SPLIT = Cfg::SPLIT, RING = Cfg::RING, NCH = Cfg::NCH;
   constexpr uint32_t SLOT_BYTES = Cfg::SLOT_BYTES, PIECE_BYTES = Cfg::PIECE_BYTES, ATOM_BYTES = Cfg::ATOM_BYTES;
   const EvalParams& p = tp.ev;
@@ -130,15 +153,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
   unsigned char* const smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
   unsigned char* const act = smem + Cfg::OFF_ACT;   // A_hi (the only copy when SPLIT = 1), then A_lo
+  unsigned char* const inbuf = smem + Cfg::OFF_IN;  // the first layer's input rows (written a tile ahead)
   unsigned char* const ring = smem + Cfg::OFF_RING;
   float* const bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
-  float* const maha = reinterpret_cast<float*>(smem + Cfg::OFF_MAHA);
-  float* const re_s = reinterpret_cast<float*>(smem + Cfg::OFF_RE);
+  float* const scale_s = bias_s + (Cfg::BIAS_IN_SMEM ? MAX_TC_LAYERS * H : 0);
+  const float* const bias_all = Cfg::BIAS_IN_SMEM ? bias_s : tp.bias;
+  float* const maha2 = reinterpret_cast<float*>(smem + Cfg::OFF_MAHA);
+  float* const re2 = reinterpret_cast<float*>(smem + Cfg::OFF_RE);
   const uint32_t bar_full = smem_u32(smem + Cfg::OFF_BARS), bar_empty = bar_full + 8 * RING;
   // Layer pipeline barriers (nfb_tc.cuh).  a0 / a1a / a1b are waited on in the leader CTA only: K region 0 / the first /
   // the second half of K region 1's slices are in shared memory and the TMEM they came from is drained.
   const uint32_t bar_a0 = bar_empty + 8 * RING, bar_a1a = bar_a0 + 8, bar_a1b = bar_a1a + 8, bar_d0 = bar_a1b + 8, bar_k0 = bar_d0 + 8,
                  bar_d1 = bar_k0 + 8;
+  // Tile hand-over barriers.  in (leader): the featurise warps of both CTAs have written the tile's input rows.
+  // drained (leader): the epilogue warps of both CTAs have read the last layer's accumulators.  infree (both, by commit):
+  // layer 0 has consumed the input rows.  tiledone (local): this CTA's epilogue warps have finished the tile's decode.
+  const uint32_t bar_in = bar_d1 + 8, bar_drained = bar_in + 8, bar_infree = bar_drained + 8, bar_tiledone = bar_infree + 8;
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -146,11 +176,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
   const long long n_tiles = (p.n + NQT - 1) / NQT;
   const uint32_t my_tiles = uint32_t((n_tiles + gridDim.x - 1) / gridDim.x);  // same for every CTA
   const uint32_t cta_rank = cluster_ctarank();
-  int steps_per_tile = 0;
-  for (int l = 0; l < L; ++l) steps_per_tile += Cfg::steps_in_layer(l, L);
+  int slots_per_tile = 0;
+  for (int l = 0; l < L; ++l) slots_per_tile += Cfg::slots_in_layer(l, L);
 
-  for (int i = tid; i < L * H; i += THREADS) bias_s[i] = tp.bias[i];
-  if (tid < L) bias_s[MAX_TC_LAYERS * H + tid] = tp.inv_scale[tid];
+  if constexpr (Cfg::BIAS_IN_SMEM)
+    for (int i = tid; i < L * H; i += THREADS2) bias_s[i] = tp.bias[i];
+  if (tid < L) scale_s[tid] = tp.inv_scale[tid];
   if (tid == 0) {
     for (int s = 0; s < RING; ++s) {
       mbar_init(bar_full + 8 * s, cta_rank == 0 ? 2 : 1);  // leader: its own producer + the peer's relay
@@ -162,6 +193,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
     mbar_init(bar_d0, 1);
     mbar_init(bar_k0, 1);
     mbar_init(bar_d1, 1);
+    mbar_init(bar_in, 2 * FW_WARPS);
+    mbar_init(bar_drained, 2 * EPI_WARPS);
+    mbar_init(bar_infree, 1);
+    mbar_init(bar_tiledone, EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -175,37 +210,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ============================ weight producer: my half of every slice ============================
-    if (lane == 0) {
-      constexpr size_t STEP_BYTES = size_t(Cfg::SLOTS_PER_STEP) * Cfg::SLICE_BYTES;
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(tp.wblob) + cta_rank * PIECE_BYTES;
-      uint32_t s = 0, ph = 0;
-      for (uint32_t t = 0; t < my_tiles; ++t)
-        for (int l = 0, base = 0; l < L; base += Cfg::steps_in_layer(l, L), ++l) {
-          const int kt = Cfg::k_slices(l);
-          for (int nb = 0; nb < Cfg::n_blocks(l, L); ++nb)
-            for (int pos = 0; pos < kt; ++pos) {
-              const size_t j = size_t(base + nb * kt + Cfg::k_slice_at(pos, kt));  // blob order: layer, N-block, k-slice
-              mbar_wait(bar_empty + 8 * s, ph ^ 1);
-              mbar_arrive_expect_tx(bar_full + 8 * s, SLOT_BYTES);
-              const uint32_t dst = smem_u32(ring + s * SLOT_BYTES);
-              bulk_copy_g2s(dst, src + j * STEP_BYTES, PIECE_BYTES, bar_full + 8 * s);  // W_hi rows
-              if constexpr (SPLIT == 3)
-                bulk_copy_g2s(dst + PIECE_BYTES, src + j * STEP_BYTES + Cfg::SLICE_BYTES, PIECE_BYTES, bar_full + 8 * s);  // W_lo rows
-              if (++s == RING) { s = 0; ph ^= 1; }
-            }
-        }
+    // ============================ weight producer: my rank's slot stream, one bulk copy per slot ============================
+    // Runs warp-converged with one elected lane issuing, so that the loop state lives in uniform registers.
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(tp.wblob) + size_t(cta_rank) * size_t(slots_per_tile) * SLOT_BYTES;
+    const uint32_t total = my_tiles * uint32_t(slots_per_tile);
+    uint32_t s = 0, ph = 0;
+    long long wait_empty = 0;  // diagnostics (tp.dbg only)
+    for (uint32_t it = 0, j = 0; it < total; ++it) {
+      const bool timing = tp.dbg && it >= uint32_t(slots_per_tile) && it < 2u * uint32_t(slots_per_tile);
+      const long long c0 = timing ? clock64() : 0;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (timing) wait_empty += clock64() - c0;
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar_full + 8 * s, SLOT_BYTES);
+        bulk_copy_g2s(smem_u32(ring + s * SLOT_BYTES), src + size_t(j) * SLOT_BYTES, SLOT_BYTES, bar_full + 8 * s);
+      }
+      __syncwarp();
+      if (++j == uint32_t(slots_per_tile)) j = 0;
+      if (++s == RING) { s = 0; ph ^= 1; }
     }
+    if (tp.dbg && lane == 0 && blockIdx.x < 2) tp.dbg[51 + blockIdx.x] = wait_empty;
   } else if (warp == 1 && cta_rank != 0) {
     // ============================ peer CTA: relay "slot landed" to the leader ============================
-    const uint32_t total = my_tiles * uint32_t(steps_per_tile);
-    const uint32_t leader_full = map_to_rank(bar_full, 0);
-    uint32_t s = 0, ph = 0;
-    for (uint32_t it = 0; it < total; ++it) {
-      mbar_wait(bar_full + 8 * s, ph);
-      if (lane == 0) mbar_arrive_cluster(leader_full + 8 * s);
-      __syncwarp();
-      if (++s == RING) { s = 0; ph ^= 1; }
+    // One lane per ring slot, so that the round trip of a remote arrive does not pace the stream.
+    if (lane < RING) {
+      const uint32_t total = my_tiles * uint32_t(slots_per_tile);
+      const uint32_t mine = bar_full + 8 * lane, leaders = map_to_rank(mine, 0);
+      uint32_t ph = 0;
+      for (uint32_t it = lane; it < total; it += RING, ph ^= 1) {
+        mbar_wait(mine, ph);
+        mbar_arrive_cluster(leaders);
+      }
     }
   } else if (warp == 1) {
     // ============================ leader CTA: MMA issue for the pair ============================
@@ -215,15 +250,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
     const uint64_t a_hi = (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
     const uint64_t b_hi = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
     // (14-bit start-address field; in a cluster the 32-bit shared address carries the CTA rank in its top bits)
-    const uint32_t a0 = (smem_u32(act) >> 4) & 0x3FFF, b0 = (smem_u32(ring) >> 4) & 0x3FFF;
-    constexpr uint32_t LO = Cfg::A_BYTES >> 4, WLO = PIECE_BYTES >> 4;
-    uint32_t s = 0, ph = 0, ph_a0 = 0, ph_a1 = 0;  // (a1a and a1b flip together)
+    const uint32_t a_act = (smem_u32(act) >> 4) & 0x3FFF, a_in = (smem_u32(inbuf) >> 4) & 0x3FFF, b0 = (smem_u32(ring) >> 4) & 0x3FFF;
+    constexpr uint32_t WLO = PIECE_BYTES >> 4;
+    uint32_t a0 = a_in, LO = 4;  // A base and distance of the lo half: layer 0 reads [x_hi | x_lo] of the input buffer, the others A_hi / A_lo
+    uint32_t s = 0, ph = 0, ph_a0 = 0, ph_a1 = 0, ph_in = 0, ph_dr = 0;  // (a1a and a1b flip together)
     long long wait_full = 0, wait_a0 = 0, wait_a1 = 0;  // diagnostics (tp.dbg only): cycles this warp spent waiting
     const bool timing = tp.dbg && blockIdx.x == 0;
-    // MMAs of one k-slice (ring slot s) into N-block nb; called by the elected lane
-    auto mma_step = [&](int nb, int ks, uint32_t slot, bool first) {
+    // MMAs of one position of a K sweep (k-slice ks of the A tile; its weights at byte offset b_ofs >> 4 of the ring)
+    // into N-block nb; called by the elected lane
+    auto mma_pos = [&](int nb, int ks, uint32_t b_lo, bool first) {
+      if (SPLIT == 1 && a0 == a_in) ks = (ks == 1);  // layer 0 of the one-term kernel: [x_hi | x_lo | x_hi | x_hi] . [W_hi | W_hi | W_lo | 0]
       const uint32_t a_lo = a0 + uint32_t(ks >> 1) * (ATOM_BYTES >> 4) + uint32_t(ks & 1) * 4;  // 64 B per 32 k
-      const uint32_t b_lo = b0 + slot * (SLOT_BYTES >> 4);
       const uint32_t d = tmem + nb * Cfg::TILE_COLS, d_small = d + Cfg::D_LO_OFFSET;
       umma_f16_pair(d, a_hi | a_lo, b_hi | b_lo, idesc, !first);                            // a_hi . w_hi -> D_hi
       umma_f16_pair(d, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
@@ -233,36 +270,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
         umma_f16_pair(d_small, a_hi | a_lo, b_hi | (b_lo + WLO), idesc, 1u);                // a_hi . w_lo -> D_lo
         umma_f16_pair(d_small, a_hi | (a_lo + 2), b_hi | (b_lo + WLO + 16), idesc, 1u);
       }
-      umma_commit_pair(bar_empty + 8 * slot);  // the slot is free in both CTAs once both tensor cores have read it
     };
-    auto wait_slot = [&](uint32_t slot, uint32_t phase) {
-      const long long c0 = timing ? clock64() : 0;
-      mbar_wait(bar_full + 8 * slot, phase);
-      if (timing) wait_full += clock64() - c0;
-    };
-    // Positions [pos_begin, pos_end) of N-block nb's K sweep.  SPLIT = 1 steps are only two MMAs (256 cycles) long, which
-    // the wait / elect / descriptor overhead of a step does not fit under: they are issued two slots at a time.
+    // Positions [pos_begin, pos_end) of N-block nb's K sweep (whole ring slots: SPS positions each)
     auto issue = [&](int nb, int kt, int pos_begin, int pos_end) {
-      int pos = pos_begin;
-      if constexpr (SPLIT == 1) {
-        for (; pos + 1 < pos_end; pos += 2) {
-          const uint32_t s1 = (s + 1 == RING) ? 0 : s + 1, ph1 = (s + 1 == RING) ? ph ^ 1 : ph;
-          wait_slot(s, ph);
-          wait_slot(s1, ph1);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            mma_step(nb, Cfg::k_slice_at(pos, kt), s, pos == 0);
-            mma_step(nb, Cfg::k_slice_at(pos + 1, kt), s1, false);
-          }
-          __syncwarp();
-          s = s1 + 1; ph = ph1;
-          if (s == RING) { s = 0; ph ^= 1; }
-        }
-      }
-      for (; pos < pos_end; ++pos) {
-        wait_slot(s, ph);
+      for (int pos = pos_begin; pos < pos_end; pos += Cfg::SPS) {
+        const long long c0 = timing ? clock64() : 0;
+        mbar_wait(bar_full + 8 * s, ph);
+        if (timing) wait_full += clock64() - c0;
         tc_fence_after();
-        if (elect_one_sync()) mma_step(nb, Cfg::k_slice_at(pos, kt), s, pos == 0);
+        if (elect_one_sync()) {
+          const uint32_t b_lo = b0 + s * (SLOT_BYTES >> 4);
+#pragma unroll
+          for (int u = 0; u < Cfg::SPS; ++u) mma_pos(nb, Cfg::k_slice_at(pos + u, kt), b_lo + u * (Cfg::POS_BYTES >> 4), pos + u == 0);
+          umma_commit_pair(bar_empty + 8 * s);  // the slot is free in both CTAs once both tensor cores have read it
+        }
         __syncwarp();
         if (++s == RING) { s = 0; ph ^= 1; }
       }
@@ -271,12 +292,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
       if (elect_one_sync()) umma_commit_pair(bar);
       __syncwarp();
     };
-    for (uint32_t t = 0; t < my_tiles; ++t)
-      for (int l = 0; l < L; ++l) {
+    for (uint32_t t = 0; t < my_tiles; ++t) {
+      {  // ---- layer 0: from the input buffer, as soon as it is written and the previous tile's accumulators are read ----
+        const int kt = Cfg::k_slices(0);
+        if (timing && t == 1) wait_full = wait_a0 = wait_a1 = 0;
+        const long long c0 = timing ? clock64() : 0;
+        mbar_wait(bar_in, ph_in);
+        ph_in ^= 1;
+        if (t != 0) {
+          mbar_wait(bar_drained, ph_dr);
+          ph_dr ^= 1;
+        }
+        if (timing) wait_a0 += clock64() - c0;
+        tc_fence_after();
+        if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[32] = clock64();
+        a0 = a_in;
+        LO = 4;
+        issue(0, kt, 0, kt);
+        commit(bar_d0);
+        issue(1, kt, 0, kt);
+        commit(bar_k0);
+        commit(bar_d1);
+        commit(bar_infree);
+        if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[33] = clock64();
+        a0 = a_act;
+        LO = Cfg::A_BYTES >> 4;
+      }
+      for (int l = 1; l < L; ++l) {
         const int kt = Cfg::k_slices(l);
-        const int kh = (kt < 4) ? kt : kt / 2;                 // slices in K region 0 (the first layer's inputs all are)
+        const int kh = kt / 2;                                 // slices in K region 0
         const int km = kh + (kt - kh) / 2;
-        if (timing && t == 1 && l == 0) wait_full = wait_a0 = wait_a1 = 0;
         long long c0 = timing ? clock64() : 0;
         mbar_wait(bar_a0, ph_a0);
         if (timing) wait_a0 += clock64() - c0;
@@ -310,6 +355,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
           if (l == L - 1) { tp.dbg[48] = wait_full; tp.dbg[49] = wait_a0; tp.dbg[50] = wait_a1; }
         }
       }
+    }
+  } else if (warp >= FW_WARP0) {
+    // ============================ featurise-ahead warps (both CTAs) ============================
+    // Thread ft owns batch rows ft (, ft + 64): row n is query n of the tile, row NQT + n its flipped twin.
+    constexpr int RPT = ROWS / (32 * FW_WARPS);
+    const int ft = tid - 32 * FW_WARP0;
+    const uint32_t leader_in = map_to_rank(bar_in, 0);
+    uint32_t ph_free = 0, ph_done = 0;
+    for (uint32_t t = 0; t < my_tiles; ++t) {
+      const long long tile_q0 = (blockIdx.x + (long long)t * gridDim.x) * NQT;  // may be past the end: an all-padding tile
+      float* const maha = maha2 + (t & 1) * ROWS;
+      float* const re_s = re2 + (t & 1) * NQT;
+#pragma unroll 1  // (one copy of the featurisation code: the kernel is instruction-cache heavy as it is)
+      for (int j = 0; j < RPT; ++j) {
+        const int n = ft + 64 * j;
+        const bool twin = n >= NQT;
+        const long long qi = tile_q0 + (twin ? n - NQT : n);
+        uint32_t hi[16], lo[16];
+        float m, re;
+        featurise_pack(p, qi, qi < p.n, twin, hi, lo, m, re);
+        if (j == 0) {
+          if (t >= 1) {  // layer 0 of the previous tile has consumed the input rows
+            mbar_wait(bar_infree, ph_free);
+            ph_free ^= 1;
+          }
+          if (t >= 2) {  // the decode of the tile before that has finished with this parity's maha / re
+            mbar_wait(bar_tiledone, ph_done);
+            ph_done ^= 1;
+          }
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const uint4 vh = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);
+          const uint4 vl = make_uint4(lo[4 * c8], lo[4 * c8 + 1], lo[4 * c8 + 2], lo[4 * c8 + 3]);
+          *reinterpret_cast<uint4*>(inbuf + act_chunk_offset<Cfg>(n, 8 * c8)) = vh;
+          *reinterpret_cast<uint4*>(inbuf + act_chunk_offset<Cfg>(n, 32 + 8 * c8)) = vl;
+        }
+        maha[n] = m;
+        if (n < NQT) re_s[n] = re;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_in);
+    }
   } else {
     // ============================ epilogue warps (both CTAs) ============================
     // ROWS = 128: TMEM lane 32 q + lane = batch row; the two warps of a lane quarter split an N-block's features.
@@ -320,10 +409,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
     const int g = (ROWS == 64) ? 2 * (q >> 1) + part : part;             // feature group of this thread
     const int fofs = 32 * NCH * g;                                       // first of my features within an N-block
     const int fcol = (ROWS == 64) ? 32 * NCH * part : fofs;              // ... and their first column within the accumulator tile
-    const bool featurises = (ROWS == 64) ? (q < 2 && part == 0) : (part == 0);
     const int et = (e << 5) | lane;                                      // 0..255
     const uint32_t t_lane = tmem + (uint32_t(32 * q) << 16);
-    const uint32_t leader_a0 = map_to_rank(bar_a0, 0), leader_a1a = map_to_rank(bar_a1a, 0), leader_a1b = map_to_rank(bar_a1b, 0);
+    const uint32_t leader_a0 = map_to_rank(bar_a0, 0), leader_a1a = map_to_rank(bar_a1a, 0), leader_a1b = map_to_rank(bar_a1b, 0),
+                   leader_drained = map_to_rank(bar_drained, 0);
     const bool vec_ok =
         p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
                   : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
@@ -372,25 +461,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
     for (uint32_t t = 0; t < my_tiles; ++t) {
       const long long tile = blockIdx.x + (long long)t * gridDim.x;  // may be past the end: an all-padding tile
       const long long tile_q0 = tile * NQT;
-      const bool stamp = tp.dbg && blockIdx.x == 0 && t == 1 && warp == 4 && lane == 0;  // a featurising warp
-      if (stamp) tp.dbg[0] = clock64();
-      if (featurises) {  // one thread per batch row (row n: query n, row NQT + n: its twin)
-        const bool twin = n >= NQT;
-        const long long qi = tile_q0 + (twin ? n - NQT : n);
-        featurise_row<Cfg>(p, qi, qi < p.n, twin, n, act, maha, re_s);
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(leader_a0);
-        mbar_arrive_cluster(leader_a1a);
-        mbar_arrive_cluster(leader_a1b);
-      }
-      if (stamp) tp.dbg[1] = clock64();
+      const bool stamp = tp.dbg && blockIdx.x == 0 && t == 1 && warp == 4 && lane == 0;
+      const float* const maha = maha2 + (t & 1) * ROWS;   // written by the featurise warps before this tile's layer 0 ran
+      const float* const re_s = re2 + (t & 1) * NQT;
+      if (stamp) tp.dbg[0] = tp.dbg[1] = clock64();
 
       for (int l = 0; l < L - 1; ++l) {
-        const float inv_s = bias_s[MAX_TC_LAYERS * H + l];
-        const float* b = bias_s + l * H + fofs;
+        const float inv_s = scale_s[l];
+        const float* b = bias_all + l * H + fofs;
         // ---- half 0: N-block 0 complete after q2; its outputs may only land in K region 0 after q3 ----
         mbar_wait(bar_d0, ph_d0);
         ph_d0 ^= 1;
@@ -434,8 +512,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
       if (stamp) tp.dbg[20] = clock64();
       {
         float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_STAGE);
-        const float inv_s = bias_s[MAX_TC_LAYERS * H + (L - 1)];
-        const float* b = bias_s + (L - 1) * H;
+        const float inv_s = scale_s[L - 1];
+        const float* b = bias_all + (L - 1) * H;
         // my packed rows: ROWS = 64: the N-block's [fofs, fofs + 64); ROWS = 128: [128 part, 128 part + 128) (columns = rows)
         const int f_begin = (ROWS == 64) ? fofs : 128 * part, f_count = (ROWS == 64) ? 32 * NCH : 128;
         const int c_begin = (ROWS == 64) ? fcol : f_begin;
@@ -449,6 +527,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
           for (int i = 0; i < 32; ++i) stage[(f0 + i) * ROWS + n] = fmaf(__uint_as_float(v[i]), inv_s, b[f0 + i]);
         }
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_drained);  // the next tile's layer 0 may overwrite the accumulators
         named_bar_sync(1, EPI_THREADS);
         if (stamp) tp.dbg[21] = clock64();
         for (int item = et; item < (M_LAST / 4) * (NQT / 4); item += EPI_THREADS) {
@@ -466,7 +546,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc2_
           const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
           decode_and_store(p, gq, q0, nvalid, vec_ok, acc, maha + qb, maha + NQT + qb, re_s + qb);
         }
-        named_bar_sync(1, EPI_THREADS);  // staging (and maha / re) consumed before the next tile's featurise overwrites them
+        named_bar_sync(1, EPI_THREADS);  // staging consumed before the next tile's activations overwrite it
+        if (lane == 0) mbar_arrive(bar_tiledone);
         if (stamp) tp.dbg[22] = clock64();
       }
     }

@@ -36,3 +36,4 @@ print("  last: D ready", st[20] - t0, "staged", st[21] - t0, "decoded", st[22] -
 for l in range(L):
     print(f"  MMA layer {l}: start {st[32 + 2 * l] - t0} end {st[33 + 2 * l] - t0} (span {st[33 + 2 * l] - st[32 + 2 * l]})")
 print(f"  MMA warp waits over the tile: weight slots {st[48]}, a0 {st[49]}, a1 {st[50]} cycles")
+print(f"  producer waits for a free slot over the tile: leader {st[51]}, peer {st[52]} cycles")
