@@ -229,8 +229,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) nfb_tc_k
   constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES, ATOM_BYTES = Cfg::ATOM_BYTES;
   const EvalParams& p = tp.ev;
   extern __shared__ unsigned char smem_unaligned[];
-  unsigned char* const smem =
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
+  // (1024-aligned by pointer arithmetic on the __shared__ array, not by integer round-trip: the latter makes every
+  //  access below a generic LD / ST instead of LDS / STS)
+  unsigned char* const smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
   unsigned char* const act = smem + Cfg::OFF_ACT;   // A_hi (the only copy when SPLIT = 1), then A_lo
   unsigned char* const ring = smem + Cfg::OFF_RING;
   float* const bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);

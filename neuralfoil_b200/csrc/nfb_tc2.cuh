@@ -69,9 +69,8 @@ struct Tc2Cfg {
   // written a tile ahead.  (SPLIT = 1 reads them as the K = 96 concatenation [x_hi | x_lo | x_hi]: its third k-slice
   // points at the first again.)
   static constexpr uint32_t IN_BYTES = ATOM_BYTES;
-  // (Measured: reading the 512-wide models' 14 KB of biases through L1 instead, to buy weight-ring slots, loses 5 %:
-  //  with 227 KB of shared memory carved out the L1 is too small to keep them.)
-  static constexpr bool BIAS_IN_SMEM = true;
+  // (Measured: reading the 512-wide models' 14 KB of biases through L1 instead of from shared memory, to buy weight-ring
+  //  slots, loses 5 %: with 227 KB of shared memory carved out the L1 is too small to keep them.)
   // TMEM: D_hi of N-block nb at column nb * TILE_COLS; SPLIT = 3 keeps the two small product terms in accumulators of
   // their own (the tensor core truncates at every accumulation, see nfb_tc.cuh) at + 256
   static constexpr uint32_t TILE_COLS = (ROWS == 64) ? BLOCK_N / 2 : BLOCK_N;
@@ -80,7 +79,7 @@ struct Tc2Cfg {
   // epilogue geometry: G thread groups along the features of an N-block, each thread NCH chunks of 32 features per half
   static constexpr int G = (ROWS == 64) ? 4 : 2;
   static constexpr int NCH = BLOCK_N / (32 * G);
-  static constexpr uint32_t BIAS_FLOATS = (BIAS_IN_SMEM ? MAX_TC_LAYERS * H : 0) + 16;   // biases [L][H], then 1 / scale [L]
+  static constexpr uint32_t BIAS_FLOATS = MAX_TC_LAYERS * H + 16;   // biases [L][H], then 1 / scale [L]
   static constexpr uint32_t FIXED_BYTES = REGION_BYTES + IN_BYTES + BIAS_FLOATS * 4 + 2 * ROWS * 4 + 2 * NQT * 4 + N_BARS * 8 + 16 + 1024;
   static constexpr int RING_FIT = int((232448 - FIXED_BYTES) / SLOT_BYTES);
   static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;          // weight ring depth: what fits, at most 10
@@ -144,20 +143,42 @@ __device__ __forceinline__ float silu_ex2(float h) {
   return h * r;
 }
 
+// tcgen05.ld without the wait, and the wait as a separate statement that "produces" the registers, so that the compiler
+// cannot move their consumers above it: lets the next chunk's TMEM read overlap the current chunk's arithmetic.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
 template <class Cfg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2_kernel(const TcParams tp) {
   constexpr int H = Cfg::H, ROWS = Cfg::ROWS, NQT = Cfg::NQT, SPLIT = Cfg::SPLIT, RING = Cfg::RING, NCH = Cfg::NCH;
   constexpr uint32_t SLOT_BYTES = Cfg::SLOT_BYTES, PIECE_BYTES = Cfg::PIECE_BYTES, ATOM_BYTES = Cfg::ATOM_BYTES;
   const EvalParams& p = tp.ev;
   extern __shared__ unsigned char smem_unaligned[];
-  unsigned char* const smem =
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) & ~uintptr_t(1023));
+  // (1024-aligned by pointer arithmetic on the __shared__ array, not by integer round-trip: the latter makes every
+  //  access below a generic LD / ST instead of LDS / STS)
+  unsigned char* const smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
   unsigned char* const act = smem + Cfg::OFF_ACT;   // A_hi (the only copy when SPLIT = 1), then A_lo
   unsigned char* const inbuf = smem + Cfg::OFF_IN;  // the first layer's input rows (written a tile ahead)
   unsigned char* const ring = smem + Cfg::OFF_RING;
   float* const bias_s = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
-  float* const scale_s = bias_s + (Cfg::BIAS_IN_SMEM ? MAX_TC_LAYERS * H : 0);
-  const float* const bias_all = Cfg::BIAS_IN_SMEM ? bias_s : tp.bias;
+  float* const scale_s = bias_s + MAX_TC_LAYERS * H;
   float* const maha2 = reinterpret_cast<float*>(smem + Cfg::OFF_MAHA);
   float* const re2 = reinterpret_cast<float*>(smem + Cfg::OFF_RE);
   const uint32_t bar_full = smem_u32(smem + Cfg::OFF_BARS), bar_empty = bar_full + 8 * RING;
@@ -179,8 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
   int slots_per_tile = 0;
   for (int l = 0; l < L; ++l) slots_per_tile += Cfg::slots_in_layer(l, L);
 
-  if constexpr (Cfg::BIAS_IN_SMEM)
-    for (int i = tid; i < L * H; i += THREADS2) bias_s[i] = tp.bias[i];
+  for (int i = tid; i < L * H; i += THREADS2) bias_s[i] = tp.bias[i];
   if (tid < L) scale_s[tid] = tp.inv_scale[tid];
   if (tid == 0) {
     for (int s = 0; s < RING; ++s) {
@@ -425,6 +445,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
         const float y0 = fmaf(__uint_as_float(v[2 * i]), inv_s, b[2 * i]);
         const float y1 = fmaf(__uint_as_float(v[2 * i + 1]), inv_s, b[2 * i + 1]);
         if constexpr (SPLIT == 1) {
+          // (Measured alternative: h + h tanh(h) in packed fp16 with tanh.approx.f16x2 -- one MUFU per two activations,
+          //  2.5 instructions each -- makes the epilogue 12 % faster but doubles the variant's error: not taken.)
           w[i] = pack_f16x2(silu_fast(y0), silu_fast(y1));
         } else {
           const float x0 = silu_ex2(y0), x1 = silu_ex2(y1);
@@ -468,7 +490,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
 
       for (int l = 0; l < L - 1; ++l) {
         const float inv_s = scale_s[l];
-        const float* b = bias_all + l * H + fofs;
+        const float* b = bias_s + l * H + fofs;
         // ---- half 0: N-block 0 complete after q2; its outputs may only land in K region 0 after q3 ----
         mbar_wait(bar_d0, ph_d0);
         ph_d0 ^= 1;
@@ -476,30 +498,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
         if (stamp) tp.dbg[2 + 2 * l] = clock64();
         {
           uint32_t w[NCH][16], wl[SPLIT == 3 ? NCH : 1][16];
+          if constexpr (SPLIT == 1) {  // the next chunk's TMEM read is in flight while this one is activated
+            uint32_t v[2][32];
+            tmem_ld32_issue(t_lane + fcol, v[0]);
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t v[32];
-            load_acc(uint32_t(fcol + 32 * c), v);
-            activate(v, b + 32 * c, inv_s, w[c], wl[SPLIT == 3 ? c : 0]);
+            for (int c = 0; c < NCH; ++c) {
+              tmem_ld_wait(v[c & 1]);
+              if (c + 1 < NCH) tmem_ld32_issue(t_lane + fcol + 32 * (c + 1), v[(c + 1) & 1]);
+              activate(v[c & 1], b + 32 * c, inv_s, w[c], w[c]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              uint32_t v[32];
+              load_acc(uint32_t(fcol + 32 * c), v);
+              activate(v, b + 32 * c, inv_s, w[c], wl[c]);
+            }
           }
+          if (stamp && l == 2) tp.dbg[53] = clock64();
           mbar_wait(bar_k0, ph_k0);
           ph_k0 ^= 1;
+          if (stamp && l == 2) tp.dbg[54] = clock64();
 #pragma unroll
           for (int c = 0; c < NCH; ++c) store32(fofs + 32 * c, w[c], wl[SPLIT == 3 ? c : 0]);
         }
         publish(leader_a0);
+        if (stamp && l == 2) tp.dbg[55] = clock64();
         // ---- half 1: N-block 1 complete (and K region 1 free) after q4; overlaps the next layer's q1 and, for its
         //      second NCH / 2 chunks, the first part of q2 ----
         mbar_wait(bar_d1, ph_d1);
         ph_d1 ^= 1;
         tc_fence_after();
+        if (stamp && l == 2) tp.dbg[56] = clock64();
+        if constexpr (SPLIT == 1) {
+          uint32_t v[2][32];
+          tmem_ld32_issue(t_lane + Cfg::TILE_COLS + fcol, v[0]);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t w[16];
+            tmem_ld_wait(v[c & 1]);
+            if (c + 1 < NCH) tmem_ld32_issue(t_lane + Cfg::TILE_COLS + fcol + 32 * (c + 1), v[(c + 1) & 1]);
+            activate(v[c & 1], b + Cfg::BLOCK_N + 32 * c, inv_s, w, w);
+            store32(Cfg::BLOCK_N + fofs + 32 * c, w, w);
+            if (c == NCH / 2 - 1) publish(leader_a1a);
+          }
+        } else {
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t v[32], w[16], wl[16];
-          load_acc(uint32_t(Cfg::TILE_COLS + fcol + 32 * c), v);
-          activate(v, b + Cfg::BLOCK_N + 32 * c, inv_s, w, wl);
-          store32(Cfg::BLOCK_N + fofs + 32 * c, w, wl);
-          if (c == NCH / 2 - 1) publish(leader_a1a);
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t v[32], w[16], wl[16];
+            load_acc(uint32_t(Cfg::TILE_COLS + fcol + 32 * c), v);
+            activate(v, b + Cfg::BLOCK_N + 32 * c, inv_s, w, wl);
+            store32(Cfg::BLOCK_N + fofs + 32 * c, w, wl);
+            if (c == NCH / 2 - 1) publish(leader_a1a);
+          }
         }
         publish(leader_a1b);
         if (stamp) tp.dbg[3 + 2 * l] = clock64();
@@ -513,7 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
       {
         float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_STAGE);
         const float inv_s = scale_s[L - 1];
-        const float* b = bias_all + (L - 1) * H;
+        const float* b = bias_s + (L - 1) * H;
         // my packed rows: ROWS = 64: the N-block's [fofs, fofs + 64); ROWS = 128: [128 part, 128 part + 128) (columns = rows)
         const int f_begin = (ROWS == 64) ? fofs : 128 * part, f_count = (ROWS == 64) ? 32 * NCH : 128;
         const int c_begin = (ROWS == 64) ? fcol : f_begin;

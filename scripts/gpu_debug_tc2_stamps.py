@@ -37,3 +37,4 @@ for l in range(L):
     print(f"  MMA layer {l}: start {st[32 + 2 * l] - t0} end {st[33 + 2 * l] - t0} (span {st[33 + 2 * l] - st[32 + 2 * l]})")
 print(f"  MMA warp waits over the tile: weight slots {st[48]}, a0 {st[49]}, a1 {st[50]} cycles")
 print(f"  producer waits for a free slot over the tile: leader {st[51]}, peer {st[52]} cycles")
+print(f"  layer 2 epilogue: D0 ready {st[6] - t0}, half 0 activated {st[53] - t0}, K region 0 free {st[54] - t0}, half 0 published {st[55] - t0}, D1 ready {st[56] - t0}, half 1 published {st[7] - t0}")
