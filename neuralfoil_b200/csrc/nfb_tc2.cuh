@@ -63,8 +63,7 @@ struct Tc2Cfg {
   static constexpr uint32_t ATOM_BYTES = ROWS * 128;
   static constexpr uint32_t A_BYTES = (H / ATOM_K) * ATOM_BYTES;
   static constexpr uint32_t ACT_BYTES = A_BYTES * (SPLIT == 3 ? 2 : 1);  // [A_hi][A_lo]
-  static constexpr uint32_t STAGE_BYTES = M_LAST * ROWS * 4;         // last layer's latents, fp32 [224][ROWS]
-  static constexpr uint32_t REGION_BYTES = ACT_BYTES >= STAGE_BYTES ? ACT_BYTES : STAGE_BYTES;  // the idle activation tile doubles as the staging block
+  static constexpr uint32_t REGION_BYTES = ACT_BYTES;
   // first-layer input rows [x_hi | x_lo] at k = 0..63 of one atom, outside the activation tile so that they can be
   // written a tile ahead.  (SPLIT = 1 reads them as the K = 96 concatenation [x_hi | x_lo | x_hi]: its third k-slice
   // points at the first again.)
@@ -84,7 +83,6 @@ struct Tc2Cfg {
   static constexpr int RING_FIT = int((232448 - FIXED_BYTES) / SLOT_BYTES);
   static constexpr int RING = RING_FIT > 10 ? 10 : RING_FIT;          // weight ring depth: what fits, at most 10
   static constexpr uint32_t OFF_ACT = 0;
-  static constexpr uint32_t OFF_STAGE = 0;
   static constexpr uint32_t OFF_IN = REGION_BYTES;
   static constexpr uint32_t OFF_RING = OFF_IN + IN_BYTES;
   static constexpr uint32_t OFF_BIAS = OFF_RING + RING * SLOT_BYTES;
@@ -141,6 +139,101 @@ __device__ __forceinline__ float silu_ex2(float h) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fminf(-h, 80.0f) * 1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
   return h * r;
+}
+
+// Un-flip + average + squash + decode of ONE query's group g (packed rows 4 g .. 4 g + 3 of the last layer, see
+// nfb_common.cuh: pack_last_layer_row) from the query's latents y and its twin's f, stored as scalars.  The same
+// formulas as nfb::decode_and_store [main.py:274-316]; used by the pair kernels, which decode straight from the
+// accumulators (query and twin on neighbouring TMEM lanes) instead of staging the latents in shared memory.
+__device__ __forceinline__ void decode_group_store1(const EvalParams& p, int g, long long q, const float (&y)[4], const float (&f)[4],
+                                                    float maha_o, float maha_t, float re) {
+  float o[4];
+  int row[4], n_out = 4;
+  if (g < N_BL) {  // theta_u, ue_u, theta_l, ue_l of station g
+    const float zt_u = 0.5f * (y[0] + f[2]), zu_u = 0.5f * (y[1] - f[3]);
+    const float zt_l = 0.5f * (y[2] + f[0]), zu_l = 0.5f * (y[3] - f[1]);
+    o[0] = (exp10f(zt_u) - 0.1f) / (fabsf(zu_u) * re);
+    o[1] = zu_u;
+    o[2] = (exp10f(zt_l) - 0.1f) / (fabsf(zu_l) * re);
+    o[3] = zu_l;
+    row[0] = 6 + g; row[1] = 6 + 2 * N_BL + g; row[2] = 6 + 3 * N_BL + g; row[3] = 6 + 5 * N_BL + g;
+  } else if (g < 48) {  // H_u, H_l of stations s, s + 1
+    const int s = 2 * (g - N_BL);
+    o[0] = 2.6f * expf(0.5f * (y[0] + f[2]));
+    o[1] = 2.6f * expf(0.5f * (y[1] + f[3]));
+    o[2] = 2.6f * expf(0.5f * (y[2] + f[0]));
+    o[3] = 2.6f * expf(0.5f * (y[3] + f[1]));
+    row[0] = 6 + N_BL + s; row[1] = 6 + N_BL + s + 1; row[2] = 6 + 4 * N_BL + s; row[3] = 6 + 4 * N_BL + s + 1;
+  } else if (g == 48) {  // analysis_confidence, CL, CD, CM
+    const float z0 = 0.5f * ((y[0] - maha_o) + (f[0] - maha_t));
+    const float z1 = 0.5f * (y[1] - f[1]), z2 = 0.5f * (y[2] + f[2]), z3 = 0.5f * (y[3] - f[3]);
+    o[0] = 1.0f / (1.0f + expf(-z0));
+    o[1] = 0.5f * z1;
+    o[2] = expf((z2 - 2.0f) * 2.0f);
+    o[3] = z3 / 20.0f;
+    row[0] = 0; row[1] = 1; row[2] = 2; row[3] = 3;
+  } else if (g == 49) {  // Top_Xtr, Bot_Xtr
+    o[0] = clip01_keep_nan(0.5f * (y[0] + f[1]));
+    o[1] = clip01_keep_nan(0.5f * (y[1] + f[0]));
+    o[2] = o[3] = 0.0f;
+    row[0] = 4; row[1] = 5; row[2] = row[3] = 0;
+    n_out = 2;
+  } else {
+    return;  // padding rows
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < n_out) {
+      if (p.out_f64) __stcs(static_cast<double*>(p.out) + row[k] * p.out_ld + q, double(o[k]));
+      else __stcs(static_cast<float*>(p.out) + row[k] * p.out_ld + q, o[k]);
+    }
+}
+
+__device__ __forceinline__ void store1(const EvalParams& p, int row, long long q, float v) {
+  if (p.out_f64) __stcs(static_cast<double*>(p.out) + row * p.out_ld + q, double(v));
+  else __stcs(static_cast<float*>(p.out) + row * p.out_ld + q, v);
+}
+// Four decode groups of the same kind at once (g0 .. g0 + 3, all boundary-layer theta / ue groups or all H groups): the
+// sixteen outputs are independent chains, which is what hides the MUFU and division latencies with two warps per
+// scheduler.  exp / exp10 / division by the fast intrinsics (relative error < 1e-6, two orders of magnitude inside the
+// decode tolerance of the tensor variants; the fp32 kernels keep the accurate library versions).
+__device__ __forceinline__ void decode_groups4_store(const EvalParams& p, int g0, long long q, const float (&y)[4][4], const float (&f)[4][4],
+                                                     float re) {
+  float o[4][4];
+  if (g0 < N_BL) {  // theta_u, ue_u, theta_l, ue_l of stations g0 .. g0 + 3
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+      const float zt_u = 0.5f * (y[gg][0] + f[gg][2]), zu_u = 0.5f * (y[gg][1] - f[gg][3]);
+      const float zt_l = 0.5f * (y[gg][2] + f[gg][0]), zu_l = 0.5f * (y[gg][3] - f[gg][1]);
+      o[gg][0] = __fdividef(exp2f(zt_u * 3.3219280948873623f) - 0.1f, fabsf(zu_u) * re);
+      o[gg][1] = zu_u;
+      o[gg][2] = __fdividef(exp2f(zt_l * 3.3219280948873623f) - 0.1f, fabsf(zu_l) * re);
+      o[gg][3] = zu_l;
+    }
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+      store1(p, 6 + g0 + gg, q, o[gg][0]);
+      store1(p, 6 + 2 * N_BL + g0 + gg, q, o[gg][1]);
+      store1(p, 6 + 3 * N_BL + g0 + gg, q, o[gg][2]);
+      store1(p, 6 + 5 * N_BL + g0 + gg, q, o[gg][3]);
+    }
+  } else {  // H_u, H_l of stations s, s + 1 for groups g0 .. g0 + 3 (all in [32, 48))
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+      o[gg][0] = 2.6f * __expf(0.5f * (y[gg][0] + f[gg][2]));
+      o[gg][1] = 2.6f * __expf(0.5f * (y[gg][1] + f[gg][3]));
+      o[gg][2] = 2.6f * __expf(0.5f * (y[gg][2] + f[gg][0]));
+      o[gg][3] = 2.6f * __expf(0.5f * (y[gg][3] + f[gg][1]));
+    }
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) {
+      const int s = 2 * (g0 + gg - N_BL);
+      store1(p, 6 + N_BL + s, q, o[gg][0]);
+      store1(p, 6 + N_BL + s + 1, q, o[gg][1]);
+      store1(p, 6 + 4 * N_BL + s, q, o[gg][2]);
+      store1(p, 6 + 4 * N_BL + s + 1, q, o[gg][3]);
+    }
+  }
 }
 
 // tcgen05.ld without the wait, and the wait as a separate statement that "produces" the registers, so that the compiler
@@ -378,7 +471,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
     }
   } else if (warp >= FW_WARP0) {
     // ============================ featurise-ahead warps (both CTAs) ============================
-    // Thread ft owns batch rows ft (, ft + 64): row n is query n of the tile, row NQT + n its flipped twin.
+    // Thread ft owns batch rows ft (, ft + 64): row 2 i is query i of the tile, row 2 i + 1 its flipped twin -- neighbouring
+    // TMEM lanes, so that the final decode can pair them with a warp shuffle.
     constexpr int RPT = ROWS / (32 * FW_WARPS);
     const int ft = tid - 32 * FW_WARP0;
     const uint32_t leader_in = map_to_rank(bar_in, 0);
@@ -390,8 +484,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
 #pragma unroll 1  // (one copy of the featurisation code: the kernel is instruction-cache heavy as it is)
       for (int j = 0; j < RPT; ++j) {
         const int n = ft + 64 * j;
-        const bool twin = n >= NQT;
-        const long long qi = tile_q0 + (twin ? n - NQT : n);
+        const bool twin = n & 1;
+        const long long qi = tile_q0 + (n >> 1);
         uint32_t hi[16], lo[16];
         float m, re;
         featurise_pack(p, qi, qi < p.n, twin, hi, lo, m, re);
@@ -413,7 +507,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
           *reinterpret_cast<uint4*>(inbuf + act_chunk_offset<Cfg>(n, 32 + 8 * c8)) = vl;
         }
         maha[n] = m;
-        if (n < NQT) re_s[n] = re;
+        if (!twin) re_s[n >> 1] = re;
       }
       fence_async_smem();
       __syncwarp();
@@ -429,13 +523,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
     const int g = (ROWS == 64) ? 2 * (q >> 1) + part : part;             // feature group of this thread
     const int fofs = 32 * NCH * g;                                       // first of my features within an N-block
     const int fcol = (ROWS == 64) ? 32 * NCH * part : fofs;              // ... and their first column within the accumulator tile
-    const int et = (e << 5) | lane;                                      // 0..255
     const uint32_t t_lane = tmem + (uint32_t(32 * q) << 16);
     const uint32_t leader_a0 = map_to_rank(bar_a0, 0), leader_a1a = map_to_rank(bar_a1a, 0), leader_a1b = map_to_rank(bar_a1b, 0),
                    leader_drained = map_to_rank(bar_drained, 0);
-    const bool vec_ok =
-        p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
-                  : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     uint32_t ph_d0 = 0, ph_k0 = 0, ph_d1 = 0;
     // scale, bias, SiLU and fp16 packing of 32 accumulators: w = the fp16 activations (the hi halves when SPLIT = 3),
     // wl = their fp16 remainders (SPLIT = 3 only)
@@ -556,48 +646,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
         if (stamp) tp.dbg[3 + 2 * l] = clock64();
       }
 
-      // ---- last layer: latents -> fp32 staging [224 packed rows][ROWS] (the idle activation tile when it fits) ----
+      // ---- last layer: decode straight from the accumulators.  My lane holds 32-row chunks of the packed latents of one
+      //      batch row; lane ^ 1 holds the same chunks of its twin (or query).  Of a chunk's 8 decode groups the query's
+      //      lane takes the first four and the twin's lane the last four, after swapping the halves they lack. ----
       mbar_wait(bar_d0, ph_d0);
       ph_d0 ^= 1;
       tc_fence_after();
       if (stamp) tp.dbg[20] = clock64();
       {
-        float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_STAGE);
         const float inv_s = scale_s[L - 1];
         const float* b = bias_s + (L - 1) * H;
         // my packed rows: ROWS = 64: the N-block's [fofs, fofs + 64); ROWS = 128: [128 part, 128 part + 128) (columns = rows)
         const int f_begin = (ROWS == 64) ? fofs : 128 * part, f_count = (ROWS == 64) ? 32 * NCH : 128;
         const int c_begin = (ROWS == 64) ? fcol : f_begin;
+        const bool odd = n & 1;                       // my row is a twin (n and lane have the same parity)
+        const long long qg = tile_q0 + (n >> 1);      // the query my lane pair decodes
+        const bool valid = qg < p.n;
+        const float maha_o = maha[n & ~1], maha_t = maha[n | 1], re = re_s[n >> 1];
 #pragma unroll 1
         for (int c = 0; c < f_count; c += 32) {
           const int f0 = f_begin + c;    // packed rows f0 .. f0 + 31
-          if (f0 >= M_LAST) break;       // (warp-uniform)
+          if (f0 >= M_LAST_USED) break;  // (warp-uniform; the rest is padding)
           uint32_t v[32];
           load_acc(uint32_t(c_begin + c), v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) stage[(f0 + i) * ROWS + n] = fmaf(__uint_as_float(v[i]), inv_s, b[f0 + i]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(leader_drained);  // the next tile's layer 0 may overwrite the accumulators
-        named_bar_sync(1, EPI_THREADS);
-        if (stamp) tp.dbg[21] = clock64();
-        for (int item = et; item < (M_LAST / 4) * (NQT / 4); item += EPI_THREADS) {
-          const int gq = item / (NQT / 4), qb = (item % (NQT / 4)) * 4;
-          float acc[4][8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 y = *reinterpret_cast<const float4*>(stage + (4 * gq + i) * ROWS + qb);
-            const float4 f = *reinterpret_cast<const float4*>(stage + (4 * gq + i) * ROWS + NQT + qb);
-            acc[i][0] = y.x; acc[i][1] = y.y; acc[i][2] = y.z; acc[i][3] = y.w;
-            acc[i][4] = f.x; acc[i][5] = f.y; acc[i][6] = f.z; acc[i][7] = f.w;
+          if (c + 32 >= f_count || f0 + 32 >= M_LAST_USED) {  // that was my last read of the accumulators
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_drained);  // the next tile's layer 0 may overwrite them
+            if (stamp) tp.dbg[21] = clock64();
           }
-          const long long q0 = tile_q0 + qb;
-          const long long left = p.n - q0;
-          const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
-          decode_and_store(p, gq, q0, nvalid, vec_ok, acc, maha + qb, maha + NQT + qb, re_s + qb);
+          float z[32], other[16];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) z[i] = fmaf(__uint_as_float(v[i]), inv_s, b[f0 + i]);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) other[k] = __shfl_xor_sync(0xffffffffu, odd ? z[k] : z[16 + k], 1);
+          float y[4][4], f[4][4];
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              y[gg][i] = odd ? other[4 * gg + i] : z[4 * gg + i];
+              f[gg][i] = odd ? z[16 + 4 * gg + i] : other[4 * gg + i];
+            }
+          const int g0 = (f0 >> 2) + (odd ? 4 : 0);
+          if (valid) {
+            if (f0 < 4 * 48) {  // (warp-uniform) boundary-layer and H groups: four of a kind
+              decode_groups4_store(p, g0, qg, y, f, re);
+            } else {            // the scalars' chunk: groups 48 (confidence, CL, CD, CM), 49 (Xtr), padding
+#pragma unroll
+              for (int gg = 0; gg < 2; ++gg) decode_group_store1(p, g0 + gg, qg, y[gg], f[gg], maha_o, maha_t, re);
+            }
+          }
         }
-        named_bar_sync(1, EPI_THREADS);  // staging consumed before the next tile's activations overwrite it
+        __syncwarp();
         if (lane == 0) mbar_arrive(bar_tiledone);
         if (stamp) tp.dbg[22] = clock64();
       }

@@ -459,3 +459,54 @@ def test_tensor_fp32_variant_golden_and_invariants(evaluator, golden_dir):
         torch.cuda.synchronize()
         assert torch.equal(out_p, out[:, perm]), size
         np.testing.assert_array_equal(out_m.cpu().numpy(), unmirror_outputs(out.cpu().numpy()))
+
+
+# ---------------------------------------------------------------------------------------------
+# The tensor variants run on CTA pairs (nfb_tc2.cuh); the one-SM kernels (nfb_tc.cuh) are a second, independent
+# implementation of the same pipeline, selectable with NFB_TC_ONE_SM=1 (read once per process)
+# ---------------------------------------------------------------------------------------------
+_ONE_SM_CHECK = r"""
+import sys, numpy as np
+sys.path.insert(0, {repo!r}); sys.path.insert(0, {tests!r})
+import parity
+from neuralfoil_b200 import Evaluator, synthetic
+from oracle.neuralfoil_oracle import Oracle
+extra = {{"xxxlarge": synthetic.synthetic_xxxlarge_params()}}
+ev, orc = Evaluator(device=0, extra_models=extra), Oracle(extra_models=extra)
+for size, n in (("xxlarge", 4001), ("xxxlarge", 1003), ("xxxlarge", 65)):
+    raw = synthetic.sample_training_distribution(n, seed=77 + n)
+    want = orc.evaluate_raw(raw, size)
+    for variant in ("tensor", "tensor_fp32"):
+        got = ev.evaluate_host(raw, size, out_dtype=np.float64, variant=variant)
+        parity.assert_parity(got, want, raw[19], check_distribution=False, variant=variant, label=f"{{variant}} {{size}} n={{n}}")
+print("ONE_SM_OK")
+"""
+
+
+def test_one_sm_tensor_kernels_still_match_oracle():
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    repo = Path(__file__).resolve().parents[1]
+    env = dict(os.environ, NFB_TC_ONE_SM="1")
+    code = _ONE_SM_CHECK.format(repo=str(repo), tests=str(repo / "tests"))
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ONE_SM_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+@pytest.mark.parametrize("variant", ["tensor", "tensor_fp32"])
+def test_tensor_variants_fp32_output_unaligned_and_fp64_input(evaluator, oracle, variant):
+    """Device API on the pair kernels: fp64 strided inputs, fp32 output whose leading dimension is not a multiple of 4."""
+    import torch
+
+    n = 1237
+    raw = synthetic.sample_training_distribution(n, seed=91)
+    d_raw = torch.from_numpy(raw).cuda()                     # float64 rows
+    for size in ("xxlarge", "xxxlarge"):
+        want = oracle.evaluate_raw(raw, size)
+        out = torch.full((198, n + 1), float("nan"), dtype=torch.float32, device="cuda")[:, :n]   # ld = n + 1: odd
+        res = evaluator.evaluate_device(d_raw, size, out=out, variant=variant)
+        torch.cuda.synchronize()
+        parity.assert_parity(res.cpu().numpy().astype(np.float64), want, raw[19], check_distribution=False, variant=variant, label=size)
