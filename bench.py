@@ -50,7 +50,7 @@ FLOP_PER_QUERY = {  # 2 twins x 2 x sum(in * out) over the layers, unpadded
 # DRAM traffic per query of the two xxxlarge kernels, from one `ncu --set full` capture each of this file's own
 # command at 10 M queries (profiles/r1_ncu_full_xxxlarge_ffma.txt / _tensor.txt: dram__bytes_read.sum + dram__bytes_write.sum
 # = 8.900 GB and 8.805 GB per launch; algorithmic 8.840 GB).  Reported as roofline.traffic, scaled to the run's n.
-NCU_TRAFFIC_BYTES_PER_QUERY = {("xxxlarge", "fp32"): 890.0, ("xxxlarge", "tensor"): 880.5}
+NCU_TRAFFIC_BYTES_PER_QUERY = {("xxxlarge", "fp32"): 890.0, ("xxxlarge", "tensor"): 880.4, ("xxxlarge", "tensor_fp32"): 882.9}
 METRIC = "airfoil_queries_per_sec"
 UNIT = "queries/s"
 
