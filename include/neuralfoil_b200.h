@@ -107,6 +107,21 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n,
                   const void* const* in_rows, const int64_t* in_strides, int in_dtype,
                   void* out, int64_t out_ld, int out_dtype, int64_t chunk);
 
+/* Outputs AND their derivatives with respect to the 23 raw inputs (forward mode, fp32 arithmetic, every model size).
+ * what a design optimiser needs from the path; the reference's users obtain it by tracing main.py
+ * through CasADi (studies/sequential_multifidelity_optimization.py:21-56, benchmarking/daedalus_optimization.py:14-60).
+ *   values, values_ld   198 x values_ld block as nfb_eval_device's `out` (may be NULL); bit-identical to variant 0
+ *   jac                 n x 198 x 23, contiguous: jac[q][row][t] = d output_row / d raw_input_t of query q, inputs in the
+ *                       row order of in_rows (upper 0..7, lower 8..15, LE 16, TE 17, alpha 18 [per degree], Re 19, n_crit 20,
+ *                       xtr_upper 21, xtr_lower 22)
+ * Device pointers / host pointers as for the two calls above. */
+int nfb_eval_jacobian_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                             const int64_t* in_strides, int in_dtype, void* values, int64_t values_ld,
+                             void* jac, int out_dtype, void* stream);
+int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                           const int64_t* in_strides, int in_dtype, void* values, int64_t values_ld,
+                           void* jac, int out_dtype);
+
 /* Pinned host memory helpers for callers without their own allocator. */
 int nfb_host_alloc(void** out_ptr, int64_t bytes);
 int nfb_host_free(void* ptr);

@@ -8,6 +8,7 @@ and raises if the library or a B200 is missing (there is no CPU fallback).
 
 from .geometry import Airfoil  # noqa: F401
 from .main import (  # noqa: F401
+    JACOBIAN_INPUTS,
     MODEL_SIZES,
     Evaluator,
     bl_x_points,
@@ -15,6 +16,7 @@ from .main import (  # noqa: F401
     get_aero_from_airfoil,
     get_aero_from_coordinates,
     get_aero_from_dat_file,
+    get_aero_and_jacobian_from_kulfan_parameters,
     get_aero_from_kulfan_parameters,
     output_keys,
 )

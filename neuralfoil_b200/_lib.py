@@ -51,6 +51,16 @@ _SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
          C.c_void_p, C.c_int64, C.c_int, C.c_int64],
     ),
+    "nfb_eval_jacobian_device": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+         C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p],
+    ),
+    "nfb_eval_jacobian_host": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+         C.c_void_p, C.c_int64, C.c_void_p, C.c_int],
+    ),
     "nfb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "nfb_host_free": (C.c_int, [C.c_void_p]),
     "nfb_launch_count": (C.c_int64, [C.c_void_p]),

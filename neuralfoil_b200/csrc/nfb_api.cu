@@ -14,6 +14,7 @@
 #include "nfb_small.cuh"
 #include "nfb_tc.cuh"
 #include "nfb_tc2.cuh"
+#include "nfb_jac.cuh"
 
 namespace {
 
@@ -289,6 +290,20 @@ int launch_small(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream
   using Cfg = nfb::SmallCfg<H>;
   const int grid = int((p.n + nfb::SMALL_QUERIES - 1) / nfb::SMALL_QUERIES);
   nfb::nfb_small_kernel<H><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
+template <int H>
+int launch_jac(nfb_context* ctx, const nfb::JacParams& jp, cudaStream_t stream) {
+  using Cfg = nfb::JacCfg<H>;
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_jac_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
+    configured_device = ctx->device;
+  }
+  nfb::nfb_jac_kernel<H><<<unsigned(jp.ev.n), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(jp);  // one CTA per query
   NFB_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return NFB_OK;
@@ -634,6 +649,84 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   }
   for (auto& s : ctx->slots) NFB_CUDA(cudaStreamSynchronize(s.stream));
   (void)done;
+  return NFB_OK;
+}
+
+int nfb_eval_jacobian_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                             const int64_t* in_strides, int in_dtype, void* values, int64_t values_ld, void* jac,
+                             int out_dtype, void* stream) {
+  static char dummy_out;  // check_eval_args wants a non-NULL out; `values` is optional here
+  int rc = check_eval_args(ctx, model_id, NFB_VARIANT_FP32_FFMA, n, in_rows, in_strides, in_dtype, values ? values : &dummy_out,
+                           values ? values_ld : n, out_dtype);
+  if (rc != NFB_OK || n == 0) return rc;
+  if (!jac) return fail(NFB_ERR_INVALID_ARGUMENT, "jac is NULL");
+  if (n > (int64_t(1) << 30)) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld: the Jacobian kernel takes at most 2^30 queries per call", (long long)n);
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  const Model& m = ctx->models[model_id];
+  nfb::JacParams jp;
+  for (int i = 0; i < nfb::N_RAW; ++i) {
+    jp.ev.in[i] = in_rows[i];
+    jp.ev.in_stride[i] = in_strides[i];
+  }
+  jp.ev.out = values;
+  jp.ev.out_ld = values_ld;
+  jp.ev.n = n;
+  jp.ev.blob = m.blob;
+  jp.ev.n_layers = m.n_layers;
+  jp.ev.in_f64 = (in_dtype == NFB_F64);
+  jp.ev.out_f64 = (out_dtype == NFB_F64);
+  jp.jac = jac;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (m.h_pad) {
+    case 64: return launch_jac<64>(ctx, jp, st);
+    case 128: return launch_jac<128>(ctx, jp, st);
+    case 256: return launch_jac<256>(ctx, jp, st);
+    default: return launch_jac<512>(ctx, jp, st);
+  }
+}
+
+int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                           const int64_t* in_strides, int in_dtype, void* values, int64_t values_ld, void* jac,
+                           int out_dtype) {
+  static char dummy_out;
+  int rc = check_eval_args(ctx, model_id, NFB_VARIANT_FP32_FFMA, n, in_rows, in_strides, in_dtype, values ? values : &dummy_out,
+                           values ? values_ld : n, out_dtype);
+  if (rc != NFB_OK || n == 0) return rc;
+  if (!jac) return fail(NFB_ERR_INVALID_ARGUMENT, "jac is NULL");
+  if (n > (int64_t(1) << 22)) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld: at most 2^22 queries per host call (72 KB of derivatives each)", (long long)n);
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
+  const int64_t ld = (n + 3) & ~int64_t(3);
+  std::vector<char> h_in(size_t(nfb::N_RAW) * n * isz);
+  const void* d_rows[nfb::N_RAW];
+  int64_t d_strides[nfb::N_RAW];
+  char *d_in = nullptr, *d_val = nullptr, *d_jac = nullptr;
+  const size_t jac_bytes = size_t(n) * nfb::N_OUT * nfb::JAC_T * osz, val_bytes = size_t(nfb::N_OUT) * ld * osz;
+  NFB_CUDA(cudaMalloc(&d_in, h_in.size()));
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_val); cudaFree(d_jac); };
+  if (cudaMalloc(&d_val, val_bytes) != cudaSuccess || cudaMalloc(&d_jac, jac_bytes) != cudaSuccess) {
+    cleanup();
+    return fail(NFB_ERR_CUDA, "out of device memory for %lld Jacobians", (long long)n);
+  }
+  for (int r = 0; r < nfb::N_RAW; ++r) {
+    char* dst = h_in.data() + size_t(r) * n * isz;
+    const char* src = static_cast<const char*>(in_rows[r]);
+    for (int64_t i = 0; i < n; ++i) memcpy(dst + i * isz, src + size_t(i) * in_strides[r] * isz, isz);
+    d_rows[r] = d_in + size_t(r) * n * isz;
+    d_strides[r] = 1;
+  }
+  HostSlot& s = ctx->slots[0];
+  cudaError_t e = cudaMemcpyAsync(d_in, h_in.data(), h_in.size(), cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess) {
+    rc = nfb_eval_jacobian_device(ctx, model_id, n, d_rows, d_strides, in_dtype, d_val, ld, d_jac, out_dtype, s.stream);
+    if (rc != NFB_OK) { cleanup(); return rc; }
+    e = cudaMemcpyAsync(jac, d_jac, jac_bytes, cudaMemcpyDeviceToHost, s.stream);
+  }
+  if (e == cudaSuccess && values)
+    e = cudaMemcpy2DAsync(values, size_t(values_ld) * osz, d_val, size_t(ld) * osz, size_t(n) * osz, nfb::N_OUT, cudaMemcpyDeviceToHost, s.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  cleanup();
+  if (e != cudaSuccess) return fail(NFB_ERR_CUDA, "Jacobian evaluation failed: %s", cudaGetErrorString(e));
   return NFB_OK;
 }
 

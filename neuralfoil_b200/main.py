@@ -44,6 +44,12 @@ def output_keys() -> list[str]:
 _OUTPUT_KEYS = output_keys()
 _ONES_23 = (C.c_int64 * 23)(*([1] * 23))
 
+# The 23 scalar inputs of the path in the row order of the C ABI: the columns of every Jacobian this package returns.
+JACOBIAN_INPUTS = tuple(
+    [f"upper_weights_{i}" for i in range(8)] + [f"lower_weights_{i}" for i in range(8)]
+    + ["leading_edge_weight", "TE_thickness", "alpha", "Re", "n_crit", "xtr_upper", "xtr_lower"]
+)
+
 
 def _length(x) -> int:
     """aerosandbox.numpy.length as used at main.py:161,189-193: len() of sized things, 1 for scalars."""
@@ -214,6 +220,74 @@ class Evaluator:
         rows = [np.ascontiguousarray(raw[i]) for i in range(_lib.N_RAW_ROWS)]
         block = self._evaluate_host_rows(self._model_id(model_size), rows, raw.shape[1], out_dtype, chunk, variant)
         return block[:, : raw.shape[1]]
+
+    # -- derivatives -----------------------------------------------------------------
+    def evaluate_jacobian_host(self, raw: np.ndarray, model_size: str = "xlarge", out_dtype=np.float64):
+        """
+        raw (23, N) host array -> (values (198, N), jac (N, 198, 23)): the outputs and their derivatives with
+        respect to the 23 raw inputs in row order (`JACOBIAN_INPUTS`; alpha per degree).  Forward mode in fp32 on
+        the GPU; `values` is bit-identical to `evaluate_host(..., variant="fp32")`.
+        """
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        if raw.ndim != 2 or raw.shape[0] != _lib.N_RAW_ROWS:
+            raise ValueError(f"raw must have shape (23, N), got {raw.shape}")
+        n = raw.shape[1]
+        ld = (n + 3) & ~3
+        values = np.empty((_lib.N_OUTPUT_ROWS, ld), dtype=out_dtype)
+        jac = np.empty((n, _lib.N_OUTPUT_ROWS, _lib.N_RAW_ROWS), dtype=out_dtype)
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].ctypes.data for i in range(_lib.N_RAW_ROWS)])
+        _lib.check(
+            self._lib.nfb_eval_jacobian_host(
+                self._ctx, self._model_id(model_size), n, ptrs, _ONES_23, _lib.F64,
+                values.ctypes.data_as(C.c_void_p), ld, jac.ctypes.data_as(C.c_void_p),
+                _lib.F64 if np.dtype(out_dtype) == np.float64 else _lib.F32,
+            )
+        )
+        return values[:, :n], jac
+
+    def evaluate_jacobian_device(self, raw, model_size: str = "xlarge", out_dtype=None):
+        """raw: (23, N) torch CUDA tensor (float32/float64, contiguous rows) -> (values (198, N), jac (N, 198, 23)) CUDA tensors.
+        Enqueues on torch's current stream; does not synchronise."""
+        import torch
+
+        if not isinstance(raw, torch.Tensor) or raw.dim() != 2 or raw.shape[0] != _lib.N_RAW_ROWS or not raw.is_cuda:
+            raise ValueError("raw must be a (23, N) CUDA tensor")
+        if raw.dtype not in (torch.float32, torch.float64) or raw.stride(1) != 1:
+            raise ValueError("raw must be float32 or float64 with contiguous rows")
+        n = int(raw.shape[1])
+        out_dtype = out_dtype or torch.float32
+        ld = (n + 3) & ~3
+        dev = f"cuda:{self.device}"
+        values = torch.empty((_lib.N_OUTPUT_ROWS, ld), dtype=out_dtype, device=dev)
+        jac = torch.empty((n, _lib.N_OUTPUT_ROWS, _lib.N_RAW_ROWS), dtype=out_dtype, device=dev)
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].data_ptr() for i in range(_lib.N_RAW_ROWS)])
+        _lib.check(
+            self._lib.nfb_eval_jacobian_device(
+                self._ctx, self._model_id(model_size), n, ptrs, _ONES_23,
+                _lib.F64 if raw.dtype == torch.float64 else _lib.F32,
+                C.c_void_p(values.data_ptr()), ld, C.c_void_p(jac.data_ptr()),
+                _lib.F64 if out_dtype == torch.float64 else _lib.F32,
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream),
+            )
+        )
+        return values[:, :n], jac
+
+    def get_aero_and_jacobian_from_kulfan_parameters(
+        self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"
+    ):
+        """
+        The reference's dict (as `get_aero_from_kulfan_parameters`) plus, under the same keys, the derivatives
+        of every output with respect to the 23 scalar inputs: `jac[key]` has shape (N_cases, 23), columns named by
+        `JACOBIAN_INPUTS`.  What an optimiser obtains from the reference by tracing main.py through CasADi.
+        """
+        model_id = self._model_id(model_size)
+        rows, n_cases = prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower)
+        raw = np.empty((_lib.N_RAW_ROWS, n_cases))
+        for i, r in enumerate(rows):
+            raw[i] = r
+        del model_id
+        values, jac = self.evaluate_jacobian_host(raw, model_size)
+        return dict(zip(_OUTPUT_KEYS, values)), {k: jac[:, i, :] for i, k in enumerate(_OUTPUT_KEYS)}
 
     def evaluate_host_into(self, raw: np.ndarray, model_size: str, out: np.ndarray, chunk: int = 0,
                            variant: str = "fp32") -> np.ndarray:
@@ -416,6 +490,15 @@ def get_aero_from_kulfan_parameters(
     stated in DESIGN.md.
     """
     return default_evaluator().get_aero_from_kulfan_parameters(
+        kulfan_parameters, alpha, Re, n_crit=n_crit, xtr_upper=xtr_upper, xtr_lower=xtr_lower, model_size=model_size
+    )
+
+
+def get_aero_and_jacobian_from_kulfan_parameters(
+    kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"
+):
+    """`get_aero_from_kulfan_parameters` plus d(every output)/d(every scalar input): see the `Evaluator` method."""
+    return default_evaluator().get_aero_and_jacobian_from_kulfan_parameters(
         kulfan_parameters, alpha, Re, n_crit=n_crit, xtr_upper=xtr_upper, xtr_lower=xtr_lower, model_size=model_size
     )
 

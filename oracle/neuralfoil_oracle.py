@@ -234,6 +234,98 @@ def evaluate_raw(layers, dist, raw: np.ndarray, return_latent: bool = False, fp3
 
 
 # ------------------------------------------------------------------------------------------
+# Jacobian of the path.  The reference has no gradient code of its own: its users
+# differentiate main.py by tracing it through CasADi (studies/sequential_multifidelity_optimization.py:21-56).
+# This is the forward-mode derivative of the functions above, term by term, in float64; it is pinned
+# by central differences of evaluate_raw (tests/test_oracle_golden.py::test_jacobian_matches_finite_differences).
+# Tangent arrays carry the 23 raw inputs on axis 1: (rows, 23, N).
+# ------------------------------------------------------------------------------------------
+def featurise_with_tangents(raw: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    raw = np.asarray(raw, dtype=np.float64)
+    n = raw.shape[1]
+    x = featurise(raw)
+    dx = np.zeros((N_INPUTS, N_RAW, n))
+    for i in range(17):
+        dx[i, i] = 1.0
+    dx[17, 17] = 50.0
+    k = np.pi / 180
+    a = raw[18] * k
+    dx[18, 18] = 2 * k * np.cos(2 * a)
+    dx[19, 18] = -k * np.sin(a)
+    dx[20, 18] = 2 * k * np.cos(a) * np.sin(a)
+    dx[21, 19] = 1.0 / (3.5 * raw[19])
+    dx[22, 20] = 1.0 / 4.5
+    dx[23, 21] = 1.0
+    dx[24, 22] = 1.0
+    return x, dx
+
+
+def mlp_with_tangents(layers, x: np.ndarray, dx: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    h, dh = x, dx
+    last = len(layers) - 1
+    for j, (w, b) in enumerate(layers):
+        w = np.asarray(w, dtype=np.float64)
+        h = w @ h + np.asarray(b, dtype=np.float64)[:, None]
+        dh = np.einsum("oi,itn->otn", w, dh, optimize=True)
+        if j != last:
+            s = 1 / (1 + np.exp(-h))
+            dh = (s * (1 + h * (1 - s)))[:, None, :] * dh  # d/dz [z sigmoid(z)]
+            h = h * s
+    return h, dh
+
+
+def jacobian_raw(layers, dist, raw: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """raw (23, N) -> outputs (198, N) and d outputs / d raw inputs (198, 23, N), float64."""
+    raw = np.asarray(raw, dtype=np.float64)
+    n_bl = N_BL
+    x, dx = featurise_with_tangents(raw)
+    sym = dist["inv_cov"] + dist["inv_cov"].T
+
+    def twin(xx, dxx):
+        y, dy = mlp_with_tangents(layers, xx, dxx)
+        d = xx - dist["mean"][:, None]
+        y[0] = y[0] - squared_mahalanobis(dist, xx) / (2 * N_INPUTS)
+        dy[0] = dy[0] - np.einsum("in,ij,jtn->tn", d, sym, dxx, optimize=True) / (2 * N_INPUTS)
+        return y, dy
+
+    y, dy = twin(x, dx)
+    yf, dyf = twin(flip_inputs(x), flip_inputs(dx))  # the flip is a signed permutation of axis 0: linear
+    z = (y + unflip_outputs(yf)) / 2
+    dz = (dy + unflip_outputs(dyf)) / 2
+    out = np.empty_like(z)
+    jac = np.empty_like(dz)
+    conf = 1 / (1 + np.exp(-np.clip(z[0], LN_EPS, -LN_EPS)))
+    out[0], jac[0] = conf, (conf * (1 - conf))[None, :] * dz[0]
+    out[1], jac[1] = z[1] / 2, dz[1] / 2
+    out[2] = np.exp((z[2] - 2) * 2)
+    jac[2] = 2 * out[2][None, :] * dz[2]
+    out[3], jac[3] = z[3] / 20, dz[3] / 20
+    for r in (4, 5):
+        out[r] = np.clip(z[r], 0, 1)
+        jac[r] = dz[r] * ((z[r] > 0) & (z[r] < 1))[None, :]
+    re = raw[19]
+    d_re = np.zeros((N_RAW, raw.shape[1]))
+    d_re[19] = 1.0
+    for o in (6, 6 + 3 * n_bl):
+        zt, dzt = z[o : o + n_bl], dz[o : o + n_bl]
+        ue, due = z[o + 2 * n_bl : o + 3 * n_bl], dz[o + 2 * n_bl : o + 3 * n_bl]
+        p10 = 10**zt
+        theta = (p10 - 0.1) / (np.abs(ue) * re[None, :])
+        out[o : o + n_bl] = theta
+        jac[o : o + n_bl] = (
+            (np.log(10) * p10 / (np.abs(ue) * re[None, :]))[:, None, :] * dzt
+            - (theta / ue)[:, None, :] * due  # d|ue| / |ue| = due / ue
+            - theta[:, None, :] * (d_re / re[None, :])[None, :, :]
+        )
+        hh = 2.6 * np.exp(z[o + n_bl : o + 2 * n_bl])
+        out[o + n_bl : o + 2 * n_bl] = hh
+        jac[o + n_bl : o + 2 * n_bl] = hh[:, None, :] * dz[o + n_bl : o + 2 * n_bl]
+        out[o + 2 * n_bl : o + 3 * n_bl] = ue
+        jac[o + 2 * n_bl : o + 3 * n_bl] = due
+    return out, jac
+
+
+# ------------------------------------------------------------------------------------------
 # Reference-shaped front door (validation + broadcast: main.py:154-199)
 # ------------------------------------------------------------------------------------------
 def _length(v) -> int:
@@ -296,6 +388,9 @@ class Oracle:
 
     def evaluate_raw(self, raw, model_size="xlarge", return_latent=False, fp32_mlp=False):
         return evaluate_raw(self.models[model_size], self.dist, raw, return_latent, fp32_mlp)
+
+    def jacobian_raw(self, raw, model_size="xlarge"):
+        return jacobian_raw(self.models[model_size], self.dist, raw)
 
     def get_aero_from_kulfan_parameters(
         self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"

@@ -133,3 +133,56 @@ def assert_parity(got, want, Re, check_distribution: bool = True, label: str = "
         assert rep["median_rel"] <= 2e-6, f"{label}: {rep}"
         assert rep["frac_rel_le_1e-5"] >= 0.92, f"{label}: {rep}"
     return rep
+
+
+# ---------------------------------------------------------------------------------------------------
+# Jacobian: d outputs / d raw inputs from the fp32 forward-mode kernel against the oracle's
+# analytic float64 Jacobian (oracle.jacobian_raw, itself pinned by central differences of the value oracle).
+#
+# A derivative is compared after multiplying by the size of a typical change of its input (JAC_INPUT_SCALE; Re:
+# a relative change), i.e. as "change of the output for a typical change of the input", against
+#     JAC_RTOL * (1 + JAC_UE_FLOOR / |ue|  for theta rows) * (|that change| + |the output itself|).
+# theta = (10^z - 0.1) / (|ue| Re) and its derivatives are ill-conditioned where the edge velocity passes through zero:
+# a latent error of 1e-6 (typical for fp32) changes them by 2e-6 / |ue| relative.  Measured on B200 (2,000 queries per
+# size): non-theta rows worst 3e-4, theta rows worst 0.13 at |ue| = 3e-5 (bound there: 0.67), median 1e-8 .. 6e-8.
+# Top_Xtr / Bot_Xtr are clipped to [0, 1]: their derivative jumps at the clip, so elements whose value lies within
+# 1e-4 of 0 or 1 (and is not exactly clipped in both evaluations) are not compared.
+# Bulk and worst case, as for the tensor variants: at least 99.9 % of the compared elements meet the bound above
+# (measured: all but 2e-5 of them); none misses it by more than JAC_WORST_FACTOR.  The elements that exceed it belong to
+# far-from-training queries (analysis_confidence 0.02) of the trained xxlarge, where forward mode in fp32 is off by 0.6 %
+# even in a NumPy float32 emulation and by 3 % on the GPU (sequential fma chains): a latent derivative error of 2e-3.
+# ---------------------------------------------------------------------------------------------------
+JAC_INPUT_SCALE = np.array([0.1] * 16 + [0.1, 0.002, 1.0, np.nan, 1.0, 0.1, 0.1])  # Re (row 19): relative, filled per query
+JAC_RTOL = 2e-3
+JAC_UE_FLOOR = 1e-2
+JAC_BULK_FRACTION = 1e-3
+JAC_WORST_FACTOR = 25.0
+
+
+def assert_jacobian_parity(got_j, want_j, got_v, want_v, raw, label: str = "") -> dict:
+    """got_j (n, 198, 23) from the library; want_j (198, 23, n), want_v (198, n) from the oracle; got_v (198, n); raw (23, n)."""
+    got = np.transpose(np.asarray(got_j, dtype=np.float64), (1, 2, 0))
+    assert got.shape == want_j.shape, (got.shape, want_j.shape)
+    assert np.isfinite(got).all(), f"{label}: non-finite derivative"
+    scale = np.broadcast_to(JAC_INPUT_SCALE[None, :, None], want_j.shape).copy()
+    scale[:, 19, :] = raw[19][None, :]
+    dw, dg = want_j * scale, got * scale
+    tol = JAC_RTOL * (np.abs(dw) + np.abs(want_v)[:, None, :])
+    ue = np.abs(want_v[ROW_UE])  # theta rows and ue rows are in the same order
+    tol[ROW_THETA] *= (1.0 + JAC_UE_FLOOR / np.maximum(ue, 1e-300))[:, None, :]
+    compare = np.ones(want_j.shape, dtype=bool)
+    for r in (4, 5):
+        inside = (want_v[r] > 1e-4) & (want_v[r] < 1 - 1e-4) & (got_v[r] > 1e-4) & (got_v[r] < 1 - 1e-4)
+        clipped = ((want_v[r] == 0) | (want_v[r] == 1)) & (got_v[r] == want_v[r])
+        compare[r] = (inside | clipped)[None, :]
+    err = np.abs(dg - dw)
+    ratio = np.where(compare, err / np.maximum(tol, 1e-300), 0.0)
+    k = np.unravel_index(np.argmax(ratio), ratio.shape)
+    rel = err / np.maximum(np.abs(dw) + np.abs(want_v)[:, None, :], 1e-300)
+    rep = {"worst_ratio": float(ratio.max()), "median_rel": float(np.median(rel[compare])), "compared": float(compare.mean()),
+           "frac_outside": float((ratio > 1.0).sum() / compare.sum())}
+    assert ratio.max() <= JAC_WORST_FACTOR, f"{label}: derivative of output row {k[0]} w.r.t. input {k[1]} (query {k[2]}): got {got[k]:.6g}, want {want_j[k]:.6g}, error/tolerance {ratio.max():.2f}"
+    assert rep["frac_outside"] <= JAC_BULK_FRACTION, f"{label}: {rep['frac_outside']:.2e} of the derivatives outside the bound"
+    assert rep["median_rel"] <= 1e-6, f"{label}: median relative error of the derivatives {rep['median_rel']:.2e}"
+    assert rep["compared"] > 0.99
+    return rep

@@ -510,3 +510,57 @@ def test_tensor_variants_fp32_output_unaligned_and_fp64_input(evaluator, oracle,
         res = evaluator.evaluate_device(d_raw, size, out=out, variant=variant)
         torch.cuda.synchronize()
         parity.assert_parity(res.cpu().numpy().astype(np.float64), want, raw[19], check_distribution=False, variant=variant, label=size)
+
+
+# ---------------------------------------------------------------------------------------------
+# Jacobian kernel: values bit-identical to the fp32 path, derivatives against the oracle's analytic Jacobian
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", MODEL_SIZES)
+def test_jacobian_matches_oracle(evaluator, oracle, size):
+    n = 400 if size in ("xxlarge", "xxxlarge") else 1000
+    raw = synthetic.sample_training_distribution(n, seed=31)
+    want_v, want_j = oracle.jacobian_raw(raw, size)
+    got_v, got_j = evaluator.evaluate_jacobian_host(raw, size)
+    assert got_v.shape == (198, n) and got_j.shape == (n, 198, 23)
+    np.testing.assert_array_equal(got_v, evaluator.evaluate_host(raw, size, out_dtype=np.float64))  # same arithmetic as the fp32 kernels
+    parity.assert_jacobian_parity(got_j, want_j, got_v, want_v, raw, label=size)
+
+
+@pytest.mark.parametrize("n", [1, 3, 17])
+def test_jacobian_small_batches_and_device_api(evaluator, oracle, n):
+    import torch
+
+    raw = synthetic.sample_training_distribution(n, seed=40 + n)
+    want_v, want_j = oracle.jacobian_raw(raw, "xlarge")
+    got_v, got_j = evaluator.evaluate_jacobian_host(raw, "xlarge", out_dtype=np.float32)
+    assert got_v.dtype == np.float32 and got_j.dtype == np.float32
+    parity.assert_jacobian_parity(got_j, want_j, got_v.astype(np.float64), want_v, raw)
+    dv, dj = evaluator.evaluate_jacobian_device(torch.from_numpy(raw.astype(np.float32)).cuda(), "xlarge")
+    torch.cuda.synchronize()
+    assert dv.shape == (198, n) and dj.shape == (n, 198, 23) and dj.dtype == torch.float32
+    # float32 inputs differ from the float64 ones by rounding only
+    np.testing.assert_allclose(dj.cpu().numpy()[:, 1, 18], got_j[:, 1, 18], rtol=2e-3, atol=1e-6)  # dCL/dalpha
+
+
+def test_jacobian_dict_api_and_symmetry(evaluator):
+    """Reference-shaped front door; for a symmetric airfoil at alpha = 0 the odd outputs have even inputs' derivatives = 0."""
+    import neuralfoil_b200 as nf
+
+    w = np.array([0.15, 0.20, 0.15, 0.20, 0.15, 0.20, 0.15, 0.15])
+    sym = dict(upper_weights=w, lower_weights=-w, leading_edge_weight=0.0, TE_thickness=0.002)
+    aero, jac = evaluator.get_aero_and_jacobian_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size="large")
+    ref = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size="large")
+    assert list(aero) == list(ref) and all(np.array_equal(aero[k], ref[k]) for k in ref)
+    assert set(jac) == set(ref) and jac["CL"].shape == (1, 23) and len(nf.JACOBIAN_INPUTS) == 23
+    i_alpha, i_re, i_te = nf.JACOBIAN_INPUTS.index("alpha"), nf.JACOBIAN_INPUTS.index("Re"), nf.JACOBIAN_INPUTS.index("TE_thickness")
+    assert jac["CL"][0, i_alpha] > 0.05                      # lift-curve slope, per degree
+    assert jac["CL"][0, i_re] == 0.0 and jac["CL"][0, i_te] == 0.0 and jac["CM"][0, i_re] == 0.0   # exact by symmetry
+    assert jac["CD"][0, i_alpha] == 0.0
+    # mirrored pairs of Kulfan weights: dCL/d upper_i == dCL/d lower_i at a symmetric point (both raise camber)
+    np.testing.assert_array_equal(jac["CL"][0, 0:8], jac["CL"][0, 8:16])
+    # finite-difference sanity check of the slope through the value path (fp32 values: loose)
+    a1 = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.5, Re=1e6, model_size="large")["CL"][0]
+    a0 = evaluator.get_aero_from_kulfan_parameters(sym, alpha=-0.5, Re=1e6, model_size="large")["CL"][0]
+    assert abs((a1 - a0) - jac["CL"][0, i_alpha]) < 2e-3
+    with pytest.raises(ValueError):
+        evaluator.evaluate_jacobian_host(np.zeros((22, 4)), "large")

@@ -129,3 +129,24 @@ def test_synthetic_xxxlarge_is_deterministic():
     assert [a[k].shape for k in a] == [b[k].shape for k in b]
     assert all(np.array_equal(a[k], b[k]) for k in a)
     assert sum(v.size for v in a.values()) == 1_428_166  # reference README.md:246
+
+
+def test_jacobian_matches_finite_differences():
+    """The oracle's analytic Jacobian against central differences of the pinned value oracle."""
+    o = orc.Oracle()
+    raw = synthetic.sample_training_distribution(24, seed=5)
+    for size in ("xxsmall", "large"):
+        out, jac = o.jacobian_raw(raw, size)
+        ref = o.evaluate_raw(raw, size)
+        np.testing.assert_allclose(out, ref, rtol=1e-11, atol=0)
+        inside = (ref[4:6] > 1e-3) & (ref[4:6] < 1 - 1e-3) | (ref[4:6] == 0) | (ref[4:6] == 1)   # away from the Xtr clip
+        for t in range(23):
+            s_t = np.maximum(np.abs(raw[t]), 1e-2)
+            h = 1e-6 * s_t
+            rp, rm = raw.copy(), raw.copy()
+            rp[t] += h
+            rm[t] -= h
+            fd = (o.evaluate_raw(rp, size) - o.evaluate_raw(rm, size)) / (2 * h)
+            err = np.abs(jac[:, t, :] - fd) * s_t / (np.abs(fd) * s_t + 1e-3 * (np.abs(ref) + 1e-6))
+            err[4:6] = np.where(inside, err[4:6], 0.0)
+            assert err.max() < 2e-4, (size, t, err.max())
