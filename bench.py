@@ -321,6 +321,26 @@ def main():
         tensor_fp32_extra = measure_other("tensor_fp32")
         tensor_extra = measure_other("tensor")
 
+    # ---- the Jacobian kernel, briefly: outputs + 198 x 23 derivatives per query, device-resident ----
+    jacobian_extra = None
+    if variant == "fp32" and not args.no_tensor_extra:
+        nj = min(n, 20_000)
+        rj = raw_dev[:, :nj].contiguous()
+        for _ in range(2):
+            ev.evaluate_jacobian_device(rj, size)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(3):
+            ev.evaluate_jacobian_device(rj, size)
+        t1e.record()
+        barrier()
+        t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / 3
+        jf = 24 * FLOP_PER_QUERY[size] * nj / (t_ms * 1e-3) / 1e12
+        jacobian_extra = {"value": world * nj / (t_ms * 1e-3), "unit": "jacobians/s", "queries_per_launch": nj, "ms_per_launch": t_ms,
+                          "kernel": "nfb_jac_kernel<H> (forward mode, fp32 FFMA: the query, its twin and 23 tangents each)",
+                          "achieved_tflops": jf, "note": "24 x the value path's FLOP per query; one CTA per query"}
+
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -387,7 +407,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, weights_note),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "tensor_variant": tensor_extra,
-            "tensor_fp32_variant": tensor_fp32_extra,
+            "tensor_fp32_variant": tensor_fp32_extra, "jacobian": jacobian_extra,
             "checksum_first_1000": checksum,
         }
         print(json.dumps(line), flush=True)
