@@ -90,6 +90,9 @@ struct nfb_context {
   bool have_distribution = false;
   Model models[NFB_MAX_MODELS];
   HostSlot slots[2];
+  void* jac_dev = nullptr;   // nfb_eval_jacobian_host: [inputs | values | jac] device block and its pinned host mirror
+  void* jac_host = nullptr;
+  size_t jac_dev_bytes = 0, jac_host_bytes = 0;
   int64_t launches = 0;
   long long* tc_debug = nullptr;  // device buffer for nfb_debug_tc_stamps (64 x clock64), normally NULL
 };
@@ -464,6 +467,8 @@ void nfb_destroy(nfb_context* ctx) {
     if (s.h_stage) cudaFreeHost(s.h_stage);
   }
   if (ctx->tc_debug) cudaFree(ctx->tc_debug);
+  if (ctx->jac_dev) cudaFree(ctx->jac_dev);
+  if (ctx->jac_host) cudaFreeHost(ctx->jac_host);
   delete ctx;
 }
 
@@ -697,36 +702,55 @@ int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void
   NFB_CUDA(cudaSetDevice(ctx->device));
   const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
   const int64_t ld = (n + 3) & ~int64_t(3);
-  std::vector<char> h_in(size_t(nfb::N_RAW) * n * isz);
+  auto align = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t in_bytes = align(size_t(nfb::N_RAW) * n * isz), val_bytes = align(size_t(nfb::N_OUT) * ld * osz);
+  const size_t jac_bytes = size_t(n) * nfb::N_OUT * nfb::JAC_T * osz, total = in_bytes + val_bytes + jac_bytes;
+  if ((rc = ensure(&ctx->jac_dev, &ctx->jac_dev_bytes, total, false)) != NFB_OK) return rc;
+  char* const d_in = static_cast<char*>(ctx->jac_dev);
+  char* const d_val = d_in + in_bytes;
+  char* const d_jac = d_val + val_bytes;
+  HostSlot& s = ctx->slots[0];
+  NFB_CUDA(cudaStreamSynchronize(s.stream));
   const void* d_rows[nfb::N_RAW];
   int64_t d_strides[nfb::N_RAW];
-  char *d_in = nullptr, *d_val = nullptr, *d_jac = nullptr;
-  const size_t jac_bytes = size_t(n) * nfb::N_OUT * nfb::JAC_T * osz, val_bytes = size_t(nfb::N_OUT) * ld * osz;
-  NFB_CUDA(cudaMalloc(&d_in, h_in.size()));
-  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_val); cudaFree(d_jac); };
-  if (cudaMalloc(&d_val, val_bytes) != cudaSuccess || cudaMalloc(&d_jac, jac_bytes) != cudaSuccess) {
-    cleanup();
-    return fail(NFB_ERR_CUDA, "out of device memory for %lld Jacobians", (long long)n);
-  }
   for (int r = 0; r < nfb::N_RAW; ++r) {
-    char* dst = h_in.data() + size_t(r) * n * isz;
-    const char* src = static_cast<const char*>(in_rows[r]);
-    for (int64_t i = 0; i < n; ++i) memcpy(dst + i * isz, src + size_t(i) * in_strides[r] * isz, isz);
     d_rows[r] = d_in + size_t(r) * n * isz;
     d_strides[r] = 1;
   }
-  HostSlot& s = ctx->slots[0];
-  cudaError_t e = cudaMemcpyAsync(d_in, h_in.data(), h_in.size(), cudaMemcpyHostToDevice, s.stream);
-  if (e == cudaSuccess) {
+  auto pack_inputs = [&](char* dst_base) {
+    for (int r = 0; r < nfb::N_RAW; ++r) {
+      char* dst = dst_base + size_t(r) * n * isz;
+      const char* src = static_cast<const char*>(in_rows[r]);
+      if (in_strides[r] == 1) memcpy(dst, src, size_t(n) * isz);
+      else for (int64_t i = 0; i < n; ++i) memcpy(dst + i * isz, src + size_t(i) * in_strides[r] * isz, isz);
+    }
+  };
+  // An optimiser's per-iteration call: everything through one pinned block -- one H2D copy, one launch, one D2H copy.
+  const bool small = total <= (size_t(32) << 20);
+  if (small) {
+    if ((rc = ensure(&ctx->jac_host, &ctx->jac_host_bytes, total, true)) != NFB_OK) return rc;
+    char* const h = static_cast<char*>(ctx->jac_host);
+    pack_inputs(h);
+    NFB_CUDA(cudaMemcpyAsync(d_in, h, in_bytes, cudaMemcpyHostToDevice, s.stream));
     rc = nfb_eval_jacobian_device(ctx, model_id, n, d_rows, d_strides, in_dtype, d_val, ld, d_jac, out_dtype, s.stream);
-    if (rc != NFB_OK) { cleanup(); return rc; }
-    e = cudaMemcpyAsync(jac, d_jac, jac_bytes, cudaMemcpyDeviceToHost, s.stream);
+    if (rc != NFB_OK) return rc;
+    NFB_CUDA(cudaMemcpyAsync(h + in_bytes, d_val, val_bytes + jac_bytes, cudaMemcpyDeviceToHost, s.stream));
+    NFB_CUDA(cudaStreamSynchronize(s.stream));
+    memcpy(jac, h + in_bytes + val_bytes, jac_bytes);
+    if (values)
+      for (int r = 0; r < nfb::N_OUT; ++r)
+        memcpy(static_cast<char*>(values) + size_t(r) * values_ld * osz, h + in_bytes + size_t(r) * ld * osz, size_t(n) * osz);
+  } else {
+    std::vector<char> h_in(size_t(nfb::N_RAW) * n * isz);
+    pack_inputs(h_in.data());
+    NFB_CUDA(cudaMemcpyAsync(d_in, h_in.data(), h_in.size(), cudaMemcpyHostToDevice, s.stream));
+    rc = nfb_eval_jacobian_device(ctx, model_id, n, d_rows, d_strides, in_dtype, d_val, ld, d_jac, out_dtype, s.stream);
+    if (rc != NFB_OK) return rc;
+    NFB_CUDA(cudaMemcpyAsync(jac, d_jac, jac_bytes, cudaMemcpyDeviceToHost, s.stream));
+    if (values)
+      NFB_CUDA(cudaMemcpy2DAsync(values, size_t(values_ld) * osz, d_val, size_t(ld) * osz, size_t(n) * osz, nfb::N_OUT, cudaMemcpyDeviceToHost, s.stream));
+    NFB_CUDA(cudaStreamSynchronize(s.stream));
   }
-  if (e == cudaSuccess && values)
-    e = cudaMemcpy2DAsync(values, size_t(values_ld) * osz, d_val, size_t(ld) * osz, size_t(n) * osz, nfb::N_OUT, cudaMemcpyDeviceToHost, s.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-  cleanup();
-  if (e != cudaSuccess) return fail(NFB_ERR_CUDA, "Jacobian evaluation failed: %s", cudaGetErrorString(e));
   return NFB_OK;
 }
 

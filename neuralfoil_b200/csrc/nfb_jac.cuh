@@ -31,7 +31,11 @@ struct JacParams {
 
 template <int H>
 struct JacCfg {
-  static constexpr int THREADS = H > 256 ? H : 256;  // >= 224 rows of the last layer
+  // One output row per thread; TWO for the 512-wide model (256 threads, 96 accumulators each, 255 registers): an
+  // activation row read from shared memory then feeds 96 FFMAs instead of 48 -- with one row per thread the broadcast
+  // LDS.128s (12 per 48 FFMA) tie with the FFMA pipe, and 512 threads cap the registers at 128.
+  static constexpr int RPT = H > 256 ? 2 : 1;
+  static constexpr int THREADS = 256;                // >= 224 rows of the last layer
   static constexpr int KMAX = H > K0_PAD ? H : K0_PAD;
   static constexpr size_t SMEM_BYTES =
       sizeof(float) * (size_t(KMAX) * JAC_COLS + size_t(M_LAST) * JAC_COLS + JAC_COLS + 8) + sizeof(double) * 2 * N_IN;
@@ -130,58 +134,76 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, 1) nfb_jac_kernel(const Ja
   }
   __syncthreads();
 
-  // ---- layers: one thread per output row, 48 columns in registers ----
-  auto affine = [&](const float* __restrict__ w, int ldw, int K, float bias, float (&acc)[JAC_COLS]) {
+  // ---- layers: RPT output rows per thread (rows tid, tid + 256), 48 columns each in registers ----
+  constexpr int RPT = Cfg::RPT;
+  auto affine = [&](const float* __restrict__ w, int ldw, int K, int rows_here, const float* __restrict__ bias, float (&acc)[RPT][JAC_COLS]) {
 #pragma unroll
-    for (int c = 0; c < JAC_COLS; ++c) acc[c] = (c % JAC_HALF == 0) ? bias : 0.0f;
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      float wv[8];
+    for (int r = 0; r < RPT; ++r) {
+      const float b = (r < rows_here) ? __ldg(bias + tid + 256 * r) : 0.0f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + size_t(k0 + u) * ldw);
+      for (int c = 0; c < JAC_COLS; ++c) acc[r][c] = (c % JAC_HALF == 0) ? b : 0.0f;
+    }
+    constexpr int U = (RPT == 1) ? 8 : 4;  // weight loads in flight per row
+    for (int k0 = 0; k0 < K; k0 += U) {
+      float wv[RPT][U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int u = 0; u < U; ++u) wv[r][u] = (r < rows_here) ? __ldg(w + size_t(k0 + u) * ldw + tid + 256 * r) : 0.0f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         const float4* a4 = reinterpret_cast<const float4*>(act + (k0 + u) * JAC_COLS);
 #pragma unroll
         for (int c4 = 0; c4 < JAC_COLS / 4; ++c4) {
           const float4 a = a4[c4];
-          acc[4 * c4 + 0] = fmaf(wv[u], a.x, acc[4 * c4 + 0]);
-          acc[4 * c4 + 1] = fmaf(wv[u], a.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(wv[u], a.z, acc[4 * c4 + 2]);
-          acc[4 * c4 + 3] = fmaf(wv[u], a.w, acc[4 * c4 + 3]);
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            acc[r][4 * c4 + 0] = fmaf(wv[r][u], a.x, acc[r][4 * c4 + 0]);
+            acc[r][4 * c4 + 1] = fmaf(wv[r][u], a.y, acc[r][4 * c4 + 1]);
+            acc[r][4 * c4 + 2] = fmaf(wv[r][u], a.z, acc[r][4 * c4 + 2]);
+            acc[r][4 * c4 + 3] = fmaf(wv[r][u], a.w, acc[r][4 * c4 + 3]);
+          }
         }
       }
     }
   };
+  auto put_rows = [&](float* dst, int rows_here, const float (&acc)[RPT][JAC_COLS]) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+      if (r < rows_here) {
+#pragma unroll
+        for (int c4 = 0; c4 < JAC_COLS / 4; ++c4)
+          reinterpret_cast<float4*>(dst + (tid + 256 * r) * JAC_COLS)[c4] =
+              make_float4(acc[r][4 * c4], acc[r][4 * c4 + 1], acc[r][4 * c4 + 2], acc[r][4 * c4 + 3]);
+      }
+  };
   for (int l = 0; l < L - 1; ++l) {
     const int K = (l == 0) ? K0_PAD : H;
     const float* w = p.blob + blob_layer_offset<H>(l);
-    float acc[JAC_COLS];
-    if (tid < H) {
-      affine(w + tid, H, K, __ldg(w + size_t(K) * H + tid), acc);
+    const int rows_here = (tid + 256 * (RPT - 1) < H) ? RPT : (tid < H ? 1 : 0);
+    float acc[RPT][JAC_COLS];
+    if (rows_here) {
+      affine(w, H, K, rows_here, w + size_t(K) * H, acc);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float z = acc[half * JAC_HALF], slope = silu_slope(z);
-        acc[half * JAC_HALF] = silu(z);
+      for (int r = 0; r < RPT; ++r)
 #pragma unroll
-        for (int t = 1; t < JAC_HALF; ++t) acc[half * JAC_HALF + t] *= slope;
-      }
+        for (int half = 0; half < 2; ++half) {
+          const float z = acc[r][half * JAC_HALF], slope = silu_slope(z);
+          acc[r][half * JAC_HALF] = silu(z);
+#pragma unroll
+          for (int t = 1; t < JAC_HALF; ++t) acc[r][half * JAC_HALF + t] *= slope;
+        }
     }
     __syncthreads();  // everybody has read the layer's input
-    if (tid < H) {
-#pragma unroll
-      for (int c4 = 0; c4 < JAC_COLS / 4; ++c4)
-        reinterpret_cast<float4*>(act + tid * JAC_COLS)[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-    }
+    if (rows_here) put_rows(act, rows_here, acc);
     __syncthreads();
   }
   {
     const float* w = p.blob + blob_layer_offset<H>(L - 1);
-    if (tid < M_LAST) {
-      float acc[JAC_COLS];
-      affine(w + tid, M_LAST, H, __ldg(w + size_t(H) * M_LAST + tid), acc);
-#pragma unroll
-      for (int c4 = 0; c4 < JAC_COLS / 4; ++c4)
-        reinterpret_cast<float4*>(stage + tid * JAC_COLS)[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+    if (tid < M_LAST) {  // 224 rows: one per thread
+      float acc[RPT][JAC_COLS];
+      affine(w, M_LAST, H, 1, w + size_t(H) * M_LAST, acc);
+      put_rows(stage, 1, acc);
     }
   }
   __syncthreads();
