@@ -18,9 +18,9 @@
 //     CTA's MMA warp has nothing to issue; it relays "my half of slot s has landed" to the leader's full barrier.
 //   * Layer pipeline: the half-layer schedule of nfb_tc.cuh (quarters q1..q4), with the epilogue -> MMA barriers in
 //     the leader CTA (both CTAs' epilogue warps arrive there) and the MMA -> epilogue barriers signalled in both CTAs
-//     by multicast commits.  K region 1 of a layer is swept chunk-major (k_slice_at) and its readiness is signalled in
-//     two steps (a1a, a1b), so q2 starts while the second half of the previous layer's N-block 1 is still being
-//     activated.
+//     by multicast commits.  K region 1 of a layer is swept chunk-major (k_slice_at) and its readiness is signalled
+//     chunk by chunk (barriers a1[0..NCH)), so q2 starts while the rest of the previous layer's N-block 1 is still
+//     being activated.
 //   * Featurisation runs ahead: two extra warps compute the NEXT tile's 25 inputs and Mahalanobis terms (fp64, ~7,000
 //     latency-bound cycles per tile) while the current tile's layers run, and drop them into a small first-layer input
 //     buffer of their own as soon as layer 0 of the current tile has consumed it.  The next tile's layer 0 then starts
@@ -94,22 +94,22 @@ struct Tc2Cfg {
   static_assert(H == 512 || H == 256, "tensor-core variants: 512- or 256-wide models");
   static_assert(SPLIT == 1 || SPLIT == 3, "one MMA per product, or the three-term fp16 split");
   static_assert(NCH == 2 || NCH == 4, "chunks per thread per half");
-  static_assert(RING >= 3 && 2 * RING + 10 <= N_BARS, "weight ring / barrier block");
+  static_assert(RING >= 3 && 2 * RING + 12 <= N_BARS, "weight ring / barrier block");
   static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
 
   __host__ __device__ static constexpr int k_slices(int l) { return (l == 0 ? K0 : H) / SLICE_K; }
   __host__ __device__ static constexpr int n_blocks(int l, int L) { return l == L - 1 ? LAST_ROWS / BLOCK_N : 2; }
   __host__ __device__ static constexpr int slots_in_layer(int l, int L) { return k_slices(l) * n_blocks(l, L) / SPS; }
   // Position in a layer's K sweep -> k-slice.  K region 1 (the second half of the inputs) is swept chunk-major: first the
-  // slices that hold the chunks every epilogue thread of the previous layer writes in its first NCH / 2 rounds, then the
-  // others, so the sweep can start on the former while the latter are still being activated (barriers a1a / a1b).
-  // Thread group g writes slices g NCH .. g NCH + NCH - 1 of the region, one per round.
+  // G slices that hold the chunk every epilogue thread of the previous layer writes first, then those of the second
+  // chunk, ... so the sweep can start on a chunk while the later ones are still being activated (barriers a1[chunk]).
+  // Thread group g writes slices g NCH .. g NCH + NCH - 1 of the region, one per chunk.
   __host__ __device__ static constexpr int k_slice_at(int pos, int kt) {
     if (kt != H / SLICE_K || pos < kt / 2) return pos;  // (the first layer's few slices all count as region 0)
-    const int R = kt / 2, hn = NCH / 2, j = pos - R;
-    const int phase = j / (R / 2), jj = j % (R / 2);
-    return R + (jj / hn) * NCH + phase * hn + jj % hn;
+    const int R = kt / 2, j = pos - R;
+    return R + (j % G) * NCH + j / G;
   }
+  static_assert(G % SPS == 0, "a chunk's slices are whole ring slots");
 };
 
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -275,9 +275,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
   float* const maha2 = reinterpret_cast<float*>(smem + Cfg::OFF_MAHA);
   float* const re2 = reinterpret_cast<float*>(smem + Cfg::OFF_RE);
   const uint32_t bar_full = smem_u32(smem + Cfg::OFF_BARS), bar_empty = bar_full + 8 * RING;
-  // Layer pipeline barriers (nfb_tc.cuh).  a0 / a1a / a1b are waited on in the leader CTA only: K region 0 / the first /
+  // Layer pipeline barriers (nfb_tc.cuh).  a0 / a1[c] are waited on in the leader CTA only: K region 0 / chunk c of K region 1 /
   // the second half of K region 1's slices are in shared memory and the TMEM they came from is drained.
-  const uint32_t bar_a0 = bar_empty + 8 * RING, bar_a1a = bar_a0 + 8, bar_a1b = bar_a1a + 8, bar_d0 = bar_a1b + 8, bar_k0 = bar_d0 + 8,
+  const uint32_t bar_a0 = bar_empty + 8 * RING, bar_a1 = bar_a0 + 8, bar_d0 = bar_a1 + 8 * 4, bar_k0 = bar_d0 + 8,
                  bar_d1 = bar_k0 + 8;
   // Tile hand-over barriers.  in (leader): the featurise warps of both CTAs have written the tile's input rows.
   // drained (leader): the epilogue warps of both CTAs have read the last layer's accumulators.  infree (both, by commit):
@@ -301,8 +301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
       mbar_init(bar_empty + 8 * s, 1);                     // one multicast commit
     }
     mbar_init(bar_a0, 2 * EPI_WARPS);                      // the epilogue warps of both CTAs
-    mbar_init(bar_a1a, 2 * EPI_WARPS);
-    mbar_init(bar_a1b, 2 * EPI_WARPS);
+    for (int c = 0; c < NCH; ++c) mbar_init(bar_a1 + 8 * c, 2 * EPI_WARPS);
     mbar_init(bar_d0, 1);
     mbar_init(bar_k0, 1);
     mbar_init(bar_d1, 1);
@@ -366,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
     const uint32_t a_act = (smem_u32(act) >> 4) & 0x3FFF, a_in = (smem_u32(inbuf) >> 4) & 0x3FFF, b0 = (smem_u32(ring) >> 4) & 0x3FFF;
     constexpr uint32_t WLO = PIECE_BYTES >> 4;
     uint32_t a0 = a_in, LO = 4;  // A base and distance of the lo half: layer 0 reads [x_hi | x_lo] of the input buffer, the others A_hi / A_lo
-    uint32_t s = 0, ph = 0, ph_a0 = 0, ph_a1 = 0, ph_in = 0, ph_dr = 0;  // (a1a and a1b flip together)
+    uint32_t s = 0, ph = 0, ph_a0 = 0, ph_a1 = 0, ph_in = 0, ph_dr = 0;  // (the a1 barriers flip together)
     long long wait_full = 0, wait_a0 = 0, wait_a1 = 0;  // diagnostics (tp.dbg only): cycles this warp spent waiting
     const bool timing = tp.dbg && blockIdx.x == 0;
     // MMAs of one position of a K sweep (k-slice ks of the A tile; its weights at byte offset b_ofs >> 4 of the ring)
@@ -434,7 +433,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
       for (int l = 1; l < L; ++l) {
         const int kt = Cfg::k_slices(l);
         const int kh = kt / 2;                                 // slices in K region 0
-        const int km = kh + (kt - kh) / 2;
         long long c0 = timing ? clock64() : 0;
         mbar_wait(bar_a0, ph_a0);
         if (timing) wait_a0 += clock64() - c0;
@@ -442,17 +440,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
         tc_fence_after();
         if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[32 + 2 * l] = clock64();
         issue(0, kt, 0, kh);                                   // q1
-        c0 = timing ? clock64() : 0;
-        mbar_wait(bar_a1a, ph_a1);
-        if (timing) wait_a1 += clock64() - c0;
-        tc_fence_after();
-        issue(0, kt, kh, km);                                  // q2, the slices written first
-        c0 = timing ? clock64() : 0;
-        mbar_wait(bar_a1b, ph_a1);
-        if (timing) wait_a1 += clock64() - c0;
+        for (int c = 0; c < NCH; ++c) {                        // q2, chunk by chunk as the previous layer's epilogue delivers
+          c0 = timing ? clock64() : 0;
+          mbar_wait(bar_a1 + 8 * c, ph_a1);
+          if (timing) wait_a1 += clock64() - c0;
+          tc_fence_after();
+          issue(0, kt, kh + c * Cfg::G, kh + (c + 1) * Cfg::G);
+        }
         ph_a1 ^= 1;
-        tc_fence_after();
-        issue(0, kt, km, kt);                                  // q2, the rest
         if (l != L - 1) {
           commit(bar_d0);
           issue(1, kt, 0, kh);                                 // q3
@@ -524,7 +519,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
     const int fofs = 32 * NCH * g;                                       // first of my features within an N-block
     const int fcol = (ROWS == 64) ? 32 * NCH * part : fofs;              // ... and their first column within the accumulator tile
     const uint32_t t_lane = tmem + (uint32_t(32 * q) << 16);
-    const uint32_t leader_a0 = map_to_rank(bar_a0, 0), leader_a1a = map_to_rank(bar_a1a, 0), leader_a1b = map_to_rank(bar_a1b, 0),
+    const uint32_t leader_a0 = map_to_rank(bar_a0, 0), leader_a1 = map_to_rank(bar_a1, 0),
                    leader_drained = map_to_rank(bar_drained, 0);
     uint32_t ph_d0 = 0, ph_k0 = 0, ph_d1 = 0;
     // scale, bias, SiLU and fp16 packing of 32 accumulators: w = the fp16 activations (the hi halves when SPLIT = 3),
@@ -630,7 +625,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
             if (c + 1 < NCH) tmem_ld32_issue(t_lane + Cfg::TILE_COLS + fcol + 32 * (c + 1), v[(c + 1) & 1]);
             activate(v[c & 1], b + Cfg::BLOCK_N + 32 * c, inv_s, w, w);
             store32(Cfg::BLOCK_N + fofs + 32 * c, w, w);
-            if (c == NCH / 2 - 1) publish(leader_a1a);
+            publish(leader_a1 + 8 * c);
           }
         } else {
 #pragma unroll 1
@@ -639,10 +634,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
             load_acc(uint32_t(Cfg::TILE_COLS + fcol + 32 * c), v);
             activate(v, b + Cfg::BLOCK_N + 32 * c, inv_s, w, wl);
             store32(Cfg::BLOCK_N + fofs + 32 * c, w, wl);
-            if (c == NCH / 2 - 1) publish(leader_a1a);
+            publish(leader_a1 + 8 * c);
           }
         }
-        publish(leader_a1b);
         if (stamp) tp.dbg[3 + 2 * l] = clock64();
       }
 
