@@ -157,11 +157,12 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, 1) nfb_jac_kernel(const Ja
         for (int c4 = 0; c4 < JAC_COLS / 4; ++c4) {
           const float4 a = a4[c4];
 #pragma unroll
-          for (int r = 0; r < RPT; ++r) {
-            acc[r][4 * c4 + 0] = fmaf(wv[r][u], a.x, acc[r][4 * c4 + 0]);
-            acc[r][4 * c4 + 1] = fmaf(wv[r][u], a.y, acc[r][4 * c4 + 1]);
-            acc[r][4 * c4 + 2] = fmaf(wv[r][u], a.z, acc[r][4 * c4 + 2]);
-            acc[r][4 * c4 + 3] = fmaf(wv[r][u], a.w, acc[r][4 * c4 + 3]);
+          for (int r = 0; r < RPT; ++r) {  // packed FFMA2 (fma.rn.f32x2): one IEEE fma per lane, half the issue slots
+            const float2 w2 = make_float2(wv[r][u], wv[r][u]);
+            const float2 lo = __ffma2_rn(w2, make_float2(a.x, a.y), make_float2(acc[r][4 * c4 + 0], acc[r][4 * c4 + 1]));
+            const float2 hi = __ffma2_rn(w2, make_float2(a.z, a.w), make_float2(acc[r][4 * c4 + 2], acc[r][4 * c4 + 3]));
+            acc[r][4 * c4 + 0] = lo.x; acc[r][4 * c4 + 1] = lo.y;
+            acc[r][4 * c4 + 2] = hi.x; acc[r][4 * c4 + 3] = hi.y;
           }
         }
       }
