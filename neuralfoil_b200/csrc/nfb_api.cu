@@ -69,8 +69,11 @@ struct Model {
 #endif
 using Cfg64 = nfb::FfmaCfg<64, NFB_KC_NARROW, 4, NFB_TN_NARROW>;
 using Cfg128 = nfb::FfmaCfg<128, NFB_KC, 4, NFB_TN_WIDE>;
-using Cfg256 = nfb::FfmaCfg<256, NFB_KC, 4, NFB_TN_WIDE>;
-using Cfg512 = nfb::FfmaCfg<512, NFB_KC, 4, NFB_TN_WIDE>;
+#ifndef NFB_STAGES
+#define NFB_STAGES 4
+#endif
+using Cfg256 = nfb::FfmaCfg<256, NFB_KC, NFB_STAGES, NFB_TN_WIDE>;
+using Cfg512 = nfb::FfmaCfg<512, NFB_KC, NFB_STAGES, NFB_TN_WIDE>;
 
 struct HostSlot {  // one in-flight chunk of nfb_eval_host
   cudaStream_t stream = nullptr;

@@ -422,6 +422,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_kernel(const EvalPar
           acc[4 + i][jj] = make_float2(b_hi, b_hi);
         }
       }
+      // (Measured and rejected: waiting for two K-slices at a time -- half the barrier waits and warp syncs -- is 17 %
+      //  slower: a slot is then released a slice later, and the ring is latency-critical.)
       for (int c = 0; c < K / KC; ++c) {
         uint32_t s;
         wait_slice(s);
