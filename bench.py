@@ -316,10 +316,40 @@ def main():
                             "note": "same nfb_eval_host path (pinned host in/out); PCIe device->host moves 792 B/query"}
         return extra
 
+    # ---- outputs="scalars" (NFB_OUTPUT_SCALARS), briefly: only the six scalar rows travel back over PCIe ----
+    def measure_scalars(v: str) -> dict:
+        out6_dev = torch.empty((6, ld), dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            ev.evaluate_device(raw_dev, size, out=out6_dev, variant=v, outputs="scalars")
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(args.steps):
+            ev.evaluate_device(raw_dev, size, out=out6_dev, variant=v, outputs="scalars")
+        t1e.record()
+        barrier()
+        t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
+        res = {"value": world * n / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms, "d2h_bytes_per_query": 24}
+        if not args.no_e2e:
+            out6_host = torch.empty((6, ld), dtype=torch.float32).pin_memory()
+            ev.evaluate_host_into(raw_host.numpy(), size, out6_host.numpy(), variant=v, outputs="scalars")
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                ev.evaluate_host_into(raw_host.numpy(), size, out6_host.numpy(), variant=v, outputs="scalars")
+                _ = float(out6_host[1, 0])
+            torch.cuda.synchronize()
+            te = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+            res["e2e"] = {"value": world * n / te, "unit": UNIT, "ms_per_step": te * 1e3}
+        return res
+
     tensor_extra = tensor_fp32_extra = None
     if size in ("xxxlarge", "xxlarge") and variant == "fp32" and not args.no_tensor_extra:
         tensor_fp32_extra = measure_other("tensor_fp32")
         tensor_extra = measure_other("tensor")
+        if not args.no_e2e:
+            tensor_fp32_extra["scalars_only"] = measure_scalars("tensor_fp32")
+            tensor_extra["scalars_only"] = measure_scalars("tensor")
 
     # ---- the Jacobian kernel, briefly: outputs + 198 x 23 derivatives per query, device-resident ----
     jacobian_extra = None

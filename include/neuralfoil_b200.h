@@ -57,6 +57,11 @@ enum nfb_dtype { NFB_F32 = 0, NFB_F64 = 1 };
  *                FP32_FFMA tolerance.  Same model restriction. */
 enum nfb_variant { NFB_VARIANT_FP32_FFMA = 0, NFB_VARIANT_TENSOR_FP16 = 1, NFB_VARIANT_TENSOR_FP16X3 = 2 };
 
+/* May be OR-ed into `variant`: write only the six scalar outputs (analysis_confidence, CL, CD, CM, Top_Xtr, Bot_Xtr --
+ * rows 0..5 of the full block, bit-identical to them).  `out` is then a 6 x out_ld block: 24 instead of 792 bytes per
+ * query travel back over PCIe in nfb_eval_host, which is what bounds every model but the largest there. */
+#define NFB_OUTPUT_SCALARS 0x100
+
 typedef struct nfb_context nfb_context;
 
 /* Library / build identification (static string, never NULL). */

@@ -20,6 +20,8 @@ F32, F64 = 0, 1
 VARIANT_FP32_FFMA = 0
 VARIANT_TENSOR_FP16 = 1
 VARIANT_TENSOR_FP16X3 = 2
+OUTPUT_SCALARS = 0x100  # NFB_OUTPUT_SCALARS: OR-ed into the variant, only the six scalar rows are written
+N_SCALAR_ROWS = 6
 VARIANTS = {"fp32": VARIANT_FP32_FFMA, "tensor": VARIANT_TENSOR_FP16, "tensor_fp32": VARIANT_TENSOR_FP16X3}
 
 OK = 0

@@ -323,6 +323,7 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   if (!ctx->models[model_id].loaded) return fail(NFB_ERR_NOT_LOADED, "model slot %d is empty", model_id);
   if (!ctx->have_distribution)
     return fail(NFB_ERR_NOT_LOADED, "nfb_set_distribution has not been called");
+  variant &= ~NFB_OUTPUT_SCALARS;
   if (variant != NFB_VARIANT_FP32_FFMA && variant != NFB_VARIANT_TENSOR_FP16 && variant != NFB_VARIANT_TENSOR_FP16X3)
     return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
   if (variant != NFB_VARIANT_FP32_FFMA && !ctx->models[model_id].tc_w)
@@ -358,6 +359,8 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
   p.n_layers = m.n_layers;
   p.in_f64 = (in_dtype == NFB_F64);
   p.out_f64 = (out_dtype == NFB_F64);
+  p.scalars_only = (variant & NFB_OUTPUT_SCALARS) ? 1 : 0;
+  variant &= ~NFB_OUTPUT_SCALARS;
   if (variant == NFB_VARIANT_TENSOR_FP16 || variant == NFB_VARIANT_TENSOR_FP16X3) {
     const bool x3 = (variant == NFB_VARIANT_TENSOR_FP16X3);
     nfb::tc::TcParams tp;
@@ -588,7 +591,8 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
   if (chunk <= 0) chunk = 1 << 19;
   chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
-  const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(nfb::N_OUT) * chunk * osz;
+  const int out_rows = (variant & NFB_OUTPUT_SCALARS) ? 6 : nfb::N_OUT;
+  const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(out_rows) * chunk * osz;
 
   // Small batches (a design optimiser's per-iteration call): pack everything into one pinned block so
   // that there is exactly one H2D copy, one launch and one D2H copy.
@@ -647,11 +651,11 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
       char* hs_out = static_cast<char*>(s.h_stage) + in_need;
       NFB_CUDA(cudaMemcpyAsync(hs_out, s.d_out, out_need, cudaMemcpyDeviceToHost, s.stream));
       NFB_CUDA(cudaStreamSynchronize(s.stream));
-      for (int r = 0; r < nfb::N_OUT; ++r)
+      for (int r = 0; r < out_rows; ++r)
         memcpy(out_c + size_t(r) * out_ld * osz, hs_out + size_t(r) * chunk * osz, size_t(cn) * osz);
     } else {
       NFB_CUDA(cudaMemcpy2DAsync(out_c, size_t(out_ld) * osz, s.d_out, size_t(chunk) * osz, size_t(cn) * osz,
-                                 nfb::N_OUT, cudaMemcpyDeviceToHost, s.stream));
+                                 out_rows, cudaMemcpyDeviceToHost, s.stream));
     }
     done += cn;
   }
@@ -683,6 +687,7 @@ int nfb_eval_jacobian_device(nfb_context* ctx, int model_id, int64_t n, const vo
   jp.ev.n_layers = m.n_layers;
   jp.ev.in_f64 = (in_dtype == NFB_F64);
   jp.ev.out_f64 = (out_dtype == NFB_F64);
+  jp.ev.scalars_only = 0;
   jp.jac = jac;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (m.h_pad) {

@@ -29,6 +29,7 @@ struct EvalParams {
   int n_layers;                // affine layers L
   int in_f64;
   int out_f64;
+  int scalars_only;            // NFB_OUTPUT_SCALARS: store rows 0..5 only (out is 6 x out_ld)
 };
 
 // Mean (25) and packed symmetric quadratic form (325, off-diagonals pre-summed S_ij + S_ji) of the

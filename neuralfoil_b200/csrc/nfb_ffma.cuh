@@ -248,6 +248,7 @@ __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, lon
                                                  const float* __restrict__ maha_t,
                                                  const float* __restrict__ re4) {
   float o0[4], o1[4], o2[4], o3[4];
+  if (p.scalars_only && g < 48) return;  // boundary-layer rows not wanted
   if (g < N_BL) {  // theta_u, ue_u, theta_l, ue_l of station g
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

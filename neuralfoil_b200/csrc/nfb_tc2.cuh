@@ -661,14 +661,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
         for (int c = 0; c < f_count; c += 32) {
           const int f0 = f_begin + c;    // packed rows f0 .. f0 + 31
           if (f0 >= M_LAST_USED) break;  // (warp-uniform; the rest is padding)
+          const bool skip = p.scalars_only && f0 < 4 * 48;  // (warp-uniform) boundary-layer chunks not wanted
           uint32_t v[32];
-          load_acc(uint32_t(c_begin + c), v);
+          if (!skip) load_acc(uint32_t(c_begin + c), v);
           if (c + 32 >= f_count || f0 + 32 >= M_LAST_USED) {  // that was my last read of the accumulators
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_drained);  // the next tile's layer 0 may overwrite them
             if (stamp) tp.dbg[21] = clock64();
           }
+          if (skip) continue;
           float z[32], other[16];
 #pragma unroll
           for (int i = 0; i < 32; ++i) z[i] = fmaf(__uint_as_float(v[i]), inv_s, b[f0 + i]);

@@ -192,6 +192,15 @@ class Evaluator:
         except KeyError:
             raise ValueError(f"Invalid {variant=}. Must be one of {set(_lib.VARIANTS)}.") from None
 
+    @staticmethod
+    def _rows_and_flag(outputs: str) -> tuple[int, int]:
+        """`outputs="all"`: the 198 rows; `"scalars"`: analysis_confidence, CL, CD, CM, Top_Xtr, Bot_Xtr only (rows 0..5)."""
+        if outputs == "all":
+            return _lib.N_OUTPUT_ROWS, 0
+        if outputs == "scalars":
+            return _lib.N_SCALAR_ROWS, _lib.OUTPUT_SCALARS
+        raise ValueError(f"Invalid {outputs=}. Must be 'all' or 'scalars'.")
+
     def _model_id(self, model_size: str) -> int:
         if model_size not in self._model_ids:
             raise ValueError(f"Invalid {model_size=}. Must be one of {self.allowable_model_sizes}.")
@@ -200,25 +209,25 @@ class Evaluator:
     # -- the drop-in call --------------------------------------------------------------------------
     def get_aero_from_kulfan_parameters(
         self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge",
-        variant: str = "fp32",
+        variant: str = "fp32", outputs: str = "all",
     ) -> dict[str, np.ndarray]:
         model_id = self._model_id(model_size)  # main.py:154-157
         rows, n_cases = prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower)
-        block = self._evaluate_host_rows(model_id, rows, n_cases, np.float64, variant=variant)
+        block = self._evaluate_host_rows(model_id, rows, n_cases, np.float64, variant=variant, outputs=outputs)
         # Row views of one (198, ld) block: each value is a contiguous (N,) float64 array, as in the
         # reference, where the keys are views of a shared Fortran-ordered block.
         return dict(zip(_OUTPUT_KEYS, block[:, :n_cases]))  # iterating a 2-D array yields its row views
 
     def evaluate_host(self, raw: np.ndarray, model_size: str = "xlarge", out_dtype=np.float32, chunk: int = 0,
-                      variant: str = "fp32"):
-        """raw (23, N) float32/float64 host array -> (198, N) host array (rows are contiguous)."""
+                      variant: str = "fp32", outputs: str = "all"):
+        """raw (23, N) float32/float64 host array -> (198, N) host array (rows are contiguous); (6, N) with outputs="scalars"."""
         raw = np.asarray(raw)
         if raw.ndim != 2 or raw.shape[0] != _lib.N_RAW_ROWS:
             raise ValueError(f"raw must have shape (23, N), got {raw.shape}")
         if raw.dtype not in (np.float32, np.float64):
             raw = raw.astype(np.float64)
         rows = [np.ascontiguousarray(raw[i]) for i in range(_lib.N_RAW_ROWS)]
-        block = self._evaluate_host_rows(self._model_id(model_size), rows, raw.shape[1], out_dtype, chunk, variant)
+        block = self._evaluate_host_rows(self._model_id(model_size), rows, raw.shape[1], out_dtype, chunk, variant, outputs)
         return block[:, : raw.shape[1]]
 
     # -- derivatives (SURVEY 8(f-2)) -----------------------------------------------------------------
@@ -290,7 +299,7 @@ class Evaluator:
         return dict(zip(_OUTPUT_KEYS, values)), {k: jac[:, i, :] for i, k in enumerate(_OUTPUT_KEYS)}
 
     def evaluate_host_into(self, raw: np.ndarray, model_size: str, out: np.ndarray, chunk: int = 0,
-                           variant: str = "fp32") -> np.ndarray:
+                           variant: str = "fp32", outputs: str = "all") -> np.ndarray:
         """
         Like `evaluate_host`, but writes into a caller-owned (ideally pinned) block `out` of shape
         (198, ld >= N) with contiguous rows, and reads `raw` (23, N) in place: no host allocation
@@ -301,14 +310,15 @@ class Evaluator:
         if raw.strides[1] != raw.itemsize:
             raise ValueError("raw rows must be contiguous")
         n = raw.shape[1]
-        if (out.ndim != 2 or out.shape[0] != _lib.N_OUTPUT_ROWS or out.shape[1] < n
+        n_rows, flag = self._rows_and_flag(outputs)
+        if (out.ndim != 2 or out.shape[0] != n_rows or out.shape[1] < n
                 or out.strides[1] != out.itemsize or out.dtype not in (np.float32, np.float64)):
-            raise ValueError("out must be a (198, >=N) float32/float64 array with contiguous rows")
+            raise ValueError(f"out must be a ({n_rows}, >=N) float32/float64 array with contiguous rows")
         ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].ctypes.data for i in range(_lib.N_RAW_ROWS)])
         strides = (C.c_int64 * _lib.N_RAW_ROWS)(*([1] * _lib.N_RAW_ROWS))
         _lib.check(
             self._lib.nfb_eval_host(
-                self._ctx, self._model_id(model_size), self._variant(variant), n, ptrs, strides,
+                self._ctx, self._model_id(model_size), self._variant(variant) | flag, n, ptrs, strides,
                 _lib.F64 if raw.dtype == np.float64 else _lib.F32,
                 out.ctypes.data_as(C.c_void_p), out.strides[0] // out.itemsize,
                 _lib.F64 if out.dtype == np.float64 else _lib.F32, chunk,
@@ -316,9 +326,11 @@ class Evaluator:
         )
         return out[:, :n]
 
-    def _evaluate_host_rows(self, model_id: int, rows, n: int, out_dtype, chunk: int = 0, variant: str = "fp32"):
+    def _evaluate_host_rows(self, model_id: int, rows, n: int, out_dtype, chunk: int = 0, variant: str = "fp32",
+                            outputs: str = "all"):
         ld = (n + 3) & ~3
-        block = np.empty((_lib.N_OUTPUT_ROWS, ld), dtype=out_dtype)
+        n_rows, flag = self._rows_and_flag(outputs)
+        block = np.empty((n_rows, ld), dtype=out_dtype)
         if n <= 4096:
             # Small batches (an optimiser's per-iteration call): gather the rows into one (23, n) float64 block so
             # that the pointer table is plain integer arithmetic -- numpy's `.ctypes` accessors cost ~1 us apiece.
@@ -339,7 +351,7 @@ class Evaluator:
             in_code = _lib.F64 if in_dtype == np.float64 else _lib.F32
         _lib.check(
             self._lib.nfb_eval_host(
-                self._ctx, model_id, self._variant(variant), n, ptrs, strides, in_code,
+                self._ctx, model_id, self._variant(variant) | flag, n, ptrs, strides, in_code,
                 block.__array_interface__["data"][0], ld,
                 _lib.F64 if block.dtype == np.float64 else _lib.F32, chunk,
             )
@@ -348,7 +360,8 @@ class Evaluator:
         return block
 
     # -- device-resident call ----------------------------------------------------------------------
-    def evaluate_device(self, raw, model_size: str = "xlarge", out=None, out_dtype=None, variant: str = "fp32"):
+    def evaluate_device(self, raw, model_size: str = "xlarge", out=None, out_dtype=None, variant: str = "fp32",
+                        outputs: str = "all"):
         """
         raw: torch CUDA tensor (23, N), float32 or float64, rows contiguous -- or a list of 23 1-D CUDA
         tensors of length N or 1 (length-1 rows are broadcast).  Returns a (198, N) CUDA tensor view
@@ -382,18 +395,19 @@ class Evaluator:
         if out_dtype is None:
             out_dtype = out.dtype if out is not None else torch.float32
         ld = (n + 3) & ~3
+        n_rows, flag = self._rows_and_flag(outputs)
         if out is None:
-            out = torch.empty((_lib.N_OUTPUT_ROWS, ld), dtype=out_dtype, device=f"cuda:{self.device}")
+            out = torch.empty((n_rows, ld), dtype=out_dtype, device=f"cuda:{self.device}")
         else:
-            if out.dim() != 2 or out.shape[0] != _lib.N_OUTPUT_ROWS or out.shape[1] < n or out.stride(1) != 1:
-                raise ValueError("out must be a (198, >=N) tensor with contiguous rows")
+            if out.dim() != 2 or out.shape[0] != n_rows or out.shape[1] < n or out.stride(1) != 1:
+                raise ValueError(f"out must be a ({n_rows}, >=N) tensor with contiguous rows")
             ld = int(out.stride(0))
         ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[r.data_ptr() for r in rows])
         c_strides = (C.c_int64 * _lib.N_RAW_ROWS)(*strides)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(
             self._lib.nfb_eval_device(
-                self._ctx, model_id, self._variant(variant), n, ptrs, c_strides,
+                self._ctx, model_id, self._variant(variant) | flag, n, ptrs, c_strides,
                 _lib.F64 if dtype == torch.float64 else _lib.F32,
                 C.c_void_p(out.data_ptr()), ld, _lib.F64 if out.dtype == torch.float64 else _lib.F32,
                 C.c_void_p(stream),

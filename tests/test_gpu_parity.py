@@ -564,3 +564,36 @@ def test_jacobian_dict_api_and_symmetry(evaluator):
     assert abs((a1 - a0) - jac["CL"][0, i_alpha]) < 2e-3
     with pytest.raises(ValueError):
         evaluator.evaluate_jacobian_host(np.zeros((22, 4)), "large")
+
+
+# ---------------------------------------------------------------------------------------------
+# outputs="scalars" (NFB_OUTPUT_SCALARS): the six scalar rows only, bit-identical to rows 0..5 of the full block
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 5, 700, 4099, 70001])
+def test_scalars_only_equals_first_six_rows(evaluator, n):
+    import torch
+
+    raw = synthetic.sample_training_distribution(n, seed=600 + n)
+    cases = [(size, "fp32") for size in ("xxsmall", "medium", "xlarge")] + [(s, v) for s in ("xxlarge", "xxxlarge") for v in ("fp32", "tensor", "tensor_fp32")]
+    for size, variant in cases:
+        full = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant=variant)
+        six = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant=variant, outputs="scalars")
+        assert six.shape == (6, n)
+        np.testing.assert_array_equal(six, full[:6], err_msg=f"{size} {variant}")
+    d = torch.from_numpy(raw.astype(np.float32)).cuda()
+    out6 = evaluator.evaluate_device(d, "xxxlarge", variant="tensor_fp32", outputs="scalars")
+    out198 = evaluator.evaluate_device(d, "xxxlarge", variant="tensor_fp32")
+    torch.cuda.synchronize()
+    assert out6.shape == (6, n) and torch.equal(out6, out198[:6])
+
+
+def test_scalars_only_dict_api_and_errors(evaluator):
+    aero = evaluator.get_aero_from_kulfan_parameters(synthetic.FIXED_KULFAN, alpha=np.linspace(-5, 10, 31), Re=1e6, model_size="large", outputs="scalars")
+    ref = evaluator.get_aero_from_kulfan_parameters(synthetic.FIXED_KULFAN, alpha=np.linspace(-5, 10, 31), Re=1e6, model_size="large")
+    assert list(aero) == ["analysis_confidence", "CL", "CD", "CM", "Top_Xtr", "Bot_Xtr"]
+    for k in aero:
+        np.testing.assert_array_equal(aero[k], ref[k])
+    with pytest.raises(ValueError):
+        evaluator.evaluate_host(np.zeros((23, 4)), "large", outputs="some")
+    with pytest.raises(ValueError):
+        evaluator.evaluate_host_into(np.zeros((23, 4)), "large", np.zeros((198, 4)), outputs="scalars")
