@@ -313,6 +313,8 @@ __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, lon
 // cap the compute warps' registers): when a warp starts slice `it`, its lane 0 -- for the one warp
 // with (it + STAGES - 2) % WARPS == warp -- issues the TMA bulk copy of slice it + STAGES - 2, whose
 // slot was last read by slice it - 2, which every warp has normally long finished.
+// (Checked again for the 8-warp configuration: a ninth, producer warp makes the register allocator budget for 12 warps
+//  -- 168 registers per thread instead of 255 -- and the 8 x 16 thread tile spills.)
 template <class Cfg>
 __device__ __forceinline__ void issue_slice(uint32_t j, uint32_t slices_per_tile, const uint2* __restrict__ table,
                                             const float* __restrict__ blob, float* ring, uint32_t bar_full,
