@@ -597,3 +597,29 @@ def test_scalars_only_dict_api_and_errors(evaluator):
         evaluator.evaluate_host(np.zeros((23, 4)), "large", outputs="some")
     with pytest.raises(ValueError):
         evaluator.evaluate_host_into(np.zeros((23, 4)), "large", np.zeros((198, 4)), outputs="scalars")
+
+
+@pytest.mark.parametrize("variant", ["tensor", "tensor_fp32"])
+def test_nan_inputs_propagate_on_tensor_variants(evaluator, variant):
+    """NaN input / Re <= 0 -> NaN outputs for that query only, also through the fp16-operand kernels,
+    whose conversions saturate instead of overflowing: the neighbours in the same tile must be untouched."""
+    n = 300
+    raw = synthetic.sample_training_distribution(n, seed=77)
+    clean = evaluator.evaluate_host(raw, "xxxlarge", out_dtype=np.float64, variant=variant)
+    bad = raw.copy()
+    bad[18, 5] = np.nan      # alpha
+    bad[19, 70] = -1.0       # Re <= 0 -> log -> NaN
+    bad[3, 131] = np.nan     # a Kulfan weight
+    got = evaluator.evaluate_host(bad, "xxxlarge", out_dtype=np.float64, variant=variant)
+    for q in (5, 70, 131):
+        assert np.isnan(got[:4, q]).all() and np.isnan(got[6:, q]).all(), (variant, q)
+    keep = np.ones(n, dtype=bool)
+    keep[[5, 70, 131]] = False
+    np.testing.assert_array_equal(got[:, keep], clean[:, keep])
+
+
+def test_jacobian_nan_inputs_propagate(evaluator):
+    raw = synthetic.sample_training_distribution(6, seed=78)
+    raw[18, 2] = np.nan
+    values, jac = evaluator.evaluate_jacobian_host(raw, "large")
+    assert np.isnan(values[1, 2]) and np.isnan(jac[2, 1]).any() and np.isfinite(jac[[0, 1, 3, 4, 5]]).all()
