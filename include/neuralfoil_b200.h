@@ -127,6 +127,16 @@ int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void
                            const int64_t* in_strides, int in_dtype, void* values, int64_t values_ld,
                            void* jac, int out_dtype);
 
+/* Vector-Jacobian product (reverse-mode result, computed by the same forward-mode kernel without ever writing the
+ * Jacobian): grad[t][q] = sum_row cot[row][q] * d output_row / d raw_input_t -- the gradient with respect to the 23 raw
+ * inputs of any scalar objective whose derivative with respect to the 198 outputs is `cot`.  92 instead of 18,216 bytes
+ * per query leave the kernel.
+ *   cot, cot_ld     198 x cot_ld cotangents (type out_dtype);  values, values_ld as above (may be NULL);
+ *   grad, grad_ld   23 x grad_ld gradients (type out_dtype), rows in the order of in_rows. */
+int nfb_eval_vjp_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                        const int64_t* in_strides, int in_dtype, const void* cot, int64_t cot_ld,
+                        void* values, int64_t values_ld, void* grad, int64_t grad_ld, int out_dtype, void* stream);
+
 /* Pinned host memory helpers for callers without their own allocator. */
 int nfb_host_alloc(void** out_ptr, int64_t bytes);
 int nfb_host_free(void* ptr);

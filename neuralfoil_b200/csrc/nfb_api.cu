@@ -664,14 +664,16 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   return NFB_OK;
 }
 
-int nfb_eval_jacobian_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
-                             const int64_t* in_strides, int in_dtype, void* values, int64_t values_ld, void* jac,
-                             int out_dtype, void* stream) {
+namespace {
+int jacobian_device_impl(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows, const int64_t* in_strides,
+                         int in_dtype, void* values, int64_t values_ld, void* jac, const void* cot, int64_t cot_ld,
+                         void* grad, int64_t grad_ld, int out_dtype, void* stream) {
   static char dummy_out;  // check_eval_args wants a non-NULL out; `values` is optional here
   int rc = check_eval_args(ctx, model_id, NFB_VARIANT_FP32_FFMA, n, in_rows, in_strides, in_dtype, values ? values : &dummy_out,
                            values ? values_ld : n, out_dtype);
   if (rc != NFB_OK || n == 0) return rc;
-  if (!jac) return fail(NFB_ERR_INVALID_ARGUMENT, "jac is NULL");
+  if (!jac && !cot) return fail(NFB_ERR_INVALID_ARGUMENT, "jac is NULL");
+  if (cot && (!grad || cot_ld < n || grad_ld < n)) return fail(NFB_ERR_INVALID_ARGUMENT, "VJP: grad is NULL or a leading dimension is smaller than n");
   if (n > (int64_t(1) << 30)) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld: the Jacobian kernel takes at most 2^30 queries per call", (long long)n);
   NFB_CUDA(cudaSetDevice(ctx->device));
   const Model& m = ctx->models[model_id];
@@ -689,6 +691,10 @@ int nfb_eval_jacobian_device(nfb_context* ctx, int model_id, int64_t n, const vo
   jp.ev.out_f64 = (out_dtype == NFB_F64);
   jp.ev.scalars_only = 0;
   jp.jac = jac;
+  jp.cot = cot;
+  jp.grad = grad;
+  jp.cot_ld = cot_ld;
+  jp.grad_ld = grad_ld;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (m.h_pad) {
     case 64: return launch_jac<64>(ctx, jp, st);
@@ -696,6 +702,23 @@ int nfb_eval_jacobian_device(nfb_context* ctx, int model_id, int64_t n, const vo
     case 256: return launch_jac<256>(ctx, jp, st);
     default: return launch_jac<512>(ctx, jp, st);
   }
+}
+}  // namespace
+
+int nfb_eval_jacobian_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                             const int64_t* in_strides, int in_dtype, void* values, int64_t values_ld, void* jac,
+                             int out_dtype, void* stream) {
+  if (!jac) return fail(NFB_ERR_INVALID_ARGUMENT, "jac is NULL");
+  return jacobian_device_impl(ctx, model_id, n, in_rows, in_strides, in_dtype, values, values_ld, jac, nullptr, 0, nullptr, 0,
+                              out_dtype, stream);
+}
+
+int nfb_eval_vjp_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows, const int64_t* in_strides,
+                        int in_dtype, const void* cot, int64_t cot_ld, void* values, int64_t values_ld, void* grad,
+                        int64_t grad_ld, int out_dtype, void* stream) {
+  if (!cot) return fail(NFB_ERR_INVALID_ARGUMENT, "cot is NULL");
+  return jacobian_device_impl(ctx, model_id, n, in_rows, in_strides, in_dtype, values, values_ld, nullptr, cot, cot_ld, grad,
+                              grad_ld, out_dtype, stream);
 }
 
 int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,

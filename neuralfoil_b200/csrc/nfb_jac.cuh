@@ -26,7 +26,11 @@ constexpr int JAC_COLS = 2 * JAC_HALF;     // 48
 
 struct JacParams {
   EvalParams ev;    // inputs, n, blob, n_layers; ev.out / ev.out_ld = values (may be NULL)
-  void* jac;        // n x 198 x 23, ev.out_f64 decides the type
+  void* jac;        // n x 198 x 23, ev.out_f64 decides the type (NULL in VJP mode)
+  // VJP mode (cot != NULL): instead of the Jacobian itself, grad[t][q] = sum_row cot[row][q] * d out_row / d raw_t
+  const void* cot;  // 198 x cot_ld cotangents, same type as the outputs
+  void* grad;       // 23 x grad_ld
+  long long cot_ld, grad_ld;
 };
 
 template <int H>
@@ -211,6 +215,11 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, 1) nfb_jac_kernel(const Ja
 
   // ---- decode: thread (group g, column c): c = 0 the values, c = 1 + t the derivative with respect to input t ----
   // y[i] / f[i]: packed rows 4 g + i of the query / the twin (value or tangent c); Y / F: always the values
+  float* const part = act;  // [50][23] partial vector-Jacobian products (the activation tile is no longer needed)
+  auto cotangent = [&](int row) -> float {
+    return p.out_f64 ? float(__ldg(static_cast<const double*>(jp.cot) + row * jp.cot_ld + q))
+                     : __ldg(static_cast<const float*>(jp.cot) + row * jp.cot_ld + q);
+  };
   for (int item = tid; item < (M_LAST_USED / 4) * JAC_HALF; item += Cfg::THREADS) {
     const int g = item / JAC_HALF, c = item % JAC_HALF;
     float y[4], f[4], Y[4], F[4];
@@ -279,6 +288,14 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, 1) nfb_jac_kernel(const Ja
       rows[0] = 4; rows[1] = 5; rows[2] = rows[3] = 0;
       n_out = 2;
     }
+    if (!val && jp.cot) {  // VJP mode: my four rows' share of grad[c - 1]
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < n_out) s = fmaf(cotangent(rows[k]), o[k], s);
+      part[g * JAC_T + (c - 1)] = s;
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k >= n_out) continue;
@@ -292,6 +309,15 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, 1) nfb_jac_kernel(const Ja
         if (p.out_f64) static_cast<double*>(jp.jac)[at] = double(o[k]);
         else static_cast<float*>(jp.jac)[at] = o[k];
       }
+    }
+  }
+  if (jp.cot) {  // fixed-order reduction over the 50 row groups: deterministic
+    __syncthreads();
+    if (tid < JAC_T) {
+      float s = 0.0f;
+      for (int g = 0; g < M_LAST_USED / 4; ++g) s += part[g * JAC_T + tid];
+      if (p.out_f64) static_cast<double*>(jp.grad)[tid * jp.grad_ld + q] = double(s);
+      else static_cast<float*>(jp.grad)[tid * jp.grad_ld + q] = s;
     }
   }
 }

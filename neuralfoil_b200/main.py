@@ -281,6 +281,50 @@ class Evaluator:
         )
         return values[:, :n], jac
 
+    def evaluate_vjp_device(self, raw, cotangent, model_size: str = "xlarge"):
+        """
+        Vector-Jacobian product: raw (23, N) and cotangent (198, N) CUDA tensors (same float dtype for the outputs;
+        contiguous rows) -> (values (198, N), grad (23, N)), grad[t] = sum_row cotangent[row] * d output_row / d raw_t:
+        the gradient with respect to the raw inputs of any scalar objective of the outputs, without materialising the
+        198 x 23 Jacobian (18 KB per query).  Enqueues on torch's current stream.
+        """
+        import torch
+
+        for name, t, rows in (("raw", raw, _lib.N_RAW_ROWS), ("cotangent", cotangent, _lib.N_OUTPUT_ROWS)):
+            if not isinstance(t, torch.Tensor) or t.dim() != 2 or t.shape[0] != rows or not t.is_cuda or t.stride(1) != 1:
+                raise ValueError(f"{name} must be a ({rows}, N) CUDA tensor with contiguous rows")
+            if t.dtype not in (torch.float32, torch.float64):
+                raise ValueError(f"{name} must be float32 or float64")
+        n = int(raw.shape[1])
+        if cotangent.shape[1] != n:
+            raise ValueError("raw and cotangent must have the same number of columns")
+        ld = (n + 3) & ~3
+        dev = f"cuda:{self.device}"
+        values = torch.empty((_lib.N_OUTPUT_ROWS, ld), dtype=cotangent.dtype, device=dev)
+        grad = torch.empty((_lib.N_RAW_ROWS, ld), dtype=cotangent.dtype, device=dev)
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].data_ptr() for i in range(_lib.N_RAW_ROWS)])
+        _lib.check(
+            self._lib.nfb_eval_vjp_device(
+                self._ctx, self._model_id(model_size), n, ptrs, _ONES_23,
+                _lib.F64 if raw.dtype == torch.float64 else _lib.F32,
+                C.c_void_p(cotangent.data_ptr()), int(cotangent.stride(0)),
+                C.c_void_p(values.data_ptr()), ld, C.c_void_p(grad.data_ptr()), ld,
+                _lib.F64 if cotangent.dtype == torch.float64 else _lib.F32,
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream),
+            )
+        )
+        return values[:, :n], grad[:, :n]
+
+    def evaluate_vjp_host(self, raw: np.ndarray, cotangent: np.ndarray, model_size: str = "xlarge"):
+        """NumPy front door of `evaluate_vjp_device` (moves the arrays with torch): -> (values (198, N), grad (23, N)) float64."""
+        import torch
+
+        dev = f"cuda:{self.device}"
+        r = torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float64)).to(dev)
+        c = torch.from_numpy(np.ascontiguousarray(cotangent, dtype=np.float64)).to(dev)
+        values, grad = self.evaluate_vjp_device(r, c, model_size)
+        return values.cpu().numpy(), grad.cpu().numpy()
+
     def get_aero_and_jacobian_from_kulfan_parameters(
         self, kulfan_parameters, alpha, Re, n_crit=9.0, xtr_upper=1.0, xtr_lower=1.0, model_size="xlarge"
     ):

@@ -623,3 +623,27 @@ def test_jacobian_nan_inputs_propagate(evaluator):
     raw[18, 2] = np.nan
     values, jac = evaluator.evaluate_jacobian_host(raw, "large")
     assert np.isnan(values[1, 2]) and np.isnan(jac[2, 1]).any() and np.isfinite(jac[[0, 1, 3, 4, 5]]).all()
+
+
+@pytest.mark.parametrize("size", ["xxsmall", "xlarge", "xxxlarge"])
+def test_vjp_matches_oracle_and_jacobian(evaluator, oracle, size):
+    """grad = J^T cotangent from the VJP mode: against the oracle's analytic Jacobian, and against the library's own Jacobian."""
+    n = 257
+    raw = synthetic.sample_training_distribution(n, seed=55)
+    rng = np.random.default_rng(5)
+    cot = np.zeros((198, n))
+    cot[1], cot[2], cot[3] = rng.normal(size=n), 50 * rng.normal(size=n), rng.normal(size=n)   # an objective of CL, CD, CM
+    cot[6 + 64 : 6 + 96] = 0.01 * rng.normal(size=(32, n))                                    # and of the upper edge velocities
+    values, grad = evaluator.evaluate_vjp_host(raw, cot, size)
+    assert values.shape == (198, n) and grad.shape == (23, n)
+    np.testing.assert_array_equal(values, evaluator.evaluate_host(raw, size, out_dtype=np.float64))
+    got_v, got_j = evaluator.evaluate_jacobian_host(raw, size)
+    mine = np.einsum("qrt,rq->tq", got_j, cot)
+    scale = parity.JAC_INPUT_SCALE.copy()[:, None] * np.ones((1, n))
+    scale[19] = raw[19]
+    np.testing.assert_allclose(grad * scale, mine * scale, rtol=2e-4, atol=2e-5)   # same derivatives, summed in fp32 vs fp64
+    want_v, want_j = oracle.jacobian_raw(raw, size)
+    want = np.einsum("rtq,rq->tq", want_j, cot)
+    err = np.abs(grad - want) * scale
+    ref = np.abs(want) * scale + np.einsum("rq,rq->q", np.abs(cot), np.abs(want_v))[None, :] * 1e-1
+    assert (err <= 5e-3 * ref + 1e-6).mean() > 0.999 and np.median(err / np.maximum(ref, 1e-30)) < 1e-5
