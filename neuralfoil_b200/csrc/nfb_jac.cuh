@@ -72,8 +72,9 @@ __device__ __forceinline__ float silu_slope(float z) {  // d/dz [z sigmoid(z)]
   return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
+// (two CTAs per SM for the narrow models, whose single CTA of 8 warps is latency bound: ncu shows 22 % issue activity)
 template <int H>
-__global__ void __launch_bounds__(JacCfg<H>::THREADS, 1) nfb_jac_kernel(const JacParams jp) {
+__global__ void __launch_bounds__(JacCfg<H>::THREADS, (H <= 256) ? 2 : 1) nfb_jac_kernel(const JacParams jp) {
   using Cfg = JacCfg<H>;
   const EvalParams& p = jp.ev;
   extern __shared__ __align__(16) unsigned char smem_raw[];
