@@ -376,6 +376,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1) nfb_tc2
       const uint32_t d = tmem + nb * Cfg::TILE_COLS, d_small = d + Cfg::D_LO_OFFSET;
       umma_f16_pair(d, a_hi | a_lo, b_hi | b_lo, idesc, !first);                            // a_hi . w_hi -> D_hi
       umma_f16_pair(d, a_hi | (a_lo + 2), b_hi | (b_lo + 16), idesc, 1u);
+      // (Measured and not taken: a_hi . w_hi and a_hi . w_lo back to back with the A slice kept in the collector
+      //  (.collector::a::fill / ::lastuse, SASS A_KEEP / A_REUSE) -- correct, but no faster: A is not what binds.)
       if constexpr (SPLIT == 3) {
         umma_f16_pair(d_small, a_hi | (a_lo + LO), b_hi | b_lo, idesc, !first);             // a_lo . w_hi -> D_lo
         umma_f16_pair(d_small, a_hi | (a_lo + LO + 2), b_hi | (b_lo + 16), idesc, 1u);
