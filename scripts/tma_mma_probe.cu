@@ -26,7 +26,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 
 constexpr int MAX_RING = 16;
 constexpr uint32_t RING_BYTES = 128 * 1024;
-constexpr uint32_t A_BYTES = 128 * 128;   // 128 rows x 64 fp16, SW128
+#ifndef ROWS
+#define ROWS 128   // A rows per CTA: 128 (pair M = 256, 128 cycles per MMA) or 64 (pair M = 128, 64 cycles)
+#endif
+constexpr uint32_t A_BYTES = ROWS * 128;   // ROWS x 64 fp16, SW128
 constexpr uint32_t B_BYTES = 16384;       // my 128 B rows x 64 k as two no-swizzle 32-k slices
 
 // mode bit 0: TMA stream, bit 1: MMA stream.  copies / mmas: how many of each per CTA (leader issues the MMAs).
@@ -81,7 +84,7 @@ probe(const unsigned char* src, uint32_t src_bytes, int mode, int copies, int mm
     if (lane == 0) stats[4 * blockIdx.x + 0] = c1 - c0;
   }
   if (warp == 1 && rank == 0 && (mode & 2)) {  // MMA stream
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)((2 * ROWS) >> 4) << 24);
     const uint64_t a_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     const uint64_t b_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint32_t a0 = (smem_u32(sA) >> 4) & 0x3FFF, b0 = (smem_u32(sB) >> 4) & 0x3FFF;
@@ -128,7 +131,7 @@ int main() {
     cudaMemcpy(h.data(), stats, 148 * 4 * 8, cudaMemcpyDeviceToHost);
     double tma = 0, mma = 0; int nt = 0, nm = 0;
     for (int b = 0; b < c.grid; ++b) { if (h[4 * b]) { tma += h[4 * b]; ++nt; } if (h[4 * b + 1]) { mma += h[4 * b + 1]; ++nm; } }
-    printf("grid %3d  %s%s  %2d x %5u B in flight:", c.grid, c.mode & 1 ? "TMA" : "   ", c.mode & 2 ? "+MMA" : "    ", c.ring, c.slot);
+    printf("M %d  grid %3d  %s%s  %2d x %5u B in flight:", 2 * ROWS, c.grid, c.mode & 1 ? "TMA" : "   ", c.mode & 2 ? "+MMA" : "    ", c.ring, c.slot);
     if (nt) printf("  %.0f cycles per copy = %.1f B/clk/SM (chip %.0f B/clk)", tma / nt / copies, double(c.slot) * copies / (tma / nt), double(c.grid) * c.slot * copies / (tma / nt));
     if (nm) printf("  MMA %.1f cycles each", mma / nm / mmas);
     printf("  [%s]\n", cudaGetErrorString(e));
