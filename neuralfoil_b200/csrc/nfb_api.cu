@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "nfb_ffma.cuh"
+#include "nfb_ffma_groups.cuh"
 #include "nfb_small.cuh"
 #include "nfb_tc.cuh"
 #include "nfb_tc2.cuh"
@@ -67,13 +68,50 @@ struct Model {
 #ifndef NFB_KC_NARROW
 #define NFB_KC_NARROW 16  // 64-wide models: a K-slice is only 256 FFMA2 cycles per warp; 16-row slices hide the TMA latency (+5 %)
 #endif
-using Cfg64 = nfb::FfmaCfg<64, NFB_KC_NARROW, 4, NFB_TN_NARROW>;
-using Cfg128 = nfb::FfmaCfg<128, NFB_KC, 4, NFB_TN_WIDE>;
+#ifndef NFB_STAGES_NARROW
+#define NFB_STAGES_NARROW 4
+#endif
 #ifndef NFB_STAGES
 #define NFB_STAGES 4
 #endif
-using Cfg256 = nfb::FfmaCfg<256, NFB_KC, NFB_STAGES, NFB_TN_WIDE>;
+#ifndef NFB_KC_128
+#define NFB_KC_128 NFB_KC
+#endif
+#ifndef NFB_STAGES_128
+#define NFB_STAGES_128 NFB_STAGES_NARROW
+#endif
+#ifndef NFB_KC_256
+#define NFB_KC_256 NFB_KC
+#endif
+#ifndef NFB_STAGES_256
+#define NFB_STAGES_256 NFB_STAGES
+#endif
+using Cfg64 = nfb::FfmaCfg<64, NFB_KC_NARROW, NFB_STAGES_NARROW, NFB_TN_NARROW>;
+using Cfg128 = nfb::FfmaCfg<128, NFB_KC_128, NFB_STAGES_128, NFB_TN_WIDE>;
+using Cfg256 = nfb::FfmaCfg<256, NFB_KC_256, NFB_STAGES_256, NFB_TN_WIDE>;
 using Cfg512 = nfb::FfmaCfg<512, NFB_KC, NFB_STAGES, NFB_TN_WIDE>;
+// Column-group kernels (nfb_ffma_groups.cuh) for the widths up to 256: <H, KC, ring depth, TN>
+#ifndef NFB_GRP_KC_64
+#define NFB_GRP_KC_64 8
+#endif
+#ifndef NFB_GRP_STAGES_64
+#define NFB_GRP_STAGES_64 16
+#endif
+#ifndef NFB_GRP_KC_128
+#define NFB_GRP_KC_128 8
+#endif
+#ifndef NFB_GRP_STAGES_128
+#define NFB_GRP_STAGES_128 16
+#endif
+#ifndef NFB_GRP_KC_256
+#define NFB_GRP_KC_256 8
+#endif
+#ifndef NFB_GRP_STAGES_256
+#define NFB_GRP_STAGES_256 8
+#endif
+using Grp64 = nfb::GroupCfg<64, NFB_GRP_KC_64, NFB_GRP_STAGES_64, NFB_TN_NARROW>;
+using Grp128 = nfb::GroupCfg<128, NFB_GRP_KC_128, NFB_GRP_STAGES_128, NFB_TN_WIDE>;
+using Grp256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, NFB_TN_WIDE>;
 
 struct HostSlot {  // one in-flight chunk of nfb_eval_host
   cudaStream_t stream = nullptr;
@@ -106,7 +144,19 @@ namespace {
 // zero-padded layout; the last layer's rows are permuted by nfb::pack_last_layer_row.
 template <int H>
 std::vector<float> pack_model(int L, const int* dims, const float* const* W, const float* const* B) {
-  std::vector<float> blob(nfb::blob_total_floats<H>(L), 0.0f);
+  std::vector<float> blob(H <= 256 ? nfb::blob_total_floats_swept<H>(L) : nfb::blob_total_floats<H>(L), 0.0f);
+  if (H <= 256) {  // sweep-layout copy of the last layer for nfb_ffma_groups_kernel: Wt[sweep][k][r], bias[256]
+    const int in = dims[L - 1], out = dims[L];
+    float* wt = blob.data() + nfb::blob_sweeps_offset<H>(L);
+    float* bias = wt + size_t(nfb::M_LAST_SWEPT) * H;
+    for (int pr = 0; pr < nfb::M_LAST_SWEPT; ++pr) {
+      const int src_row = nfb::pack_last_layer_row(pr);
+      if (src_row < 0 || src_row >= out) continue;
+      const int sweep = pr / H, r = pr % H;
+      for (int k = 0; k < in; ++k) wt[(size_t(sweep) * H + k) * H + r] = W[L - 1][size_t(src_row) * in + k];
+      bias[pr] = B[L - 1][src_row];
+    }
+  }
   for (int l = 0; l < L; ++l) {
     const int in = dims[l], out = dims[l + 1];
     const bool last = (l == L - 1);
@@ -251,6 +301,22 @@ int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream)
   return NFB_OK;
 }
 
+template <class Cfg>
+int launch_ffma_groups(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_ffma_groups_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(Cfg::SMEM_BYTES)));
+    configured_device = ctx->device;
+  }
+  const long long tiles = (p.n + Cfg::NQ - 1) / Cfg::NQ;
+  const int grid = int(std::min<long long>(tiles, ctx->sm_count));
+  nfb::nfb_ffma_groups_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
 // Batches up to this size go to the small-batch kernel (4 queries per CTA); measured crossover, DESIGN.md section 6.
 int64_t small_batch_limit(int h_pad) {
   static const char* env = getenv("NFB_SMALL_MAX");  // tuning experiments only
@@ -385,6 +451,14 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
       case 128: return launch_small<128>(ctx, p, stream);
       case 256: return launch_small<256>(ctx, p, stream);
       case 512: return launch_small<512>(ctx, p, stream);
+    }
+  }
+  static const bool tiled_only = getenv("NFB_FFMA_TILED") != nullptr;  // A/B: the CTA-synchronous kernel for every width
+  if (!tiled_only) {
+    switch (m.h_pad) {
+      case 64: return launch_ffma_groups<Grp64>(ctx, p, stream);
+      case 128: return launch_ffma_groups<Grp128>(ctx, p, stream);
+      case 256: return launch_ffma_groups<Grp256>(ctx, p, stream);
     }
   }
   switch (m.h_pad) {

@@ -16,6 +16,10 @@
 #pragma once
 #include "nfb_common.cuh"
 
+#ifndef NFB_GROUP_BARS
+#define NFB_GROUP_BARS 0
+#endif
+
 namespace nfb {
 
 template <int H_, int KC_, int STAGES_, int TN_>
@@ -55,9 +59,21 @@ __host__ __device__ constexpr size_t blob_total_floats(int n_layers) {
 }
 
 // SiLU as the reference's swish: x / (1 + exp(-x)) [main.py:239].  exp overflow must give -0, not NaN.
+// Five instructions: FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL.  exp(-h) = ex2(-h log2(e)) with the product rounded to fp32
+// carries a relative error of |h| * 8.6e-8, but what reaches the activation is at most h^2 e^-|h| * 8.6e-8 < 5e-8 in
+// absolute terms -- below the rounding of the activation itself -- so libdevice's expf (a dozen FMA-pipe instructions
+// per activation, 14 % of the pipe's time on the 128-wide models once the GEMM overlaps everything else) buys nothing.
+// Large negative h: ex2 -> inf, rcp(inf) = 0, h * 0 = -0 as in the reference; NaN propagates.
 __device__ __forceinline__ float silu(float h) {
-  const float e = expf(fminf(-h, 80.0f));  // 1 + e^80 < 2^126, the range __fdividef is exact-ish on
+#ifdef NFB_SILU_LIBDEVICE  // A/B only: the previous formulation
+  const float e = expf(fminf(-h, 80.0f));
   return __fdividef(h, 1.0f + e);
+#else
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(h * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return h * r;
+#endif
 }
 
 // One K-slice of the register-blocked GEMM: acc[TM][8] += W[k][rows] * act[k][cols], k = 0..KC-1.
@@ -242,12 +258,16 @@ __device__ __forceinline__ float clip01_keep_nan(float z) {  // np.clip propagat
 
 // Un-flip + average + squash + decode for one thread's 4 rows x (4 queries + 4 twins) and store.
 // acc[i][j]: packed row 4g+i, query j (j < 4) or twin of query j-4.   [main.py:274-316]
+// The four branches only compute; the stores are shared code behind them (the function is inlined several times per
+// kernel, and the column groups of nfb_ffma_groups_kernel run different parts of it at the same time: code size is
+// instruction-cache pressure).
 __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, long long q0, int nvalid,
                                                  bool vec_ok, const float (&acc)[4][8],
                                                  const float* __restrict__ maha_o,
                                                  const float* __restrict__ maha_t,
                                                  const float* __restrict__ re4) {
   float o0[4], o1[4], o2[4], o3[4];
+  int r0, r1, r2 = -1, r3 = -1;
   if (p.scalars_only && g < 48) return;  // boundary-layer rows not wanted
   if (g < N_BL) {  // theta_u, ue_u, theta_l, ue_l of station g
 #pragma unroll
@@ -262,10 +282,7 @@ __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, lon
       o2[j] = (exp10f(zt_l) - 0.1f) / (fabsf(zu_l) * re);
       o3[j] = zu_l;
     }
-    store_row4(p, 6 + g, q0, nvalid, vec_ok, o0);
-    store_row4(p, 6 + 2 * N_BL + g, q0, nvalid, vec_ok, o1);
-    store_row4(p, 6 + 3 * N_BL + g, q0, nvalid, vec_ok, o2);
-    store_row4(p, 6 + 5 * N_BL + g, q0, nvalid, vec_ok, o3);
+    r0 = 6 + g; r1 = 6 + 2 * N_BL + g; r2 = 6 + 3 * N_BL + g; r3 = 6 + 5 * N_BL + g;
   } else if (g < 48) {  // H_u, H_l of stations s, s + 1
     const int s = 2 * (g - N_BL);
 #pragma unroll
@@ -275,10 +292,7 @@ __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, lon
       o2[j] = 2.6f * expf(0.5f * (acc[2][j] + acc[0][4 + j]));
       o3[j] = 2.6f * expf(0.5f * (acc[3][j] + acc[1][4 + j]));
     }
-    store_row4(p, 6 + N_BL + s, q0, nvalid, vec_ok, o0);
-    store_row4(p, 6 + N_BL + s + 1, q0, nvalid, vec_ok, o1);
-    store_row4(p, 6 + 4 * N_BL + s, q0, nvalid, vec_ok, o2);
-    store_row4(p, 6 + 4 * N_BL + s + 1, q0, nvalid, vec_ok, o3);
+    r0 = 6 + N_BL + s; r1 = r0 + 1; r2 = 6 + 4 * N_BL + s; r3 = r2 + 1;
   } else if (g == 48) {  // analysis_confidence, CL, CD, CM
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -291,18 +305,23 @@ __device__ __forceinline__ void decode_and_store(const EvalParams& p, int g, lon
       o2[j] = expf((z2 - 2.0f) * 2.0f);
       o3[j] = z3 / 20.0f;
     }
-    store_row4(p, 0, q0, nvalid, vec_ok, o0);
-    store_row4(p, 1, q0, nvalid, vec_ok, o1);
-    store_row4(p, 2, q0, nvalid, vec_ok, o2);
-    store_row4(p, 3, q0, nvalid, vec_ok, o3);
+    r0 = 0; r1 = 1; r2 = 2; r3 = 3;
   } else if (g == 49) {  // Top_Xtr, Bot_Xtr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       o0[j] = clip01_keep_nan(0.5f * (acc[0][j] + acc[1][4 + j]));
       o1[j] = clip01_keep_nan(0.5f * (acc[1][j] + acc[0][4 + j]));
+      o2[j] = 0.0f; o3[j] = 0.0f;
     }
-    store_row4(p, 4, q0, nvalid, vec_ok, o0);
-    store_row4(p, 5, q0, nvalid, vec_ok, o1);
+    r0 = 4; r1 = 5;
+  } else {
+    return;
+  }
+  store_row4(p, r0, q0, nvalid, vec_ok, o0);
+  store_row4(p, r1, q0, nvalid, vec_ok, o1);
+  if (r2 >= 0) {
+    store_row4(p, r2, q0, nvalid, vec_ok, o2);
+    store_row4(p, r3, q0, nvalid, vec_ok, o3);
   }
 }
 
@@ -400,6 +419,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_kernel(const EvalPar
     ++it;
   };
 
+  // Hidden layers touch only the 64 columns of this warp's column group (WM warps): with NFB_GROUP_BARS the groups
+  // synchronise among themselves and drift apart as far as the weight ring allows.
+  auto layer_bar = [&]() {
+#if NFB_GROUP_BARS
+    named_bar_sync(2 + wn, WM * 32);
+#else
+    named_bar_sync(1, THREADS);
+#endif
+  };
+
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long tile_q0 = tile * NQ;
 
@@ -433,7 +462,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_kernel(const EvalPar
         ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
         release_slice(s);
       }
-      named_bar_sync(1, THREADS);  // everyone has finished reading this layer's input
+      layer_bar();  // everyone has finished reading this layer's input
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = (i < 4) ? h_row + i : H / 2 + h_row + (i - 4);
@@ -448,8 +477,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_kernel(const EvalPar
           *reinterpret_cast<float4*>(act + row * NC + NC / 2 + h_col + 4 * v) = hi;
         }
       }
-      named_bar_sync(1, THREADS);
+      layer_bar();
     }
+#if NFB_GROUP_BARS
+    named_bar_sync(1, THREADS);  // the last layer reads every column group's rows
+#endif
 
     // ---------------- last layer + fused epilogue, WN passes of 32 queries ----------------
     {

@@ -19,5 +19,5 @@ for size in sizes:
     for _ in range(3): ev.evaluate_device(r, size, out=out)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
-    print(f"{size}: {n / ms / 1e3:.1f} M q/s  {FLOP[size] * n / ms / 1e9:.1f} TFLOP/s", flush=True)
+    print(f"{size}: {n / ms / 1e3:.1f} M q/s  {FLOP[size] * n / ms / 1e9:.1f} TFLOP/s  checksum {float(out.double().nan_to_num(posinf=0.0, neginf=0.0).sum()):.12e}", flush=True)
     del r, out
