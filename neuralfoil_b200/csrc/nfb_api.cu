@@ -41,6 +41,7 @@ struct Model {
   bool loaded = false;
   int n_layers = 0;
   int h_pad = 0;  // 64 / 128 / 256 / 512
+  int k_hidden = 0;  // widest hidden layer rounded up to 16
   int dims[NFB_MAX_LAYERS + 1] = {0};
   float* blob = nullptr;  // device
   // tensor-core variants (256- / 512-wide models): fp16 weight slices of the one-term and the three-term kernels,
@@ -144,17 +145,31 @@ namespace {
 // zero-padded layout; the last layer's rows are permuted by nfb::pack_last_layer_row.
 template <int H>
 std::vector<float> pack_model(int L, const int* dims, const float* const* W, const float* const* B) {
-  std::vector<float> blob(H <= 256 ? nfb::blob_total_floats_swept<H>(L) : nfb::blob_total_floats<H>(L), 0.0f);
-  if (H <= 256) {  // sweep-layout copy of the last layer for nfb_ffma_groups_kernel: Wt[sweep][k][r], bias[256]
+  std::vector<float> blob(nfb::blob_total_floats<H>(L), 0.0f);
+  if constexpr (H <= 256) {  // sweep-layout copy of the last layer for nfb_ffma_groups_kernel (nfb_ffma_groups.cuh)
+    using SB = nfb::SweepBlob<H>;
+    blob.resize(SB::total(L), 0.0f);
     const int in = dims[L - 1], out = dims[L];
-    float* wt = blob.data() + nfb::blob_sweeps_offset<H>(L);
-    float* bias = wt + size_t(nfb::M_LAST_SWEPT) * H;
+    float* bias = blob.data() + SB::bias_off(L);
     for (int pr = 0; pr < nfb::M_LAST_SWEPT; ++pr) {
       const int src_row = nfb::pack_last_layer_row(pr);
       if (src_row < 0 || src_row >= out) continue;
-      const int sweep = pr / H, r = pr % H;
-      for (int k = 0; k < in; ++k) wt[(size_t(sweep) * H + k) * H + r] = W[L - 1][size_t(src_row) * in + k];
       bias[pr] = B[L - 1][src_row];
+      float* dst;      // element (k = 0) of this packed row
+      size_t k_stride;
+      if (pr < SB::NFULL * H) {
+        dst = blob.data() + SB::full_off(L) + size_t(pr / H) * H * H + pr % H;
+        k_stride = H;
+      } else if (SB::NHALF && pr < SB::HALF_ROW0 + H / 2) {
+        dst = blob.data() + SB::half_off(L) + (pr - SB::HALF_ROW0);
+        k_stride = H / 2;
+      } else if (SB::NSCAL && pr >= SB::SCAL_ROW0 && pr < SB::SCAL_ROW0 + 8) {
+        dst = blob.data() + SB::scal_off(L) + (pr - SB::SCAL_ROW0);
+        k_stride = 8;
+      } else {
+        continue;
+      }
+      for (int k = 0; k < in; ++k) dst[k * k_stride] = W[L - 1][size_t(src_row) * in + k];
     }
   }
   for (int l = 0; l < L; ++l) {
@@ -423,6 +438,7 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
   p.n = n;
   p.blob = m.blob;
   p.n_layers = m.n_layers;
+  p.k_hidden = m.k_hidden;
   p.in_f64 = (in_dtype == NFB_F64);
   p.out_f64 = (out_dtype == NFB_F64);
   p.scalars_only = (variant & NFB_OUTPUT_SCALARS) ? 1 : 0;
@@ -641,6 +657,7 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
   }
   m.loaded = true;
   m.n_layers = n_layers;
+  m.k_hidden = std::min(h_pad, (hmax + 15) / 16 * 16);
   m.h_pad = h_pad;
   std::copy(dims, dims + n_layers + 1, m.dims);
   return NFB_OK;
@@ -761,6 +778,7 @@ int jacobian_device_impl(nfb_context* ctx, int model_id, int64_t n, const void* 
   jp.ev.n = n;
   jp.ev.blob = m.blob;
   jp.ev.n_layers = m.n_layers;
+  jp.ev.k_hidden = m.k_hidden;
   jp.ev.in_f64 = (in_dtype == NFB_F64);
   jp.ev.out_f64 = (out_dtype == NFB_F64);
   jp.ev.scalars_only = 0;

@@ -30,6 +30,7 @@ struct EvalParams {
   int in_f64;
   int out_f64;
   int scalars_only;            // NFB_OUTPUT_SCALARS: store rows 0..5 only (out is 6 x out_ld)
+  int k_hidden;                // widest hidden layer rounded up to 16: rows of K beyond it are zero padding
 };
 
 // Mean (25) and packed symmetric quadratic form (325, off-diagonals pre-summed S_ij + S_ji) of the

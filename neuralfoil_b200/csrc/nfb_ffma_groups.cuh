@@ -12,9 +12,17 @@
 // The only thing the groups share is the weight stream: one ring of TMA bulk copies per CTA, which every warp
 // consumes in the same order.  The ring is deep, because its depth is what bounds the drift (see wait_slice).
 //
-// Last layer: 256 / H SWEEPS that look exactly like hidden layers (H packed output rows each, same 8 x TN thread
-// tile, same slice size) whose epilogue is un-flip + average + decode + store instead of SiLU.  Packed row
-// p = sweep * H + r holds latent row pack_last_layer_row(p); a thread owns two row groups of four per sweep.
+// Last layer: SWEEPS that look exactly like hidden layers (same 8 x TN thread tile, same slices) whose epilogue is
+// un-flip + average + decode + store instead of SiLU.  Packed row p = 4 g + i holds latent row pack_last_layer_row(p);
+// a thread owns two row groups g per full sweep.  The 198 rows are 48 groups of boundary-layer rows and 6 scalars:
+//   H =  64: three full sweeps (groups 0..47) + the scalar pass
+//   H = 128: one full sweep (groups 0..31) + one half sweep (4-row thread tile, groups 32..47) + the scalar pass
+//   H = 256: one full sweep of 256 packed rows (50 of 64 groups used)
+// The scalar pass is one more slice of the stream (8 packed rows x K): the group's first warp evaluates the six
+// scalar latents of its 32 queries and their twins, one query per lane, and stores them as 128-byte rows.  Without
+// it the scalars would cost a whole sweep of their own (H = 64: a quarter of the last layer, which is 73 % of
+// xxsmall).  With NFB_OUTPUT_SCALARS the boundary-layer sweeps are not even streamed.
+// K is trimmed to the model's real hidden width rounded up to a slice (48-wide models: 6 of 8 slices per layer).
 // Every accumulator sees the bias, then one IEEE fma per k in k order: results are bit-identical to
 // nfb_ffma_kernel, nfb_small_kernel and the value columns of nfb_jac_kernel (tests/test_gpu_parity.py).
 #pragma once
@@ -39,31 +47,40 @@ struct GroupCfg {
   static constexpr int WM = H / (8 * LM);       // warps per column group
   static constexpr int WN = WARPS / WM;         // column groups per CTA
   static constexpr int GROUP_THREADS = WM * 32;
-  static constexpr int NS = M_LAST_SWEPT / H;   // last-layer sweeps
+  static constexpr int NFULL = H == 64 ? 3 : 1;  // full sweeps: H packed rows each
+  static constexpr int NHALF = H == 128 ? 1 : 0; // half sweep: H / 2 packed rows (4-row thread tile)
+  static constexpr int NSCAL = H == 256 ? 0 : 1; // scalar pass: packed rows 192..199
   static constexpr int SLOT_FLOATS = KC * H;
-  static constexpr int MAX_SLICES = K0_PAD / KC + (NFB_MAX_LAYERS_K - 2) * (H / KC) + NS * (H / KC);
+  static constexpr int MAX_SLICES = K0_PAD / KC + (NFB_MAX_LAYERS_K - 2 + NFULL + NHALF) * (H / KC) + NSCAL;
   static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t(H) * NC + size_t(STAGES) * SLOT_FLOATS + NC + NQ) +
                                        16 * STAGES + 8 * size_t(MAX_SLICES);
   static_assert(TN == 8 || TN == 16, "thread tile is 8 or 16 columns wide");
-  static_assert(H <= 256 && M_LAST_SWEPT % H == 0 && H % (8 * LM) == 0 && WARPS % WM == 0 && WN * 64 == NC, "bad width");
+  static_assert(H <= 256 && KC >= 8 && H % (8 * LM) == 0 && WARPS % WM == 0 && WN * 64 == NC, "bad width");
   static_assert(GROUP_THREADS >= 64, "a group featurises its 64 columns with one thread each");
   static_assert((STAGES & (STAGES - 1)) == 0 && STAGES >= 4, "STAGES must be a power of two >= 4");
   static_assert(K0_PAD % KC == 0 && H % KC == 0, "KC must divide every K");
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
 };
 
-// The sweep-layout copy of the last layer sits behind the blob of nfb_ffma.cuh: Wt[NS][H (k)][H (r)], then bias[256].
+// The sweep-layout copy of the last layer sits behind the blob of nfb_ffma.cuh:
+//   full sweeps Wt[NFULL][k][H], half sweep Wt[k][H / 2], scalar rows Wt[k][8], bias[256] by packed row.
 template <int H>
-__host__ __device__ constexpr size_t blob_sweeps_offset(int n_layers) { return blob_total_floats<H>(n_layers); }
-template <int H>
-__host__ __device__ constexpr size_t blob_total_floats_swept(int n_layers) {
-  return blob_total_floats<H>(n_layers) + size_t(M_LAST_SWEPT) * H + M_LAST_SWEPT;
-}
+struct SweepBlob {
+  static constexpr int NFULL = H == 64 ? 3 : 1, NHALF = H == 128 ? 1 : 0, NSCAL = H == 256 ? 0 : 1;
+  static constexpr int HALF_ROW0 = NFULL * H;  // first packed row of the half sweep (H = 128: 128)
+  static constexpr int SCAL_ROW0 = 192;        // packed rows 192..197: the six scalar latents in latent order
+  __host__ __device__ static constexpr size_t full_off(int n_layers) { return blob_total_floats<H>(n_layers); }
+  __host__ __device__ static constexpr size_t half_off(int n_layers) { return full_off(n_layers) + size_t(NFULL) * H * H; }
+  __host__ __device__ static constexpr size_t scal_off(int n_layers) { return half_off(n_layers) + size_t(NHALF) * H * (H / 2); }
+  __host__ __device__ static constexpr size_t bias_off(int n_layers) { return scal_off(n_layers) + size_t(NSCAL) * H * 8; }
+  __host__ __device__ static constexpr size_t total(int n_layers) { return bias_off(n_layers) + M_LAST_SWEPT; }
+};
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const EvalParams p) {
   constexpr int H = Cfg::H, NC = Cfg::NC, NQ = Cfg::NQ, KC = Cfg::KC, STAGES = Cfg::STAGES, TN = Cfg::TN;
-  constexpr int WM = Cfg::WM, SLOT = Cfg::SLOT_FLOATS, LM = Cfg::LM, LN = Cfg::LN, NS = Cfg::NS;
+  constexpr int WM = Cfg::WM, SLOT = Cfg::SLOT_FLOATS, LM = Cfg::LM, LN = Cfg::LN;
+  constexpr int NFULL = Cfg::NFULL, NHALF = Cfg::NHALF, NSCAL = Cfg::NSCAL;
   constexpr int WARPS = Cfg::WARPS, THREADS = Cfg::THREADS, QT = TN / 2;  // QT queries per thread
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -78,20 +95,25 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.n_layers;
   const long long n_tiles = (p.n + NQ - 1) / NQ;
-  const uint32_t slices_per_tile = K0_PAD / KC + (L - 2 + NS) * (H / KC);
+  using SB = SweepBlob<H>;
+  const int nkh = (p.k_hidden + KC - 1) / KC;                   // K-slices of a hidden / last layer (trimmed K)
+  const bool bl_wanted = !p.scalars_only;                        // boundary-layer rows wanted?
+  const int n_full = (bl_wanted || NSCAL == 0) ? NFULL : 0;      // H = 256: the full sweep also holds the scalars
+  const int n_half = bl_wanted ? NHALF : 0;
+  const uint32_t slices_per_tile = K0_PAD / KC + (L - 2 + n_full + n_half) * nkh + NSCAL;
   const uint32_t my_tiles = uint32_t((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const uint32_t total_slices = my_tiles * slices_per_tile;
 
-  for (uint32_t j = tid; j < slices_per_tile; j += THREADS) {
-    uint32_t off;
-    if (j < K0_PAD / KC) {
-      off = j * KC * H;
-    } else {
-      const uint32_t r = j - K0_PAD / KC, l = 1 + r / (H / KC), c = r % (H / KC);
-      off = (l < uint32_t(L - 1)) ? uint32_t(blob_layer_offset<H>(int(l))) + c * KC * H
-                                  : uint32_t(blob_sweeps_offset<H>(L)) + (l - (L - 1)) * H * H + c * KC * H;
-    }
-    table[j] = make_uint2(off, KC * H * uint32_t(sizeof(float)));
+  if (tid == 0) {  // the tile's slice sequence: {float offset in the blob, bytes}
+    uint32_t j = 0;
+    for (int c = 0; c < K0_PAD / KC; ++c) table[j++] = make_uint2(c * KC * H, KC * H * 4);
+    for (int l = 1; l < L - 1; ++l)
+      for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(blob_layer_offset<H>(l)) + c * KC * H, KC * H * 4);
+    for (int sw = 0; sw < n_full; ++sw)
+      for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(SB::full_off(L)) + (sw * H + c * KC) * H, KC * H * 4);
+    for (int sw = 0; sw < n_half; ++sw)
+      for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(SB::half_off(L)) + c * KC * (H / 2), KC * (H / 2) * 4);
+    if (NSCAL) table[j++] = make_uint2(uint32_t(SB::scal_off(L)), uint32_t(p.k_hidden) * 8 * 4);
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -142,8 +164,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
     ++it;
   };
 
-  const float* const sweep_w = p.blob + blob_sweeps_offset<H>(L);
-  const float* const sweep_bias = sweep_w + size_t(M_LAST_SWEPT) * H;
+  const float* const sweep_bias = p.blob + SB::bias_off(L);
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long tile_q0 = tile * NQ;
@@ -159,8 +180,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
 
     // ---------------- hidden layers ----------------
     for (int l = 0; l < L - 1; ++l) {
-      const int K = (l == 0) ? K0_PAD : H;
-      const float* bias = p.blob + blob_layer_offset<H>(l) + size_t(K) * H;
+      const float* bias = p.blob + blob_layer_offset<H>(l) + size_t(l == 0 ? K0_PAD : H) * H;
       float2 acc[8][TN / 2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -171,7 +191,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
           acc[4 + i][jj] = make_float2(b_hi, b_hi);
         }
       }
-      for (int c = 0; c < K / KC; ++c) {
+      const int nk = (l == 0) ? K0_PAD / KC : nkh;
+      for (int c = 0; c < nk; ++c) {
         uint32_t s;
         wait_slice(s);
         ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
@@ -195,10 +216,26 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
       group_bar();
     }
 
-    // ---------------- last layer: NS sweeps of H packed rows, decode fused ----------------
-    for (int sw = 0; sw < NS; ++sw) {
-      // scalars-only output needs row groups 48 and 49 only: the other sweeps are consumed without arithmetic
-      const bool wanted = !p.scalars_only || (sw + 1) * (H / 4) > 48;
+    // ---------------- last layer: sweeps with the decode fused (the activations are only read) ----------------
+    auto decode_rows = [&](const float2(&a4)[4][TN / 2], int g) {  // four packed rows 4g..4g+3 of this thread's columns
+#pragma unroll
+      for (int v = 0; v < TN / 8; ++v) {  // groups of 4 queries (+ their twins)
+        float yf[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          yf[i][0] = a4[i][2 * v].x; yf[i][1] = a4[i][2 * v].y;
+          yf[i][2] = a4[i][2 * v + 1].x; yf[i][3] = a4[i][2 * v + 1].y;
+          yf[i][4] = a4[i][TN / 4 + 2 * v].x; yf[i][5] = a4[i][TN / 4 + 2 * v].y;
+          yf[i][6] = a4[i][TN / 4 + 2 * v + 1].x; yf[i][7] = a4[i][TN / 4 + 2 * v + 1].y;
+        }
+        const int c4 = h_col + 4 * v;
+        const long long q0 = tile_q0 + c4;
+        const long long left = p.n - q0;
+        const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
+        decode_and_store(p, g, q0, nvalid, vec_ok, yf, maha + c4, maha + NQ + c4, re_s + c4);
+      }
+    };
+    for (int sw = 0; sw < n_full; ++sw) {
       float2 acc[8][TN / 2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -209,34 +246,82 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
           acc[4 + i][jj] = make_float2(b_hi, b_hi);
         }
       }
-      for (int c = 0; c < H / KC; ++c) {
+      for (int c = 0; c < nkh; ++c) {
         uint32_t s;
         wait_slice(s);
-        if (wanted) ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
         release_slice(s);
       }
-      if (!wanted) continue;
+      const int g = sw * (H / 4) + wm * LM + lm;  // packed row groups g and g + H / 8
+      decode_rows(reinterpret_cast<const float2(&)[4][TN / 2]>(acc[0]), g);
+      decode_rows(reinterpret_cast<const float2(&)[4][TN / 2]>(acc[4]), g + H / 8);
+    }
+    if constexpr (NHALF > 0) {
+      if (n_half) {  // packed rows HALF_ROW0 + h_row..+3: one row group per thread
+        float2 acc[4][TN / 2];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int g = sw * (H / 4) + half * (H / 8) + wm * LM + lm;  // packed row group: rows 4g..4g+3
+        for (int i = 0; i < 4; ++i) {
+          const float b = __ldg(sweep_bias + SB::HALF_ROW0 + h_row + i);
 #pragma unroll
-        for (int v = 0; v < TN / 8; ++v) {  // groups of 4 queries (+ their twins)
-          float yf[4][8];
+          for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(b, b);
+        }
+        for (int c = 0; c < nkh; ++c) {
+          uint32_t s;
+          wait_slice(s);
+          ffma_slice<4, TN, H / 2, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+          release_slice(s);
+        }
+        decode_rows(acc, SB::HALF_ROW0 / 4 + wm * LM + lm);
+      }
+    }
+    if constexpr (NSCAL > 0) {
+      // scalar pass: lane = query of the group; accumulators for the query (yq) and its twin (yt), latent rows 0..5
+      uint32_t s;
+      wait_slice(s);
+      if (wm == 0) {
+        const int c = wn * 32 + lane;
+        float yq[6], yt[6];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2(&a)[TN / 2] = acc[4 * half + i];
-            yf[i][0] = a[2 * v].x; yf[i][1] = a[2 * v].y;
-            yf[i][2] = a[2 * v + 1].x; yf[i][3] = a[2 * v + 1].y;
-            yf[i][4] = a[TN / 4 + 2 * v].x; yf[i][5] = a[TN / 4 + 2 * v].y;
-            yf[i][6] = a[TN / 4 + 2 * v + 1].x; yf[i][7] = a[TN / 4 + 2 * v + 1].y;
+        for (int i = 0; i < 6; ++i) yq[i] = yt[i] = __ldg(sweep_bias + SB::SCAL_ROW0 + i);
+        const float* w = ring + s * SLOT;
+        const float* aq = act + c;
+        const int kh = p.k_hidden;
+#pragma unroll 4
+        for (int k = 0; k < kh; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * k);
+          const float2 w1 = *reinterpret_cast<const float2*>(w + 8 * k + 4);
+          const float xq = aq[k * NC], xt = aq[k * NC + NQ];
+          yq[0] = fmaf(w0.x, xq, yq[0]); yt[0] = fmaf(w0.x, xt, yt[0]);
+          yq[1] = fmaf(w0.y, xq, yq[1]); yt[1] = fmaf(w0.y, xt, yt[1]);
+          yq[2] = fmaf(w0.z, xq, yq[2]); yt[2] = fmaf(w0.z, xt, yt[2]);
+          yq[3] = fmaf(w0.w, xq, yq[3]); yt[3] = fmaf(w0.w, xt, yt[3]);
+          yq[4] = fmaf(w1.x, xq, yq[4]); yt[4] = fmaf(w1.x, xt, yt[4]);
+          yq[5] = fmaf(w1.y, xq, yq[5]); yt[5] = fmaf(w1.y, xt, yt[5]);
+        }
+        // the expressions of decode_and_store's groups 48 and 49 [main.py:244-246, 292-303]
+        const float z0 = 0.5f * ((yq[0] - maha[c]) + (yt[0] - maha[NQ + c]));
+        const float z1 = 0.5f * (yq[1] - yt[1]);
+        const float z2 = 0.5f * (yq[2] + yt[2]);
+        const float z3 = 0.5f * (yq[3] - yt[3]);
+        float o[6];
+        o[0] = 1.0f / (1.0f + expf(-z0));
+        o[1] = 0.5f * z1;
+        o[2] = expf((z2 - 2.0f) * 2.0f);
+        o[3] = z3 / 20.0f;
+        o[4] = clip01_keep_nan(0.5f * (yq[4] + yt[5]));
+        o[5] = clip01_keep_nan(0.5f * (yq[5] + yt[4]));
+        const long long q = tile_q0 + c;
+        if (q < p.n) {
+          if (p.out_f64) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) __stcs(static_cast<double*>(p.out) + i * p.out_ld + q, double(o[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) __stcs(static_cast<float*>(p.out) + i * p.out_ld + q, o[i]);
           }
-          const int c4 = h_col + 4 * v;
-          const long long q0 = tile_q0 + c4;
-          const long long left = p.n - q0;
-          const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
-          decode_and_store(p, g, q0, nvalid, vec_ok, yf, maha + c4, maha + NQ + c4, re_s + c4);
         }
       }
+      release_slice(s);
     }
   }
 }
