@@ -113,6 +113,13 @@ using Cfg512 = nfb::FfmaCfg<512, NFB_KC, NFB_STAGES, NFB_TN_WIDE>;
 using Grp64 = nfb::GroupCfg<64, NFB_GRP_KC_64, NFB_GRP_STAGES_64, NFB_TN_NARROW>;
 using Grp128 = nfb::GroupCfg<128, NFB_GRP_KC_128, NFB_GRP_STAGES_128, NFB_TN_WIDE>;
 using Grp256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, NFB_TN_WIDE>;
+#ifndef NFB_GRP_STAGES_512
+#define NFB_GRP_STAGES_512 5
+#endif
+#ifndef NFB_GRP_LEAD_512
+#define NFB_GRP_LEAD_512 0
+#endif
+using Grp512 = nfb::GroupCfg<512, 8, NFB_GRP_STAGES_512, NFB_TN_WIDE, 16, NFB_GRP_LEAD_512>;
 
 struct HostSlot {  // one in-flight chunk of nfb_eval_host
   cudaStream_t stream = nullptr;
@@ -146,7 +153,7 @@ namespace {
 template <int H>
 std::vector<float> pack_model(int L, const int* dims, const float* const* W, const float* const* B) {
   std::vector<float> blob(nfb::blob_total_floats<H>(L), 0.0f);
-  if constexpr (H <= 256) {  // sweep-layout copy of the last layer for nfb_ffma_groups_kernel (nfb_ffma_groups.cuh)
+  {  // sweep-layout copy of the last layer for nfb_ffma_groups_kernel (nfb_ffma_groups.cuh)
     using SB = nfb::SweepBlob<H>;
     blob.resize(SB::total(L), 0.0f);
     const int in = dims[L - 1], out = dims[L];
@@ -475,6 +482,7 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
       case 64: return launch_ffma_groups<Grp64>(ctx, p, stream);
       case 128: return launch_ffma_groups<Grp128>(ctx, p, stream);
       case 256: return launch_ffma_groups<Grp256>(ctx, p, stream);
+      case 512: return launch_ffma_groups<Grp512>(ctx, p, stream);
     }
   }
   switch (m.h_pad) {

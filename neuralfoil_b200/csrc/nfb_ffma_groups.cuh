@@ -1,4 +1,4 @@
-// fp32 (FFMA2) evaluator for the models up to 256 wide: the same arithmetic as nfb_ffma.cuh, scheduled so that the
+// fp32 (FFMA2) evaluator, column-group schedule: the same arithmetic as nfb_ffma.cuh, scheduled so that the
 // phases that do not use the FMA pipe (fp64 featurisation, SiLU, the MUFU-heavy decode, waiting for weights)
 // overlap the GEMM of other warps.
 //
@@ -18,6 +18,7 @@
 //   H =  64: three full sweeps (groups 0..47) + the scalar pass
 //   H = 128: one full sweep (groups 0..31) + one half sweep (4-row thread tile, groups 32..47) + the scalar pass
 //   H = 256: one full sweep of 256 packed rows (50 of 64 groups used)
+//   H = 512: two column groups of 16 queries (four warps each); the 256 packed rows are one half sweep
 // The scalar pass is one more slice of the stream (8 packed rows x K): the group's first warp evaluates the six
 // scalar latents of its 32 queries and their twins, one query per lane, and stores them as 128-byte rows.  Without
 // it the scalars would cost a whole sweep of their own (H = 64: a quarter of the last layer, which is 73 % of
@@ -32,41 +33,13 @@ namespace nfb {
 
 constexpr int M_LAST_SWEPT = 256;  // last layer's packed rows in the sweep layout (64 groups of four, 50 used)
 
-template <int H_, int KC_, int STAGES_, int TN_>
-struct GroupCfg {
-  static constexpr int H = H_;
-  static constexpr int KC = KC_;
-  static constexpr int STAGES = STAGES_;
-  static constexpr int TN = TN_;
-  static constexpr int WARPS = 128 / TN;
-  static constexpr int THREADS = WARPS * 32;
-  static constexpr int LN = 64 / TN;            // lanes along columns: a warp always spans 64 columns
-  static constexpr int LM = 32 / LN;            // lanes along rows
-  static constexpr int NC = 32768 / H;
-  static constexpr int NQ = NC / 2;
-  static constexpr int WM = H / (8 * LM);       // warps per column group
-  static constexpr int WN = WARPS / WM;         // column groups per CTA
-  static constexpr int GROUP_THREADS = WM * 32;
-  static constexpr int NFULL = H == 64 ? 3 : 1;  // full sweeps: H packed rows each
-  static constexpr int NHALF = H == 128 ? 1 : 0; // half sweep: H / 2 packed rows (4-row thread tile)
-  static constexpr int NSCAL = H == 256 ? 0 : 1; // scalar pass: packed rows 192..199
-  static constexpr int SLOT_FLOATS = KC * H;
-  static constexpr int MAX_SLICES = K0_PAD / KC + (NFB_MAX_LAYERS_K - 2 + NFULL + NHALF) * (H / KC) + NSCAL;
-  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t(H) * NC + size_t(STAGES) * SLOT_FLOATS + NC + NQ) +
-                                       16 * STAGES + 8 * size_t(MAX_SLICES);
-  static_assert(TN == 8 || TN == 16, "thread tile is 8 or 16 columns wide");
-  static_assert(H <= 256 && KC >= 8 && H % (8 * LM) == 0 && WARPS % WM == 0 && WN * 64 == NC, "bad width");
-  static_assert(GROUP_THREADS >= 64, "a group featurises its 64 columns with one thread each");
-  static_assert((STAGES & (STAGES - 1)) == 0 && STAGES >= 4, "STAGES must be a power of two >= 4");
-  static_assert(K0_PAD % KC == 0 && H % KC == 0, "KC must divide every K");
-  static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
-};
-
 // The sweep-layout copy of the last layer sits behind the blob of nfb_ffma.cuh:
 //   full sweeps Wt[NFULL][k][H], half sweep Wt[k][H / 2], scalar rows Wt[k][8], bias[256] by packed row.
 template <int H>
 struct SweepBlob {
-  static constexpr int NFULL = H == 64 ? 3 : 1, NHALF = H == 128 ? 1 : 0, NSCAL = H == 256 ? 0 : 1;
+  static constexpr int NFULL = H == 64 ? 3 : H == 512 ? 0 : 1;     // H = 512: the 256 packed rows are one half sweep
+  static constexpr int NHALF = (H == 128 || H == 512) ? 1 : 0;
+  static constexpr int NSCAL = H >= 256 ? 0 : 1;                   // H >= 256: the scalars ride in the sweep
   static constexpr int HALF_ROW0 = NFULL * H;  // first packed row of the half sweep (H = 128: 128)
   static constexpr int SCAL_ROW0 = 192;        // packed rows 192..197: the six scalar latents in latent order
   __host__ __device__ static constexpr size_t full_off(int n_layers) { return blob_total_floats<H>(n_layers); }
@@ -76,11 +49,44 @@ struct SweepBlob {
   __host__ __device__ static constexpr size_t total(int n_layers) { return bias_off(n_layers) + M_LAST_SWEPT; }
 };
 
+template <int H_, int KC_, int STAGES_, int TN_, int QG_ = 32, int LEAD_ = 0>
+struct GroupCfg {
+  static constexpr int H = H_;
+  static constexpr int KC = KC_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr int TN = TN_;
+  static constexpr int LEAD = LEAD_ > 0 ? LEAD_ : STAGES_ / 2;  // slices the copies run ahead of their issuer
+  static constexpr int QG = QG_;                // queries per column group: 32, or 16 for the 512-wide model
+  static constexpr int WARPS = 128 / TN;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int LN = 2 * QG / TN;        // lanes along columns: a warp spans its group's 2 QG columns
+  static constexpr int LM = 32 / LN;            // lanes along rows
+  static constexpr int NC = 32768 / H;
+  static constexpr int NQ = NC / 2;
+  static constexpr int WM = H / (8 * LM);       // warps per column group
+  static constexpr int WN = WARPS / WM;         // column groups per CTA
+  static constexpr int GROUP_THREADS = WM * 32;
+  static constexpr int NFULL = SweepBlob<H>::NFULL;  // full sweeps: H packed rows each
+  static constexpr int NHALF = SweepBlob<H>::NHALF;  // half sweep: H / 2 packed rows (4-row thread tile)
+  static constexpr int NSCAL = SweepBlob<H>::NSCAL;  // scalar pass: packed rows 192..199
+  static constexpr int SLOT_FLOATS = KC * H;
+  static constexpr int MAX_SLICES = K0_PAD / KC + (NFB_MAX_LAYERS_K - 2 + NFULL + NHALF) * (H / KC) + NSCAL;
+  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t(H) * NC + size_t(STAGES) * SLOT_FLOATS + NC + NQ) +
+                                       16 * STAGES + 8 * size_t(MAX_SLICES);
+  static_assert(TN == 8 || TN == 16, "thread tile is 8 or 16 columns wide");
+  static_assert(KC >= 8 && H % (8 * LM) == 0 && WARPS % WM == 0 && WN * 2 * QG == NC, "bad width");
+  static_assert(GROUP_THREADS >= 2 * QG, "a group featurises its columns with one thread each");
+  static_assert(NSCAL == 0 || QG == 32, "the scalar pass is one query per lane");
+  static_assert(STAGES >= 4 && LEAD >= 1 && LEAD < STAGES, "ring too shallow");
+  static_assert(K0_PAD % KC == 0 && H % KC == 0, "KC must divide every K");
+  static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
+};
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const EvalParams p) {
   constexpr int H = Cfg::H, NC = Cfg::NC, NQ = Cfg::NQ, KC = Cfg::KC, STAGES = Cfg::STAGES, TN = Cfg::TN;
   constexpr int WM = Cfg::WM, SLOT = Cfg::SLOT_FLOATS, LM = Cfg::LM, LN = Cfg::LN;
-  constexpr int NFULL = Cfg::NFULL, NHALF = Cfg::NHALF, NSCAL = Cfg::NSCAL;
+  constexpr int NFULL = Cfg::NFULL, NHALF = Cfg::NHALF, NSCAL = Cfg::NSCAL, QG = Cfg::QG;
   constexpr int WARPS = Cfg::WARPS, THREADS = Cfg::THREADS, QT = TN / 2;  // QT queries per thread
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -98,8 +104,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
   using SB = SweepBlob<H>;
   const int nkh = (p.k_hidden + KC - 1) / KC;                   // K-slices of a hidden / last layer (trimmed K)
   const bool bl_wanted = !p.scalars_only;                        // boundary-layer rows wanted?
-  const int n_full = (bl_wanted || NSCAL == 0) ? NFULL : 0;      // H = 256: the full sweep also holds the scalars
-  const int n_half = bl_wanted ? NHALF : 0;
+  const int n_full = (bl_wanted || NSCAL == 0) ? NFULL : 0;      // H >= 256: the sweep also holds the scalars
+  const int n_half = (bl_wanted || NSCAL == 0) ? NHALF : 0;
   const uint32_t slices_per_tile = K0_PAD / KC + (L - 2 + n_full + n_half) * nkh + NSCAL;
   const uint32_t my_tiles = uint32_t((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const uint32_t total_slices = my_tiles * slices_per_tile;
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
   const int lm = lane / LN, ln = lane % LN;
   const int wm = warp % WM, wn = warp / WM;   // wn: this warp's column group
   const int h_row = (wm * LM + lm) * 4;       // rows h_row..+3 and H/2 + h_row..+3 of a layer (or of a sweep)
-  const int h_col = wn * 32 + ln * QT;        // columns h_col..+QT-1 and NC/2 + h_col..
+  const int h_col = wn * QG + ln * QT;        // columns h_col..+QT-1 and NC/2 + h_col..
   const int gtid = tid - wn * Cfg::GROUP_THREADS;
   auto group_bar = [&]() { named_bar_sync(1 + wn, Cfg::GROUP_THREADS); };
 
@@ -141,11 +147,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
   // than LEAD slices ahead of the issuers: LEAD = STAGES / 2 bounds the drift of the groups by half a ring either way.
   // (Measured and rejected: feeding the ring opportunistically -- whichever warp finds the next slot free claims the
   //  slice with a shared-memory atomic -- puts a shared-memory round trip on every warp's path at every slice: -3 %.)
-  constexpr uint32_t LEAD = STAGES / 2;
+  constexpr uint32_t LEAD = Cfg::LEAD;
   uint32_t it = 0;  // slices this warp has consumed
   auto issue = [&](uint32_t j) {
     const uint2 e = table[j % slices_per_tile];
-    const uint32_t s = j & (STAGES - 1), ph = (j / STAGES) & 1;
+    const uint32_t s = j % STAGES, ph = (j / STAGES) & 1;
     mbar_wait(bar_empty + 8 * s, ph ^ 1);
     mbar_arrive_expect_tx(bar_full + 8 * s, e.y);
     bulk_copy_g2s(smem_u32(ring + s * SLOT), p.blob + e.x, e.y, bar_full + 8 * s);
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
   auto wait_slice = [&](uint32_t& s_out) {
     const uint32_t j = it + LEAD;
     if (lane == 0 && (j & (WARPS - 1)) == uint32_t(warp) && j < total_slices) issue(j);
-    s_out = it & (STAGES - 1);
+    s_out = it % STAGES;
     mbar_wait(bar_full + 8 * s_out, (it / STAGES) & 1);
   };
   auto release_slice = [&](uint32_t s) {
@@ -170,9 +176,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
     const long long tile_q0 = tile * NQ;
 
     group_bar();  // this group's readers of its `act` columns, `maha`, `re_s` (previous tile) are done
-    if (gtid < 64) {
-      const bool twin = gtid >= 32;
-      const int c = wn * 32 + (gtid & 31);
+    if (gtid < 2 * QG) {
+      const bool twin = gtid >= QG;
+      const int c = wn * QG + (gtid % QG);
       const long long q = tile_q0 + c;
       featurise_column<NC>(p, q, q < p.n, twin, twin ? NQ + c : c, act, maha, re_s);
     }
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
       uint32_t s;
       wait_slice(s);
       if (wm == 0) {
-        const int c = wn * 32 + lane;
+        const int c = wn * QG + lane;
         float yq[6], yt[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) yq[i] = yt[i] = __ldg(sweep_bias + SB::SCAL_ROW0 + i);

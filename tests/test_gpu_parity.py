@@ -647,3 +647,49 @@ def test_vjp_matches_oracle_and_jacobian(evaluator, oracle, size):
     err = np.abs(grad - want) * scale
     ref = np.abs(want) * scale + np.einsum("rq,rq->q", np.abs(cot), np.abs(want_v))[None, :] * 1e-1
     assert (err <= 5e-3 * ref + 1e-6).mean() > 0.999 and np.median(err / np.maximum(ref, 1e-30)) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# The fp32 path runs the column-group kernels (nfb_ffma_groups.cuh); the CTA-synchronous tiled kernels (nfb_ffma.cuh)
+# are the earlier implementation of the same arithmetic, selectable with NFB_FFMA_TILED=1 (read once per process).
+# Both must give the same bits: same bias + fma chain per output, same SiLU, same decode.
+# ---------------------------------------------------------------------------------------------
+_TILED_DUMP = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {repo!r})
+from neuralfoil_b200 import Evaluator, synthetic
+ev = Evaluator(device=0, extra_models={{"xxxlarge": synthetic.synthetic_xxxlarge_params()}})
+res = {{}}
+for size, n in {cases!r}:
+    raw = torch.from_numpy(synthetic.sample_training_distribution(n, seed=500 + n, dtype=np.float32)).cuda()
+    res[f"{{size}}_{{n}}"] = ev.evaluate_device(raw, size).cpu().numpy()
+    res[f"{{size}}_{{n}}_scalars"] = ev.evaluate_device(raw, size, outputs="scalars").cpu().numpy()
+np.savez({out!r}, **res)
+print("DUMP_OK")
+"""
+
+_GROUP_CASES = [("xxsmall", 20_011), ("xsmall", 9_999), ("small", 20_000), ("medium", 33_333), ("large", 20_001),
+                ("xlarge", 50_021), ("xxlarge", 20_003), ("xxxlarge", 9_001)]
+
+
+@pytest.mark.gpu
+def test_column_group_kernels_match_tiled_kernels_bit_for_bit(tmp_path):
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    repo = Path(__file__).resolve().parents[1]
+    dumps = {}
+    for name, extra_env in (("groups", {}), ("tiled", {"NFB_FFMA_TILED": "1"})):
+        out = tmp_path / f"{name}.npz"
+        code = _TILED_DUMP.format(repo=str(repo), cases=_GROUP_CASES, out=str(out))
+        res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra_env), capture_output=True,
+                             text=True, timeout=600)
+        assert res.returncode == 0 and "DUMP_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+        dumps[name] = np.load(out)
+    for key in dumps["groups"].files:
+        a, b = dumps["groups"][key], dumps["tiled"][key]
+        assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), key
+        if key.endswith("_scalars"):
+            assert a.shape[0] == 6 and np.array_equal(a, dumps["groups"][key[: -len("_scalars")]][:6], equal_nan=True), key
