@@ -48,7 +48,7 @@ FLOP_PER_QUERY = {  # 2 twins x 2 x sum(in * out) over the layers, unpadded
     "large": 310_784, "xlarge": 376_320, "xxlarge": 1_276_928, "xxxlarge": 5_699_584,
 }
 # DRAM traffic per query of the two xxxlarge kernels, from one `ncu --set full` capture each of this file's own
-# command at 10 M queries (profiles/r1_ncu_full_xxxlarge_ffma.txt / _tensor.txt: dram__bytes_read.sum + dram__bytes_write.sum
+# command at 10 M queries (profiles/r1_ncu_full_xxxlarge_ffma_groups.txt / _tensor_pair_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum
 # = 8.900 GB and 8.805 GB per launch; algorithmic 8.840 GB).  Reported as roofline.traffic, scaled to the run's n.
 NCU_TRAFFIC_BYTES_PER_QUERY = {("xxxlarge", "fp32"): 890.0, ("xxxlarge", "tensor"): 880.4, ("xxxlarge", "tensor_fp32"): 882.9}
 METRIC = "airfoil_queries_per_sec"
@@ -400,7 +400,7 @@ def main():
                                      "run at full rate as half of a pair-wide M = 128 MMA"}})
         roofline = {
             "bound": "fp32",
-            "kernel": "nfb_ffma_kernel",
+            "kernel": "nfb_ffma_groups_kernel",
             "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak if fp32_peak else None,
             "peak_source": "measured on this GPU by nfb_measure_fp32_peak (register-resident FFMA loop); "

@@ -1,4 +1,5 @@
-timeout 300 python scripts/size_sweep.py xxxlarge > gpurun_out/lead_2.txt 2>&1
-for v in lead1 lead3; do NFB_LIB_PATH=/root/repo/build_ab/$v.so timeout 300 python scripts/size_sweep.py xxxlarge > gpurun_out/$v.txt 2>&1; done
-tail -n 2 gpurun_out/lead*.txt
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python bench.py > gpurun_out/bench_groups.json 2> gpurun_out/bench_groups.err; echo "bench rc=$?"
+python bench.py --model-size xlarge --no-tensor-extra --no-cpu-baseline > gpurun_out/bench_groups_xlarge.json 2> gpurun_out/bench_groups_xlarge.err; echo "bench xlarge rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:nfb_ffma_groups_kernel -s 1 -c 1 -f -o gpurun_out/ffma_xxxlarge_groups_10M python scripts/ncu_target_ffma.py xxxlarge 10000000 > gpurun_out/ncu1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:nfb_ffma_groups_kernel -s 1 -c 1 -f -o gpurun_out/ffma_xlarge_groups_final python scripts/ncu_target_ffma.py xlarge 10000000 > gpurun_out/ncu2.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:nfb_ffma_groups_kernel -s 1 -c 1 -f -o gpurun_out/ffma_xxsmall_groups_final python scripts/ncu_target_ffma.py xxsmall 10000000 > gpurun_out/ncu3.log 2>&1
