@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "nfb_ffma.cuh"
@@ -128,6 +130,9 @@ struct HostSlot {  // one in-flight chunk of nfb_eval_host
   size_t in_bytes = 0, out_bytes = 0;
   void* h_stage = nullptr;  // pinned staging for the small-batch path
   size_t stage_bytes = 0;
+  void* h_in = nullptr;     // pinned staging of the large-batch path when the caller's arrays are pageable
+  void* h_out = nullptr;
+  size_t h_in_bytes = 0, h_out_bytes = 0;
 };
 
 }  // namespace
@@ -494,6 +499,65 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
   return fail(NFB_ERR_UNSUPPORTED_MODEL, "no kernel for padded width %d", m.h_pad);
 }
 
+// ---- host-side staging for pageable caller memory (nfb_eval_host, large batches) ---------------------------------
+// cudaMemcpy from / to pageable memory goes through the driver's own bounce buffers on one thread: 4 GB/s measured
+// for the 792 MB of a 1 M-query float32 block, 315 ms for the float64 dict of the drop-in call, whatever the model
+// size.  Instead the library copies between the caller's arrays and its own pinned buffers with every host core
+// (first-touch page faults of a freshly allocated result included) and lets the GPU write float32 even when the
+// caller wants float64: the widening happens in that copy, and half the bytes cross PCIe.
+int host_threads() {
+  static const int n = [] {
+    const char* e = getenv("NFB_HOST_THREADS");
+    int v = e ? atoi(e) : int(std::thread::hardware_concurrency());
+    return std::max(1, std::min(v, 32));
+  }();
+  return n;
+}
+
+template <class F>
+void parallel_units(int64_t units, F&& f) {  // f(unit) for unit in [0, units), dynamically scheduled
+  const int nt = int(std::min<int64_t>(host_threads(), units));
+  if (nt <= 1) {
+    for (int64_t u = 0; u < units; ++u) f(u);
+    return;
+  }
+  std::atomic<int64_t> next{0};
+  auto work = [&] {
+    for (int64_t u = next.fetch_add(1); u < units; u = next.fetch_add(1)) f(u);
+  };
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+}
+
+bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+constexpr int64_t STAGE_BLOCK = 1 << 16;  // elements per copy unit
+
+// rows x cn block of float32 in pinned memory (row stride src_ld) -> the caller's block (row stride dst_ld, float32 or float64)
+void unstage_output(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, bool dst_f64, int rows, int64_t cn) {
+  const int64_t blocks = (cn + STAGE_BLOCK - 1) / STAGE_BLOCK;
+  parallel_units(rows * blocks, [&](int64_t u) {
+    const int64_t r = u / blocks, i0 = (u % blocks) * STAGE_BLOCK, i1 = std::min(cn, i0 + STAGE_BLOCK);
+    const float* sp = src + r * src_ld;
+    if (dst_f64) {
+      double* dp = static_cast<double*>(dst) + r * dst_ld;
+      for (int64_t i = i0; i < i1; ++i) dp[i] = double(sp[i]);
+    } else {
+      memcpy(static_cast<float*>(dst) + r * dst_ld + i0, sp + i0, size_t(i1 - i0) * sizeof(float));
+    }
+  });
+}
+
 int ensure(void** ptr, size_t* have, size_t need, bool pinned_host) {
   if (*have >= need) return NFB_OK;
   if (*ptr) {
@@ -569,6 +633,8 @@ void nfb_destroy(nfb_context* ctx) {
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
     if (s.h_stage) cudaFreeHost(s.h_stage);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
   }
   if (ctx->tc_debug) cudaFree(ctx->tc_debug);
   if (ctx->jac_dev) cudaFree(ctx->jac_dev);
@@ -688,21 +754,42 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   if (rc != NFB_OK || n == 0) return rc;
   NFB_CUDA(cudaSetDevice(ctx->device));
   const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
-  if (chunk <= 0) chunk = 1 << 19;
-  chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
-  const int out_rows = (variant & NFB_OUTPUT_SCALARS) ? 6 : nfb::N_OUT;
-  const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(out_rows) * chunk * osz;
-
   // Small batches (a design optimiser's per-iteration call): pack everything into one pinned block so
   // that there is exactly one H2D copy, one launch and one D2H copy.
   const bool small = n <= 16384;
-  int64_t done = 0;
+  // Large batches in pageable memory (NumPy arrays): staged through pinned buffers by all host cores, see host_threads().
+  const bool stage_out = !small && is_pageable(out);
+  bool stage_in = false;
+  if (!small)
+    for (int r = 0; r < nfb::N_RAW; ++r)
+      if (in_strides[r] != 0) {
+        stage_in = is_pageable(in_rows[r]);
+        break;
+      }
+  // default chunk: 512 Ki queries; 128 Ki when the host copies are the library's own, so that they overlap the GPU sooner
+  if (chunk <= 0) chunk = stage_out ? (1 << 17) : (1 << 19);
+  chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
+  const int out_rows = (variant & NFB_OUTPUT_SCALARS) ? 6 : nfb::N_OUT;
+  const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(out_rows) * chunk * osz;
+  const int dev_out_dtype = stage_out ? NFB_F32 : out_dtype;  // staged: the GPU writes float32, the copy widens
+  const size_t dev_osz = dev_out_dtype == NFB_F64 ? 8 : 4;
+  const size_t dev_out_need = size_t(out_rows) * chunk * dev_osz;
+  struct Landed { HostSlot* slot = nullptr; int64_t c0 = 0, cn = 0; } landed;  // staged chunk whose D2H is in flight
+  auto finish_landed = [&]() -> int {
+    if (!landed.slot) return NFB_OK;
+    NFB_CUDA(cudaStreamSynchronize(landed.slot->stream));
+    unstage_output(static_cast<const float*>(landed.slot->h_out), chunk, static_cast<char*>(out) + size_t(landed.c0) * osz,
+                   out_ld, out_dtype == NFB_F64, out_rows, landed.cn);
+    landed.slot = nullptr;
+    return NFB_OK;
+  };
+
   for (int64_t c0 = 0, ci = 0; c0 < n; c0 += chunk, ++ci) {
     HostSlot& s = ctx->slots[ci & 1];
     const int64_t cn = std::min<int64_t>(chunk, n - c0);
     NFB_CUDA(cudaStreamSynchronize(s.stream));  // the slot's previous chunk has fully landed
     if ((rc = ensure(&s.d_in, &s.in_bytes, in_need, false)) != NFB_OK) return rc;
-    if ((rc = ensure(&s.d_out, &s.out_bytes, out_need, false)) != NFB_OK) return rc;
+    if ((rc = ensure(&s.d_out, &s.out_bytes, small ? out_need : dev_out_need, false)) != NFB_OK) return rc;
 
     const void* d_rows[nfb::N_RAW];
     int64_t d_strides[nfb::N_RAW];
@@ -725,6 +812,27 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
         d_rows[r] = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
       }
       NFB_CUDA(cudaMemcpyAsync(s.d_in, hs, in_need, cudaMemcpyHostToDevice, s.stream));
+    } else if (stage_in) {
+      if ((rc = ensure(&s.h_in, &s.h_in_bytes, in_need, true)) != NFB_OK) return rc;
+      char* hs = static_cast<char*>(s.h_in);
+      const int64_t blocks = (cn + STAGE_BLOCK - 1) / STAGE_BLOCK;
+      parallel_units(nfb::N_RAW * blocks, [&](int64_t u) {
+        const int64_t r = u / blocks, i0 = (u % blocks) * STAGE_BLOCK, i1 = std::min(cn, i0 + STAGE_BLOCK);
+        char* dst = hs + size_t(r) * chunk * isz;
+        const char* src = static_cast<const char*>(in_rows[r]);
+        if (in_strides[r] == 1) {
+          memcpy(dst + size_t(i0) * isz, src + size_t(c0 + i0) * isz, size_t(i1 - i0) * isz);
+        } else if (in_strides[r] == 0) {
+          if (i0 == 0) memcpy(dst, src, isz);
+        } else {
+          for (int64_t i = i0; i < i1; ++i) memcpy(dst + i * isz, src + size_t(c0 + i) * in_strides[r] * isz, isz);
+        }
+      });
+      for (int r = 0; r < nfb::N_RAW; ++r) {
+        d_rows[r] = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
+        d_strides[r] = in_strides[r] == 0 ? 0 : 1;
+      }
+      NFB_CUDA(cudaMemcpyAsync(s.d_in, hs, in_need, cudaMemcpyHostToDevice, s.stream));
     } else {
       for (int r = 0; r < nfb::N_RAW; ++r) {
         char* dst = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
@@ -743,7 +851,8 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
         d_rows[r] = dst;
       }
     }
-    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype, s.d_out, chunk, out_dtype, s.stream);
+    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype, s.d_out, chunk,
+                          small ? out_dtype : dev_out_dtype, s.stream);
     if (rc != NFB_OK) return rc;
     char* out_c = static_cast<char*>(out) + size_t(c0) * osz;
     if (small) {
@@ -752,14 +861,18 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
       NFB_CUDA(cudaStreamSynchronize(s.stream));
       for (int r = 0; r < out_rows; ++r)
         memcpy(out_c + size_t(r) * out_ld * osz, hs_out + size_t(r) * chunk * osz, size_t(cn) * osz);
+    } else if (stage_out) {
+      if ((rc = ensure(&s.h_out, &s.h_out_bytes, dev_out_need, true)) != NFB_OK) return rc;
+      NFB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, dev_out_need, cudaMemcpyDeviceToHost, s.stream));
+      if ((rc = finish_landed()) != NFB_OK) return rc;  // the previous chunk's copy-out runs under this chunk's GPU work
+      landed.slot = &s; landed.c0 = c0; landed.cn = cn;
     } else {
       NFB_CUDA(cudaMemcpy2DAsync(out_c, size_t(out_ld) * osz, s.d_out, size_t(chunk) * osz, size_t(cn) * osz,
                                  out_rows, cudaMemcpyDeviceToHost, s.stream));
     }
-    done += cn;
   }
+  if ((rc = finish_landed()) != NFB_OK) return rc;
   for (auto& s : ctx->slots) NFB_CUDA(cudaStreamSynchronize(s.stream));
-  (void)done;
   return NFB_OK;
 }
 

@@ -283,6 +283,35 @@ def test_host_chunking_is_invisible(evaluator):
     np.testing.assert_array_equal(one, many)
 
 
+def test_pageable_host_arrays_are_staged_without_changing_a_bit(evaluator):
+    """nfb_eval_host with pageable (NumPy) memory goes through the library's pinned staging buffers and host threads, and
+    the GPU writes float32 even for a float64 result; with pinned memory the copies are direct.  Same bits either way."""
+    import torch
+
+    n = 300_007  # three staged chunks of 128 Ki queries, the last one ragged
+    raw = synthetic.sample_training_distribution(n, seed=31)
+    dev = evaluator.evaluate_device(torch.from_numpy(raw.astype(np.float32)).cuda(), "medium")
+    torch.cuda.synchronize()
+    want32 = dev.cpu().numpy()
+    got32 = evaluator.evaluate_host(raw.astype(np.float32), "medium", out_dtype=np.float32)
+    np.testing.assert_array_equal(got32, want32)
+    got64 = evaluator.evaluate_host(raw.astype(np.float32), "medium", out_dtype=np.float64)
+    assert got64.dtype == np.float64
+    np.testing.assert_array_equal(got64, want32.astype(np.float64))
+    np.testing.assert_array_equal(evaluator.evaluate_host(raw.astype(np.float32), "medium", out_dtype=np.float64, chunk=50_000), got64)
+    sc = evaluator.evaluate_host(raw.astype(np.float32), "medium", out_dtype=np.float64, outputs="scalars")
+    np.testing.assert_array_equal(sc, got64[:6])
+    # float64 inputs, broadcast rows (the drop-in call): one airfoil, varying alpha / Re
+    kul = dict(upper_weights=raw[0:8, 0], lower_weights=raw[8:16, 0], leading_edge_weight=raw[16, 0], TE_thickness=raw[17, 0])
+    aero = evaluator.get_aero_from_kulfan_parameters(kul, alpha=raw[18], Re=raw[19], n_crit=7.0, model_size="medium")
+    rows = raw.copy()
+    rows[0:18] = raw[0:18, :1]
+    rows[20], rows[21], rows[22] = 7.0, 1.0, 1.0
+    ref = evaluator.evaluate_device(torch.from_numpy(rows).cuda(), "medium", out_dtype=torch.float64)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(np.stack([aero[k] for k in output_keys()]), ref.cpu().numpy())
+
+
 @pytest.mark.parametrize("size,n", [("xxxlarge", 1_000_000), ("xlarge", 1_000_000), ("xxsmall", 2_000_000)])
 def test_large_batch_properties(evaluator, oracle, size, n):
     """
