@@ -113,7 +113,10 @@ using Cfg512 = nfb::FfmaCfg<512, NFB_KC, NFB_STAGES, NFB_TN_WIDE>;
 #define NFB_GRP_STAGES_256 8
 #endif
 using Grp64 = nfb::GroupCfg<64, NFB_GRP_KC_64, NFB_GRP_STAGES_64, NFB_TN_NARROW>;
-using Grp128 = nfb::GroupCfg<128, NFB_GRP_KC_128, NFB_GRP_STAGES_128, NFB_TN_WIDE>;
+#ifndef NFB_GRP_TN_128
+#define NFB_GRP_TN_128 8  // 16 warps x (8 x 8) against 8 warps x (8 x 16): +1..2.5 % at this width, a wash at 256 and 512
+#endif
+using Grp128 = nfb::GroupCfg<128, NFB_GRP_KC_128, NFB_GRP_STAGES_128, NFB_GRP_TN_128>;
 using Grp256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, NFB_TN_WIDE>;
 #ifndef NFB_GRP_STAGES_512
 #define NFB_GRP_STAGES_512 5

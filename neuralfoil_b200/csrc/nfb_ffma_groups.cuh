@@ -75,7 +75,6 @@ struct GroupCfg {
                                        16 * STAGES + 8 * size_t(MAX_SLICES);
   static_assert(TN == 8 || TN == 16, "thread tile is 8 or 16 columns wide");
   static_assert(KC >= 8 && H % (8 * LM) == 0 && WARPS % WM == 0 && WN * 2 * QG == NC, "bad width");
-  static_assert(GROUP_THREADS >= 2 * QG, "a group featurises its columns with one thread each");
   static_assert(NSCAL == 0 || QG == 32, "the scalar pass is one query per lane");
   static_assert(STAGES >= 4 && LEAD >= 1 && LEAD < STAGES, "ring too shallow");
   static_assert(K0_PAD % KC == 0 && H % KC == 0, "KC must divide every K");
@@ -176,9 +175,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
     const long long tile_q0 = tile * NQ;
 
     group_bar();  // this group's readers of its `act` columns, `maha`, `re_s` (previous tile) are done
-    if (gtid < 2 * QG) {
-      const bool twin = gtid >= QG;
-      const int c = wn * QG + (gtid % QG);
+    for (int t = gtid; t < 2 * QG; t += Cfg::GROUP_THREADS) {
+      const bool twin = t >= QG;
+      const int c = wn * QG + (t % QG);
       const long long q = tile_q0 + c;
       featurise_column<NC>(p, q, q < p.n, twin, twin ? NQ + c : c, act, maha, re_s);
     }
