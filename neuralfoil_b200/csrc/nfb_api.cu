@@ -518,8 +518,8 @@ int host_threads() {
 }
 
 template <class F>
-void parallel_units(int64_t units, F&& f) {  // f(unit) for unit in [0, units), dynamically scheduled
-  const int nt = int(std::min<int64_t>(host_threads(), units));
+void parallel_units(int64_t units, F&& f, int max_threads = 1 << 30) {  // f(unit) for unit in [0, units), dynamically scheduled
+  const int nt = int(std::min<int64_t>(std::min(host_threads(), max_threads), units));
   if (nt <= 1) {
     for (int64_t u = 0; u < units; ++u) f(u);
     return;
@@ -549,6 +549,7 @@ constexpr int64_t STAGE_BLOCK = 1 << 16;  // elements per copy unit
 // rows x cn block of float32 in pinned memory (row stride src_ld) -> the caller's block (row stride dst_ld, float32 or float64)
 void unstage_output(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, bool dst_f64, int rows, int64_t cn) {
   const int64_t blocks = (cn + STAGE_BLOCK - 1) / STAGE_BLOCK;
+  const int max_threads = int(rows * cn / (1 << 19)) + 1;  // a thread costs ~30 us to start: one per 512 Ki elements
   parallel_units(rows * blocks, [&](int64_t u) {
     const int64_t r = u / blocks, i0 = (u % blocks) * STAGE_BLOCK, i1 = std::min(cn, i0 + STAGE_BLOCK);
     const float* sp = src + r * src_ld;
@@ -558,7 +559,7 @@ void unstage_output(const float* src, int64_t src_ld, void* dst, int64_t dst_ld,
     } else {
       memcpy(static_cast<float*>(dst) + r * dst_ld + i0, sp + i0, size_t(i1 - i0) * sizeof(float));
     }
-  });
+  }, max_threads);
 }
 
 int ensure(void** ptr, size_t* have, size_t need, bool pinned_host) {
@@ -774,7 +775,10 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
   const int out_rows = (variant & NFB_OUTPUT_SCALARS) ? 6 : nfb::N_OUT;
   const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(out_rows) * chunk * osz;
-  const int dev_out_dtype = stage_out ? NFB_F32 : out_dtype;  // staged: the GPU writes float32, the copy widens
+  // staged: the GPU writes float32, the copy widens.  Same for float64 results of the larger small batches (their rows
+  // are copied out of the pinned block anyway): half the D2H bytes.
+  const bool small_widen = small && out_dtype == NFB_F64 && n >= 2048;
+  const int dev_out_dtype = (stage_out || small_widen) ? NFB_F32 : out_dtype;
   const size_t dev_osz = dev_out_dtype == NFB_F64 ? 8 : 4;
   const size_t dev_out_need = size_t(out_rows) * chunk * dev_osz;
   struct Landed { HostSlot* slot = nullptr; int64_t c0 = 0, cn = 0; } landed;  // staged chunk whose D2H is in flight
@@ -792,7 +796,7 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
     const int64_t cn = std::min<int64_t>(chunk, n - c0);
     NFB_CUDA(cudaStreamSynchronize(s.stream));  // the slot's previous chunk has fully landed
     if ((rc = ensure(&s.d_in, &s.in_bytes, in_need, false)) != NFB_OK) return rc;
-    if ((rc = ensure(&s.d_out, &s.out_bytes, small ? out_need : dev_out_need, false)) != NFB_OK) return rc;
+    if ((rc = ensure(&s.d_out, &s.out_bytes, dev_out_need, false)) != NFB_OK) return rc;
 
     const void* d_rows[nfb::N_RAW];
     int64_t d_strides[nfb::N_RAW];
@@ -854,16 +858,19 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
         d_rows[r] = dst;
       }
     }
-    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype, s.d_out, chunk,
-                          small ? out_dtype : dev_out_dtype, s.stream);
+    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype, s.d_out, chunk, dev_out_dtype, s.stream);
     if (rc != NFB_OK) return rc;
     char* out_c = static_cast<char*>(out) + size_t(c0) * osz;
     if (small) {
       char* hs_out = static_cast<char*>(s.h_stage) + in_need;
-      NFB_CUDA(cudaMemcpyAsync(hs_out, s.d_out, out_need, cudaMemcpyDeviceToHost, s.stream));
+      NFB_CUDA(cudaMemcpyAsync(hs_out, s.d_out, dev_out_need, cudaMemcpyDeviceToHost, s.stream));
       NFB_CUDA(cudaStreamSynchronize(s.stream));
-      for (int r = 0; r < out_rows; ++r)
-        memcpy(out_c + size_t(r) * out_ld * osz, hs_out + size_t(r) * chunk * osz, size_t(cn) * osz);
+      if (small_widen) {
+        unstage_output(reinterpret_cast<const float*>(hs_out), chunk, out_c, out_ld, true, out_rows, cn);
+      } else {
+        for (int r = 0; r < out_rows; ++r)
+          memcpy(out_c + size_t(r) * out_ld * osz, hs_out + size_t(r) * chunk * osz, size_t(cn) * osz);
+      }
     } else if (stage_out) {
       if ((rc = ensure(&s.h_out, &s.h_out_bytes, dev_out_need, true)) != NFB_OK) return rc;
       NFB_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, dev_out_need, cudaMemcpyDeviceToHost, s.stream));
