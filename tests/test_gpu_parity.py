@@ -722,3 +722,48 @@ def test_column_group_kernels_match_tiled_kernels_bit_for_bit(tmp_path):
         assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), key
         if key.endswith("_scalars"):
             assert a.shape[0] == 6 and np.array_equal(a, dumps["groups"][key[: -len("_scalars")]][:6], equal_nan=True), key
+
+
+# ---------------------------------------------------------------------------------------------
+# User-supplied networks: any widths up to 512, uneven from layer to layer, 2..16 affine layers.
+# Exercises the zero padding of rows, the K trimming of the column-group kernels and every padded width.
+# ---------------------------------------------------------------------------------------------
+_ODD_ARCHITECTURES = {
+    "odd40": [25, 40, 40, 198],                 # -> 64-wide kernel, K trimmed to 48
+    "odd1layer": [25, 200, 198],                # one hidden layer -> 256-wide kernel
+    "odd_uneven": [25, 100, 72, 100, 198],      # uneven widths -> 128-wide kernel, K trimmed to 112
+    "odd300": [25, 300, 300, 300, 198],         # -> 512-wide kernel, K trimmed to 304
+    "odd_deep": [25] + [33] * 15 + [198],       # 16 affine layers (NFB_MAX_LAYERS)
+}
+
+
+def _random_network(dims, seed):
+    rng = np.random.default_rng(seed)
+    params = {}
+    for j in range(len(dims) - 1):
+        gain = 1.1 if j == len(dims) - 2 else 1.7
+        params[f"net.{2 * j}.weight"] = (rng.standard_normal((dims[j + 1], dims[j])) * gain / np.sqrt(dims[j])).astype(np.float32)
+        params[f"net.{2 * j}.bias"] = (rng.standard_normal(dims[j + 1]) * 0.1).astype(np.float32)
+    return params
+
+
+def test_user_supplied_architectures_match_oracle():
+    import torch
+    from neuralfoil_b200 import Evaluator
+    from oracle.neuralfoil_oracle import Oracle
+
+    extra = {name: _random_network(dims, 900 + i) for i, (name, dims) in enumerate(_ODD_ARCHITECTURES.items())}
+    ev, orc = Evaluator(device=0, extra_models=extra), Oracle(extra_models=extra)
+    try:
+        raw = synthetic.sample_training_distribution(9_001, seed=91)  # above every small-batch limit, ragged last tile
+        for name in extra:
+            want = orc.evaluate_raw(raw, name)
+            got = ev.evaluate_host(raw, name, out_dtype=np.float64)
+            parity.assert_parity(got, want, raw[19], check_distribution=False, label=name)
+            small = ev.evaluate_host(np.ascontiguousarray(raw[:, :37]), name, out_dtype=np.float64)  # the 4-queries-per-CTA kernel
+            np.testing.assert_array_equal(small, got[:, :37])
+            sc = ev.evaluate_device(torch.from_numpy(raw).cuda(), name, outputs="scalars", out_dtype=torch.float64)
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(sc.cpu().numpy(), got[:6])
+    finally:
+        ev.close()
