@@ -2,12 +2,13 @@
 // phases that do not use the FMA pipe (fp64 featurisation, SiLU, the MUFU-heavy decode, waiting for weights)
 // overlap the GEMM of other warps.
 //
-// A CTA still owns a tile of NC = 32768 / H columns in shared memory, but the tile is split into WN = NC / 64
-// independent COLUMN GROUPS (32 queries and their 32 twins, WM warps each).  A group does everything for its own
-// queries -- featurise, every hidden layer, the last layer, the decode, the stores -- and synchronises only with
-// itself (one named barrier per group).  Nothing in the tile loop is CTA-wide, so the groups drift apart: while one
-// group evaluates SiLUs or decodes, the others keep the FMA pipe busy (measured on B200, xlarge: 108.8 -> see
-// DESIGN.md section 6).
+// A CTA still owns a tile of NC = 32768 / H columns in shared memory, but the tile is split into WN independent
+// COLUMN GROUPS (QG queries and their QG twins, WM warps each; QG = 32, or 16 for H = 512).  A group does everything
+// for its own queries -- featurise, every hidden layer, the last layer, the decode, the stores -- and synchronises
+// only with itself (one named barrier per group).  Nothing in the tile loop is CTA-wide, so the groups drift apart:
+// while one group evaluates SiLUs or decodes, the others keep the FMA pipe busy.  Measured on B200 against the
+// CTA-synchronous kernel of nfb_ffma.cuh: xlarge 108.8 -> 143 M queries/s, xxsmall 478 -> 740, xxxlarge 10.09 -> 10.38
+// (profiles/r1_size_sweep_column_group_kernels.txt).
 //
 // The only thing the groups share is the weight stream: one ring of TMA bulk copies per CTA, which every warp
 // consumes in the same order.  The ring is deep, because its depth is what bounds the drift (see wait_slice).
