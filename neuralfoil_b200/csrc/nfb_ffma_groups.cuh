@@ -30,6 +30,10 @@
 #pragma once
 #include "nfb_ffma.cuh"
 
+#ifndef NFB_GRP_DECODE_ONCE
+#define NFB_GRP_DECODE_ONCE 0
+#endif
+
 namespace nfb {
 
 constexpr int M_LAST_SWEPT = 256;  // last layer's packed rows in the sweep layout (64 groups of four, 50 used)
@@ -259,8 +263,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
         release_slice(s);
       }
       const int g = sw * (H / 4) + wm * LM + lm;  // packed row groups g and g + H / 8
+#if NFB_GRP_DECODE_ONCE
+      // one copy of the decode code for both row groups (register selects instead of a second inlined instance):
+      // the desynchronised groups walk less SASS
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float2 a4[4][TN / 2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < TN / 2; ++jj) a4[i][jj] = half ? acc[4 + i][jj] : acc[i][jj];
+        decode_rows(a4, g + half * (H / 8));
+      }
+#else
       decode_rows(reinterpret_cast<const float2(&)[4][TN / 2]>(acc[0]), g);
       decode_rows(reinterpret_cast<const float2(&)[4][TN / 2]>(acc[4]), g + H / 8);
+#endif
     }
     if constexpr (NHALF > 0) {
       if (n_half) {  // packed rows HALF_ROW0 + h_row..+3: one row group per thread
