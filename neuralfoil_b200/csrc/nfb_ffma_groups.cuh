@@ -264,8 +264,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
       }
       const int g = sw * (H / 4) + wm * LM + lm;  // packed row groups g and g + H / 8
 #if NFB_GRP_DECODE_ONCE
-      // one copy of the decode code for both row groups (register selects instead of a second inlined instance):
-      // the desynchronised groups walk less SASS
+      // A/B only: one copy of the decode code for both row groups (register selects instead of a second inlined
+      // instance), 10 % less SASS for the desynchronised groups to walk.  Measured: no gain (64-wide -1 %, others within
+      // the +-2 % run-to-run spread).
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float2 a4[4][TN / 2];
