@@ -137,6 +137,16 @@ int nfb_eval_vjp_device(nfb_context* ctx, int model_id, int64_t n, const void* c
                         const int64_t* in_strides, int in_dtype, const void* cot, int64_t cot_ld,
                         void* values, int64_t values_ld, void* grad, int64_t grad_ld, int out_dtype, void* stream);
 
+/* Reverse-mode gradient of the six scalar outputs for large batches (nfb_grad.cuh): as nfb_eval_vjp_device with
+ * cotangents for rows 0..5 only (analysis_confidence, CL, CD, CM, Top_Xtr, Bot_Xtr) -- the gradient, with respect to the 23
+ * raw inputs, of any scalar objective of the aerodynamic scalars, at the cost of about 1.6 forward passes per query instead
+ * of the forward-mode kernel's 24.  What a reverse-mode trace of main.py:171-303 returns for such an objective.
+ *   cot, cot_ld     6 x cot_ld cotangents (type out_dtype);  values, values_ld: 6 x values_ld outputs (may be NULL);
+ *   grad, grad_ld   23 x grad_ld gradients (type out_dtype), rows in the order of in_rows. */
+int nfb_eval_scalar_grad_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                                const int64_t* in_strides, int in_dtype, const void* cot, int64_t cot_ld,
+                                void* values, int64_t values_ld, void* grad, int64_t grad_ld, int out_dtype, void* stream);
+
 /* Pinned host memory helpers for callers without their own allocator. */
 int nfb_host_alloc(void** out_ptr, int64_t bytes);
 int nfb_host_free(void* ptr);

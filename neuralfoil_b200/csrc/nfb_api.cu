@@ -18,6 +18,7 @@
 #include "nfb_tc.cuh"
 #include "nfb_tc2.cuh"
 #include "nfb_jac.cuh"
+#include "nfb_grad.cuh"
 
 namespace {
 
@@ -46,6 +47,7 @@ struct Model {
   int k_hidden = 0;  // widest hidden layer rounded up to 16
   int dims[NFB_MAX_LAYERS + 1] = {0};
   float* blob = nullptr;  // device
+  float* grad_blob = nullptr;  // nfb_grad.cuh: hidden layers, scalar rows, transposed hidden layers
   // tensor-core variants (256- / 512-wide models): fp16 weight slices of the one-term and the three-term kernels,
   // fp32 biases, per-layer 1 / scale
   __half* tc_w = nullptr;
@@ -147,6 +149,8 @@ struct nfb_context {
   bool have_distribution = false;
   Model models[NFB_MAX_MODELS];
   HostSlot slots[2];
+  void* grad_scratch = nullptr;  // nfb_eval_scalar_grad_device: SiLU slopes, one block per CTA
+  size_t grad_scratch_bytes = 0;
   void* jac_dev = nullptr;   // nfb_eval_jacobian_host: [inputs | values | jac] device block and its pinned host mirror
   void* jac_host = nullptr;
   size_t jac_dev_bytes = 0, jac_host_bytes = 0;
@@ -202,6 +206,28 @@ std::vector<float> pack_model(int L, const int* dims, const float* const* W, con
     }
   }
   return blob;
+}
+
+// Blob of the reverse-mode kernel (nfb_grad.cuh: GradBlob): the value blob's hidden layers, the six scalar rows of the last
+// layer as Wt[k][8] with their biases, and the hidden layers transposed, WT_l[m][k] = W_l[m][k] zero-padded to H x H.
+template <int H>
+std::vector<float> pack_grad_blob(int L, const int* dims, const float* const* W, const float* const* B,
+                                  const std::vector<float>& value_blob) {
+  using GB = nfb::GradBlob<H>;
+  std::vector<float> g(GB::total(L), 0.0f);
+  std::copy(value_blob.begin(), value_blob.begin() + nfb::blob_layer_offset<H>(L - 1), g.begin());
+  const int in_last = dims[L - 1];
+  for (int i = 0; i < 6; ++i) {
+    for (int k = 0; k < in_last; ++k) g[GB::scal_off(L) + size_t(k) * 8 + i] = W[L - 1][size_t(i) * in_last + k];
+    g[GB::scal_bias_off(L) + i] = B[L - 1][i];
+  }
+  for (int l = 0; l < L - 1; ++l) {
+    const int in = dims[l], out = dims[l + 1];
+    float* wt = g.data() + GB::wt_off(L, l);
+    for (int m = 0; m < out; ++m)
+      for (int k = 0; k < in; ++k) wt[size_t(m) * H + k] = W[l][size_t(m) * in + k];
+  }
+  return g;
 }
 
 // Tensor-core variant: fp16 weight slices (256 features x 32 k, K-major no-swizzle core matrices: element (r, kk)
@@ -342,6 +368,30 @@ int launch_ffma_groups(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t 
   const long long tiles = (p.n + Cfg::NQ - 1) / Cfg::NQ;
   const int grid = int(std::min<long long>(tiles, ctx->sm_count));
   nfb::nfb_ffma_groups_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
+int ensure(void** ptr, size_t* have, size_t need, bool pinned_host);
+
+template <class Cfg>
+int launch_scalar_grad(nfb_context* ctx, nfb::GradParams& gp, cudaStream_t stream) {
+  using GC = nfb::GradCfg<Cfg>;
+  static thread_local int configured_device = -1;
+  if (configured_device != ctx->device) {
+    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_scalar_grad_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(GC::SMEM_BYTES)));
+    configured_device = ctx->device;
+  }
+  const long long tiles = (gp.ev.n + Cfg::NQ - 1) / Cfg::NQ;
+  const int grid = int(std::min<long long>(tiles, ctx->sm_count));
+  const size_t need = size_t(grid) * (gp.ev.n_layers - 1) * Cfg::H * Cfg::NC * sizeof(float);
+  if (need > ctx->grad_scratch_bytes) NFB_CUDA(cudaStreamSynchronize(stream));  // nothing may still read the old block
+  int rc = ensure(&ctx->grad_scratch, &ctx->grad_scratch_bytes, need, false);
+  if (rc != NFB_OK) return rc;
+  gp.scratch = static_cast<float*>(ctx->grad_scratch);
+  nfb::nfb_scalar_grad_kernel<Cfg><<<grid, Cfg::THREADS, GC::SMEM_BYTES, stream>>>(gp);
   NFB_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return NFB_OK;
@@ -642,6 +692,7 @@ void nfb_destroy(nfb_context* ctx) {
   }
   if (ctx->tc_debug) cudaFree(ctx->tc_debug);
   if (ctx->jac_dev) cudaFree(ctx->jac_dev);
+  if (ctx->grad_scratch) cudaFree(ctx->grad_scratch);
   if (ctx->jac_host) cudaFreeHost(ctx->jac_host);
   delete ctx;
 }
@@ -701,6 +752,7 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
   if (m.blob) {
     NFB_CUDA(cudaDeviceSynchronize());
     NFB_CUDA(cudaFree(m.blob));
+    if (m.grad_blob) NFB_CUDA(cudaFree(m.grad_blob));
     if (m.tc_w) NFB_CUDA(cudaFree(m.tc_w));
     if (m.tc3_w) NFB_CUDA(cudaFree(m.tc3_w));
     if (m.tc2_w) NFB_CUDA(cudaFree(m.tc2_w));
@@ -711,6 +763,17 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
   }
   NFB_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
   NFB_CUDA(cudaMemcpy(m.blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    std::vector<float> gblob;
+    switch (h_pad) {
+      case 64: gblob = pack_grad_blob<64>(n_layers, dims, weights, biases, blob); break;
+      case 128: gblob = pack_grad_blob<128>(n_layers, dims, weights, biases, blob); break;
+      case 256: gblob = pack_grad_blob<256>(n_layers, dims, weights, biases, blob); break;
+      default: gblob = pack_grad_blob<512>(n_layers, dims, weights, biases, blob); break;
+    }
+    NFB_CUDA(cudaMalloc(&m.grad_blob, gblob.size() * sizeof(float)));
+    NFB_CUDA(cudaMemcpy(m.grad_blob, gblob.data(), gblob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if ((h_pad == 512 || h_pad == 256) && n_layers <= nfb::tc::MAX_TC_LAYERS) {
     const TcPack tcp = h_pad == 512 ? pack_model_tc<nfb::tc::TcCfg<512, 1>>(n_layers, dims, weights, biases)
                                     : pack_model_tc<nfb::tc::TcCfg<256, 1>>(n_layers, dims, weights, biases);
@@ -942,6 +1005,46 @@ int nfb_eval_vjp_device(nfb_context* ctx, int model_id, int64_t n, const void* c
   if (!cot) return fail(NFB_ERR_INVALID_ARGUMENT, "cot is NULL");
   return jacobian_device_impl(ctx, model_id, n, in_rows, in_strides, in_dtype, values, values_ld, nullptr, cot, cot_ld, grad,
                               grad_ld, out_dtype, stream);
+}
+
+int nfb_eval_scalar_grad_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows, const int64_t* in_strides,
+                                int in_dtype, const void* cot, int64_t cot_ld, void* values, int64_t values_ld, void* grad,
+                                int64_t grad_ld, int out_dtype, void* stream) {
+  static char dummy_out;
+  int rc = check_eval_args(ctx, model_id, NFB_VARIANT_FP32_FFMA, n, in_rows, in_strides, in_dtype, values ? values : &dummy_out,
+                           values ? values_ld : n, out_dtype);
+  if (rc != NFB_OK || n == 0) return rc;
+  if (!cot || !grad || cot_ld < n || grad_ld < n)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "scalar gradient: cot or grad is NULL, or a leading dimension is smaller than n");
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  const Model& m = ctx->models[model_id];
+  nfb::GradParams gp;
+  for (int i = 0; i < nfb::N_RAW; ++i) {
+    gp.ev.in[i] = in_rows[i];
+    gp.ev.in_stride[i] = in_strides[i];
+  }
+  gp.ev.out = values;
+  gp.ev.out_ld = values_ld;
+  gp.ev.n = n;
+  gp.ev.blob = m.grad_blob;
+  gp.ev.n_layers = m.n_layers;
+  gp.ev.k_hidden = m.k_hidden;
+  gp.ev.in_f64 = (in_dtype == NFB_F64);
+  gp.ev.out_f64 = (out_dtype == NFB_F64);
+  gp.ev.scalars_only = 1;
+  gp.cot = cot;
+  gp.grad = grad;
+  gp.cot_ld = cot_ld;
+  gp.grad_ld = grad_ld;
+  gp.scratch = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (m.h_pad) {
+    case 64: return launch_scalar_grad<Grp64>(ctx, gp, st);
+    case 128: return launch_scalar_grad<Grp128>(ctx, gp, st);
+    case 256: return launch_scalar_grad<Grp256>(ctx, gp, st);
+    case 512: return launch_scalar_grad<Grp512>(ctx, gp, st);
+  }
+  return fail(NFB_ERR_UNSUPPORTED_MODEL, "no kernel for padded width %d", m.h_pad);
 }
 
 int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,

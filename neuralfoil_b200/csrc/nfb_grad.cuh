@@ -1,0 +1,361 @@
+// Reverse-mode gradient of the SCALAR outputs for large batches (the "fused reverse pass").
+//
+//   grad[t][q] = sum_{i < 6} cot[i][q] * d out_i[q] / d raw_t[q],      out = (analysis_confidence, CL, CD, CM, Top_Xtr, Bot_Xtr)
+//
+// i.e. the gradient, with respect to the 23 raw inputs, of any scalar objective of the six aerodynamic scalars -- what a
+// design optimiser asks for (lift-to-drag, drag at fixed lift, ...) -- for every query of a batch, in about 1.6 forward
+// passes.  The forward-mode kernel (nfb_jac.cuh) pays 24 passes per query for the same numbers.
+//
+// Same column-group schedule, weight ring and thread tile as nfb_ffma_groups.cuh.  Per group and tile:
+//   forward   featurise; hidden layers as in the value kernel, each epilogue also storing SiLU'(z) of its element in a
+//             per-CTA scratch block in global memory ([L-1][H][NC] fp32, L2-resident: 5 KB per query and layer stack);
+//   turn      the scalar pass: the six latents of the query and of its twin (one query per lane), the six outputs
+//             (stored if wanted), their cotangents pulled back through decode, squash and the un-flip average
+//             [main.py:274-303], then d a_{L-2} = W_scal^T d latent, already multiplied by the stored slope, written
+//             over the (no longer needed) activations;
+//   backward  for l = L-2 .. 0: d a_{l-1} = W_l^T d z_l as the SAME register-blocked FFMA2 GEMM on a transposed copy of
+//             the weights (slices of KC output units x H inputs), epilogue "times the stored slope" instead of SiLU;
+//   finish    one thread per query: d x of the query + the twin's d x pulled back through the flip (a signed permutation),
+//             the Mahalanobis term of the confidence logit (fp64, as in the forward pass), the chain rule of the
+//             featurisation [main.py:171-184], 23 coalesced stores.
+// The boundary-layer rows are not differentiated here (192 more cotangent rows, a transposed sweep per sweep): an
+// objective that needs them uses nfb_eval_vjp_device.
+#pragma once
+#include "nfb_ffma_groups.cuh"
+#include "nfb_jac.cuh"  // maha_gradient
+
+namespace nfb {
+
+struct GradParams {
+  EvalParams ev;      // inputs, n, n_layers, k_hidden; ev.blob = the GRADIENT blob below; ev.out = 6 x out_ld values or NULL
+  const void* cot;    // 6 x cot_ld cotangents, type of the outputs (ev.out_f64)
+  void* grad;         // 23 x grad_ld
+  long long cot_ld, grad_ld;
+  float* scratch;     // gridDim.x blocks of (L-1) * H * NC floats
+};
+
+// Gradient blob (floats): the hidden layers of the value blob (layers 0 .. L-2 with their biases), then the scalar rows
+// of the last layer Wt[k][8] and their 8 biases, then the transposed layers WT_l[m][k] = W_l[m][k], l = 0 .. L-2, H x H each.
+template <int H>
+struct GradBlob {
+  __host__ __device__ static constexpr size_t scal_off(int L) { return blob_layer_offset<H>(L - 1); }
+  __host__ __device__ static constexpr size_t scal_bias_off(int L) { return scal_off(L) + size_t(H) * 8; }
+  __host__ __device__ static constexpr size_t wt_off(int L, int l) { return scal_bias_off(L) + 8 + size_t(l) * H * H; }
+  __host__ __device__ static constexpr size_t total(int L) { return wt_off(L, L - 1); }
+};
+
+template <class Cfg>
+struct GradCfg {
+  static constexpr int MAX_SLICES = K0_PAD / Cfg::KC + 2 * (NFB_MAX_LAYERS_K - 1) * (Cfg::H / Cfg::KC) + 1;
+  static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t(Cfg::H) * Cfg::NC + size_t(Cfg::STAGES) * Cfg::SLOT_FLOATS +
+                                                        Cfg::NC + Cfg::NQ) + 16 * Cfg::STAGES + 8 * size_t(MAX_SLICES);
+  static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const GradParams gp) {
+  constexpr int H = Cfg::H, NC = Cfg::NC, NQ = Cfg::NQ, KC = Cfg::KC, STAGES = Cfg::STAGES, TN = Cfg::TN;
+  constexpr int WM = Cfg::WM, SLOT = Cfg::SLOT_FLOATS, LM = Cfg::LM, LN = Cfg::LN, QG = Cfg::QG;
+  constexpr int WARPS = Cfg::WARPS, QT = TN / 2;
+  const EvalParams& p = gp.ev;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* const act = reinterpret_cast<float*>(smem_raw);  // [H][NC]: activations, then their cotangents
+  float* const ring = act + H * NC;                        // [STAGES][SLOT]
+  float* const maha = ring + STAGES * SLOT;                // [NC]: d2 / 50 of each column, later the cotangent of it
+  float* const re_s = maha + NC;                           // [NQ] (unused by the scalars; featurise_column writes it)
+  const uint32_t bar_full = smem_u32(re_s + NQ);
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  uint2* const table = reinterpret_cast<uint2*>(re_s + NQ + 4 * STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = p.n_layers;
+  const long long n_tiles = (p.n + NQ - 1) / NQ;
+  using GB = GradBlob<H>;
+  const int nkh = (p.k_hidden + KC - 1) / KC;
+  const uint32_t slices_per_tile = K0_PAD / KC + (L - 2) * nkh + 1 + (L - 1) * nkh;
+  const uint32_t my_tiles = uint32_t((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const uint32_t total_slices = my_tiles * slices_per_tile;
+  float* const slopes = gp.scratch + size_t(blockIdx.x) * (L - 1) * H * NC;  // [L-1][H][NC]
+
+  if (tid == 0) {
+    uint32_t j = 0;
+    for (int c = 0; c < K0_PAD / KC; ++c) table[j++] = make_uint2(c * KC * H, KC * H * 4);
+    for (int l = 1; l < L - 1; ++l)
+      for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(blob_layer_offset<H>(l)) + c * KC * H, KC * H * 4);
+    table[j++] = make_uint2(uint32_t(GB::scal_off(L)), uint32_t(p.k_hidden) * 8 * 4);
+    for (int l = L - 2; l >= 0; --l)
+      for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(GB::wt_off(L, l)) + c * KC * H, KC * H * 4);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int lm = lane / LN, ln = lane % LN;
+  const int wm = warp % WM, wn = warp / WM;
+  const int h_row = (wm * LM + lm) * 4;
+  const int h_col = wn * QG + ln * QT;
+  const int gtid = tid - wn * Cfg::GROUP_THREADS;
+  auto group_bar = [&]() { named_bar_sync(1 + wn, Cfg::GROUP_THREADS); };
+
+  constexpr uint32_t LEAD = Cfg::LEAD;  // see nfb_ffma_groups.cuh
+  uint32_t it = 0;
+  auto issue = [&](uint32_t j) {
+    const uint2 e = table[j % slices_per_tile];
+    const uint32_t s = j % STAGES, ph = (j / STAGES) & 1;
+    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+    mbar_arrive_expect_tx(bar_full + 8 * s, e.y);
+    bulk_copy_g2s(smem_u32(ring + s * SLOT), p.blob + e.x, e.y, bar_full + 8 * s);
+  };
+  if (tid == 0)
+    for (uint32_t j = 0; j < LEAD && j < total_slices; ++j) issue(j);
+  auto wait_slice = [&](uint32_t& s_out) {
+    const uint32_t j = it + LEAD;
+    if (lane == 0 && (j & (WARPS - 1)) == uint32_t(warp) && j < total_slices) issue(j);
+    s_out = it % STAGES;
+    mbar_wait(bar_full + 8 * s_out, (it / STAGES) & 1);
+  };
+  auto release_slice = [&](uint32_t s) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    ++it;
+  };
+  // this thread's tile element (row i of 8, float4 v of its query columns / twin columns) in a [.][H][NC] block
+  auto tile_offset = [&](int i, int v, bool twin) {
+    const int row = (i < 4) ? h_row + i : H / 2 + h_row + (i - 4);
+    return row * NC + (twin ? NC / 2 : 0) + h_col + 4 * v;
+  };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long tile_q0 = tile * NQ;
+
+    group_bar();
+    for (int t = gtid; t < 2 * QG; t += Cfg::GROUP_THREADS) {
+      const bool twin = t >= QG;
+      const int c = wn * QG + (t % QG);
+      const long long q = tile_q0 + c;
+      featurise_column<NC>(p, q, q < p.n, twin, twin ? NQ + c : c, act, maha, re_s);
+    }
+    group_bar();
+
+    // ---------------- forward: hidden layers, SiLU and its slope ----------------
+    for (int l = 0; l < L - 1; ++l) {
+      const float* bias = p.blob + blob_layer_offset<H>(l) + size_t(l == 0 ? K0_PAD : H) * H;
+      float2 acc[8][TN / 2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float b_lo = __ldg(bias + h_row + i), b_hi = __ldg(bias + H / 2 + h_row + i);
+#pragma unroll
+        for (int jj = 0; jj < TN / 2; ++jj) {
+          acc[i][jj] = make_float2(b_lo, b_lo);
+          acc[4 + i][jj] = make_float2(b_hi, b_hi);
+        }
+      }
+      const int nk = (l == 0) ? K0_PAD / KC : nkh;
+      for (int c = 0; c < nk; ++c) {
+        uint32_t s;
+        wait_slice(s);
+        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+        release_slice(s);
+      }
+      group_bar();
+      float* const sl = slopes + size_t(l) * H * NC;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int v = 0; v < TN / 8; ++v) {
+#pragma unroll
+          for (int tw = 0; tw < 2; ++tw) {
+            const float2 a0 = acc[i][tw * (TN / 4) + 2 * v], a1 = acc[i][tw * (TN / 4) + 2 * v + 1];
+            const float h[4] = {a0.x, a0.y, a1.x, a1.y};
+            float y[4], d[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {  // silu(h) = h r, silu'(h) = r (1 + h (1 - r)), r = 1 / (1 + exp(-h))
+              float ex, r;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(h[e] * -1.4426950408889634f));
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex));
+              y[e] = h[e] * r;
+              d[e] = r * fmaf(h[e], 1.0f - r, 1.0f);
+            }
+            const int off = tile_offset(i, v, tw == 1);
+            *reinterpret_cast<float4*>(act + off) = make_float4(y[0], y[1], y[2], y[3]);
+            __stcg(reinterpret_cast<float4*>(sl + off), make_float4(d[0], d[1], d[2], d[3]));
+          }
+        }
+      }
+      group_bar();  // also orders the slope stores before the reads of other threads of the group
+    }
+
+    // ---------------- turn: scalar latents, outputs, their cotangents, d a_{L-2} ----------------
+    {
+      uint32_t s;
+      wait_slice(s);
+      if (wm == 0 && lane < QG) {
+        const int c = wn * QG + lane;
+        const long long q = tile_q0 + c;
+        const float* const bs = p.blob + GB::scal_bias_off(L);
+        float yq[6], yt[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) yq[i] = yt[i] = __ldg(bs + i);
+        const float* w = ring + s * SLOT;
+        float* const aq = act + c;
+        const int kh = p.k_hidden;
+#pragma unroll 4
+        for (int k = 0; k < kh; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * k);
+          const float2 w1 = *reinterpret_cast<const float2*>(w + 8 * k + 4);
+          const float xq = aq[k * NC], xt = aq[k * NC + NQ];
+          yq[0] = fmaf(w0.x, xq, yq[0]); yt[0] = fmaf(w0.x, xt, yt[0]);
+          yq[1] = fmaf(w0.y, xq, yq[1]); yt[1] = fmaf(w0.y, xt, yt[1]);
+          yq[2] = fmaf(w0.z, xq, yq[2]); yt[2] = fmaf(w0.z, xt, yt[2]);
+          yq[3] = fmaf(w0.w, xq, yq[3]); yt[3] = fmaf(w0.w, xt, yt[3]);
+          yq[4] = fmaf(w1.x, xq, yq[4]); yt[4] = fmaf(w1.x, xt, yt[4]);
+          yq[5] = fmaf(w1.y, xq, yq[5]); yt[5] = fmaf(w1.y, xt, yt[5]);
+        }
+        // outputs: the expressions of decode_and_store's groups 48 and 49 [main.py:244-246, 292-303]
+        const float z0 = 0.5f * ((yq[0] - maha[c]) + (yt[0] - maha[NQ + c]));
+        const float z1 = 0.5f * (yq[1] - yt[1]);
+        const float z2 = 0.5f * (yq[2] + yt[2]);
+        const float z3 = 0.5f * (yq[3] - yt[3]);
+        const float z4 = 0.5f * (yq[4] + yt[5]), z5 = 0.5f * (yq[5] + yt[4]);
+        const float conf = 1.0f / (1.0f + expf(-z0)), cd = expf((z2 - 2.0f) * 2.0f);
+        const bool valid = q < p.n;
+        float ct[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (valid) {
+          if (p.out_f64) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ct[i] = float(__ldg(static_cast<const double*>(gp.cot) + i * gp.cot_ld + q));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ct[i] = __ldg(static_cast<const float*>(gp.cot) + i * gp.cot_ld + q);
+          }
+          if (p.out) {
+            const float o[6] = {conf, 0.5f * z1, cd, z3 / 20.0f, clip01_keep_nan(z4), clip01_keep_nan(z5)};
+            if (p.out_f64) {
+#pragma unroll
+              for (int i = 0; i < 6; ++i) static_cast<double*>(p.out)[i * p.out_ld + q] = double(o[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 6; ++i) static_cast<float*>(p.out)[i * p.out_ld + q] = o[i];
+            }
+          }
+        }
+        // cotangents of z0..z5, then of the latents of the query (dq) and of its twin (dt)
+        const float g0 = ct[0] * conf * (1.0f - conf);
+        const float g1 = ct[1] * 0.5f;
+        const float g2 = ct[2] * 2.0f * cd;
+        const float g3 = ct[3] / 20.0f;
+        const float g4 = (z4 > 0.0f && z4 < 1.0f) ? ct[4] : 0.0f;
+        const float g5 = (z5 > 0.0f && z5 < 1.0f) ? ct[5] : 0.0f;
+        const float dq[6] = {0.5f * g0, 0.5f * g1, 0.5f * g2, 0.5f * g3, 0.5f * g4, 0.5f * g5};
+        const float dt[6] = {0.5f * g0, -0.5f * g1, 0.5f * g2, -0.5f * g3, 0.5f * g5, 0.5f * g4};
+        maha[c] = -0.5f * g0;       // cotangent of the query's d2 / 50
+        maha[NQ + c] = -0.5f * g0;  // ... and of the twin's
+        const float* const sl = slopes + size_t(L - 2) * H * NC + c;
+#pragma unroll 4
+        for (int k = 0; k < kh; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * k);
+          const float2 w1 = *reinterpret_cast<const float2*>(w + 8 * k + 4);
+          const float sq = w0.x * dq[0] + w0.y * dq[1] + w0.z * dq[2] + w0.w * dq[3] + w1.x * dq[4] + w1.y * dq[5];
+          const float st = w0.x * dt[0] + w0.y * dt[1] + w0.z * dt[2] + w0.w * dt[3] + w1.x * dt[4] + w1.y * dt[5];
+          aq[k * NC] = sq * __ldcg(sl + k * NC);
+          aq[k * NC + NQ] = st * __ldcg(sl + k * NC + NQ);
+        }
+      }
+      release_slice(s);
+    }
+    group_bar();
+
+    // ---------------- backward: d a_{l-1} = W_l^T d z_l ----------------
+    for (int l = L - 2; l >= 0; --l) {
+      float2 acc[8][TN / 2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(0.0f, 0.0f);
+      for (int c = 0; c < nkh; ++c) {
+        uint32_t s;
+        wait_slice(s);
+        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+        release_slice(s);
+      }
+      group_bar();  // the group has finished reading d z_l
+      const float* const sl = slopes + size_t(l > 0 ? l - 1 : 0) * H * NC;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int v = 0; v < TN / 8; ++v) {
+#pragma unroll
+          for (int tw = 0; tw < 2; ++tw) {
+            const float2 a0 = acc[i][tw * (TN / 4) + 2 * v], a1 = acc[i][tw * (TN / 4) + 2 * v + 1];
+            const int off = tile_offset(i, v, tw == 1);
+            float4 d = make_float4(a0.x, a0.y, a1.x, a1.y);
+            if (l > 0) {  // d z_{l-1} = d a_{l-1} * SiLU'(z_{l-1}); this thread stored those slopes itself
+              const float4 m = __ldcg(reinterpret_cast<const float4*>(sl + off));
+              d.x *= m.x; d.y *= m.y; d.z *= m.z; d.w *= m.w;
+            }
+            *reinterpret_cast<float4*>(act + off) = d;
+          }
+        }
+      }
+      group_bar();
+    }
+
+    // ---------------- finish: rows 0..24 of the tile now hold d f / d x of the query and of its twin ----------------
+    for (int t = gtid; t < QG; t += Cfg::GROUP_THREADS) {
+      const int c = wn * QG + t;
+      const long long q = tile_q0 + c;
+      if (q >= p.n) continue;
+      double x[N_IN], xt[N_IN], g[N_IN], gt[N_IN];
+      float m_unused, re_unused;
+      featurise_query(p, q, true, false, x, m_unused, re_unused);
+#pragma unroll
+      for (int i = 0; i < N_IN; ++i) xt[i] = x[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { xt[i] = -x[8 + i]; xt[8 + i] = -x[i]; }  // main.py:253-265
+      xt[16] = -x[16]; xt[18] = -x[18]; xt[23] = x[24]; xt[24] = x[23];
+      maha_gradient(x, g);
+      maha_gradient(xt, gt);
+      const double mq = double(maha[c]) / (2.0 * N_IN), mt = double(maha[NQ + c]) / (2.0 * N_IN);
+      double G[N_IN], T[N_IN];
+#pragma unroll
+      for (int k = 0; k < N_IN; ++k) {
+        G[k] = double(act[k * NC + c]) + mq * g[k];
+        T[k] = double(act[k * NC + NQ + c]) + mt * gt[k];
+      }
+      // pull the twin's gradient back through the flip (its transpose: the same signed permutation)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { G[8 + i] -= T[i]; G[i] -= T[8 + i]; }
+      G[16] -= T[16]; G[17] += T[17]; G[18] -= T[18]; G[19] += T[19]; G[20] += T[20]; G[21] += T[21]; G[22] += T[22];
+      G[23] += T[24]; G[24] += T[23];
+      // featurisation [main.py:171-184]
+      constexpr double kdeg = 3.141592653589793238462643383279502884 / 180.0;
+      const double alpha = p.in_f64 ? __ldg(static_cast<const double*>(p.in[18]) + q * p.in_stride[18])
+                                    : double(__ldg(static_cast<const float*>(p.in[18]) + q * p.in_stride[18]));
+      const double rey = p.in_f64 ? __ldg(static_cast<const double*>(p.in[19]) + q * p.in_stride[19])
+                                  : double(__ldg(static_cast<const float*>(p.in[19]) + q * p.in_stride[19]));
+      const double a = alpha * kdeg;
+      double out[N_RAW];
+#pragma unroll
+      for (int i = 0; i < 17; ++i) out[i] = G[i];
+      out[17] = 50.0 * G[17];
+      out[18] = kdeg * (2.0 * cos(2.0 * a) * G[18] - sin(a) * G[19] + 2.0 * cos(a) * sin(a) * G[20]);
+      out[19] = G[21] / (3.5 * rey);
+      out[20] = G[22] / 4.5;
+      out[21] = G[23];
+      out[22] = G[24];
+      if (p.out_f64) {
+#pragma unroll
+        for (int i = 0; i < N_RAW; ++i) static_cast<double*>(gp.grad)[i * gp.grad_ld + q] = out[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < N_RAW; ++i) static_cast<float*>(gp.grad)[i * gp.grad_ld + q] = float(out[i]);
+      }
+    }
+  }
+}
+
+}  // namespace nfb

@@ -315,6 +315,52 @@ class Evaluator:
         )
         return values[:, :n], grad[:, :n]
 
+    def evaluate_scalar_grad_device(self, raw, cotangent, model_size: str = "xlarge", with_values: bool = True):
+        """
+        Reverse-mode gradient of the six scalar outputs for large batches: raw (23, N) and cotangent (6, N) CUDA tensors
+        (rows: analysis_confidence, CL, CD, CM, Top_Xtr, Bot_Xtr; contiguous rows) -> (values (6, N) or None, grad (23, N)),
+        grad[t] = sum_{i<6} cotangent[i] * d output_i / d raw_t.  About 1.6 forward passes per query (the forward-mode
+        `evaluate_vjp_device`, which also takes cotangents of the boundary-layer rows, costs 24).  Enqueues on torch's
+        current stream.
+        """
+        import torch
+
+        for name, t, rows in (("raw", raw, _lib.N_RAW_ROWS), ("cotangent", cotangent, _lib.N_SCALAR_ROWS)):
+            if not isinstance(t, torch.Tensor) or t.dim() != 2 or t.shape[0] != rows or not t.is_cuda or t.stride(1) != 1:
+                raise ValueError(f"{name} must be a ({rows}, N) CUDA tensor with contiguous rows")
+            if t.dtype not in (torch.float32, torch.float64):
+                raise ValueError(f"{name} must be float32 or float64")
+        n = int(raw.shape[1])
+        if cotangent.shape[1] != n:
+            raise ValueError("raw and cotangent must have the same number of columns")
+        ld = (n + 3) & ~3
+        dev = f"cuda:{self.device}"
+        values = torch.empty((_lib.N_SCALAR_ROWS, ld), dtype=cotangent.dtype, device=dev) if with_values else None
+        grad = torch.empty((_lib.N_RAW_ROWS, ld), dtype=cotangent.dtype, device=dev)
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].data_ptr() for i in range(_lib.N_RAW_ROWS)])
+        _lib.check(
+            self._lib.nfb_eval_scalar_grad_device(
+                self._ctx, self._model_id(model_size), n, ptrs, _ONES_23,
+                _lib.F64 if raw.dtype == torch.float64 else _lib.F32,
+                C.c_void_p(cotangent.data_ptr()), int(cotangent.stride(0)),
+                C.c_void_p(values.data_ptr()) if with_values else None, ld, C.c_void_p(grad.data_ptr()), ld,
+                _lib.F64 if cotangent.dtype == torch.float64 else _lib.F32,
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream),
+            )
+        )
+        return (values[:, :n] if with_values else None), grad[:, :n]
+
+    def evaluate_scalar_grad_host(self, raw: np.ndarray, cotangent: np.ndarray, model_size: str = "xlarge"):
+        """NumPy front door of `evaluate_scalar_grad_device` (moves the arrays with torch): -> (values (6, N), grad (23, N)) float64."""
+        import torch
+
+        dev = f"cuda:{self.device}"
+        r = torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float64)).to(dev)
+        c = torch.from_numpy(np.ascontiguousarray(cotangent, dtype=np.float64)).to(dev)
+        values, grad = self.evaluate_scalar_grad_device(r, c, model_size)
+        torch.cuda.synchronize(self.device)
+        return values.cpu().numpy(), grad.cpu().numpy()
+
     def evaluate_vjp_host(self, raw: np.ndarray, cotangent: np.ndarray, model_size: str = "xlarge"):
         """NumPy front door of `evaluate_vjp_device` (moves the arrays with torch): -> (values (198, N), grad (23, N)) float64."""
         import torch

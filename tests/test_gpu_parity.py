@@ -767,3 +767,57 @@ def test_user_supplied_architectures_match_oracle():
             np.testing.assert_array_equal(sc.cpu().numpy(), got[:6])
     finally:
         ev.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Reverse-mode gradient of the six scalar outputs (nfb_grad.cuh): against the oracle's analytic float64 Jacobian, against
+# the forward-mode VJP kernel, values against the value kernel; ragged tiles, float32 / float64, broadcast-free device API.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", list(MODEL_SIZES) + ["xxxlarge"])
+def test_scalar_gradient_matches_oracle_and_forward_mode(evaluator, oracle, size):
+    n = 1_501 if size != "xxxlarge" else 403
+    raw = synthetic.sample_training_distribution(n, seed=58)
+    rng = np.random.default_rng(6)
+    cot = rng.normal(size=(6, n)) * np.array([1.0, 1.0, 50.0, 1.0, 1.0, 1.0])[:, None]
+    values, grad = evaluator.evaluate_scalar_grad_host(raw, cot, size)
+    assert values.shape == (6, n) and grad.shape == (23, n) and np.isfinite(grad).all()
+    np.testing.assert_array_equal(values, evaluator.evaluate_host(raw, size, out_dtype=np.float64, outputs="scalars"))
+    scale = parity.JAC_INPUT_SCALE.copy()[:, None] * np.ones((1, n))
+    scale[19] = raw[19]
+    want_v, want_j = oracle.jacobian_raw(raw, size)
+    want = np.einsum("rtq,rq->tq", want_j[:6], cot)
+    err = np.abs(grad - want) * scale
+    ref = np.abs(want) * scale + np.einsum("rq,rq->q", np.abs(cot), np.abs(want_v[:6]))[None, :] * 1e-1
+    assert (err <= 5e-3 * ref + 1e-6).mean() > 0.999 and np.median(err / np.maximum(ref, 1e-30)) < 1e-5
+    cot198 = np.zeros((198, n))
+    cot198[:6] = cot
+    _, forward_mode = evaluator.evaluate_vjp_host(raw, cot198, size)
+    np.testing.assert_allclose(grad * scale, forward_mode * scale, rtol=2e-3, atol=2e-4)
+
+
+def test_scalar_gradient_float32_device_api_and_symmetry(evaluator):
+    import torch
+
+    n = 70_003  # many tiles per CTA on every width, ragged last tile
+    raw = torch.from_numpy(synthetic.sample_training_distribution(n, seed=59).astype(np.float32)).cuda()
+    cot = torch.zeros((6, n), dtype=torch.float32, device="cuda")
+    cot[1] = 1.0  # f = CL
+    for size in ("xxsmall", "xlarge", "xxlarge"):
+        values, grad = evaluator.evaluate_scalar_grad_device(raw, cot, size)
+        none, grad2 = evaluator.evaluate_scalar_grad_device(raw, cot, size, with_values=False)
+        torch.cuda.synchronize()
+        assert none is None and torch.equal(grad, grad2) and grad.dtype == torch.float32
+        assert torch.equal(values, evaluator.evaluate_device(raw, size, outputs="scalars"))
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(3)).cuda()
+        _, grad_p = evaluator.evaluate_scalar_grad_device(raw[:, perm].contiguous(), cot, size, with_values=False)
+        torch.cuda.synchronize()
+        assert torch.equal(grad_p, grad[:, perm]), size  # position independence
+    # a symmetric airfoil at alpha = 0: CL is odd in alpha, so d CL / d Re = d CL / d n_crit = 0 exactly, and
+    # d CL / d upper_i = d CL / d lower_i (the twin's contribution mirrors the query's)
+    w = np.array([0.15, 0.20, 0.15, 0.20, 0.15, 0.20, 0.15, 0.15])
+    sym = np.zeros((23, 8), dtype=np.float64)
+    sym[0:8], sym[8:16], sym[17], sym[19], sym[20], sym[21], sym[22] = w[:, None], -w[:, None], 0.002, 1e6, 9.0, 1.0, 1.0
+    c = np.zeros((6, 8)); c[1] = 1.0
+    _, g = evaluator.evaluate_scalar_grad_host(sym, c, "large")
+    assert np.all(g[19] == 0.0) and np.all(g[20] == 0.0) and np.all(g[17] == 0.0)
+    np.testing.assert_array_equal(g[0:8], g[8:16])
