@@ -371,6 +371,26 @@ def main():
                           "kernel": "nfb_jac_kernel<H> (forward mode, fp32 FFMA: the query, its twin and 23 tangents each)",
                           "achieved_tflops": jf, "note": "24 x the value path's FLOP per query; one CTA per query"}
 
+    # ---- the reverse-mode kernel: gradients of an objective of the six scalars, device-resident ----
+    scalar_grad_extra = None
+    if variant == "fp32" and not args.no_tensor_extra:
+        ng = min(n, 2_000_000)
+        rg = raw_dev[:, :ng].contiguous()
+        cot = torch.randn((6, ng), dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            ev.evaluate_scalar_grad_device(rg, cot, size)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(3):
+            ev.evaluate_scalar_grad_device(rg, cot, size)
+        t1e.record()
+        barrier()
+        t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / 3
+        scalar_grad_extra = {"value": world * ng / (t_ms * 1e-3), "unit": "gradients/s", "queries_per_launch": ng, "ms_per_launch": t_ms,
+                             "kernel": "nfb_scalar_grad_kernel (fused forward + reverse pass, fp32 FFMA2; six scalar values + d objective / d 23 raw inputs per query)"}
+        del rg, cot
+
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -437,7 +457,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, weights_note),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "tensor_variant": tensor_extra,
-            "tensor_fp32_variant": tensor_fp32_extra, "jacobian": jacobian_extra,
+            "tensor_fp32_variant": tensor_fp32_extra, "jacobian": jacobian_extra, "scalar_gradient": scalar_grad_extra,
             "checksum_first_1000": checksum,
         }
         print(json.dumps(line), flush=True)

@@ -209,7 +209,8 @@ std::vector<float> pack_model(int L, const int* dims, const float* const* W, con
 }
 
 // Blob of the reverse-mode kernel (nfb_grad.cuh: GradBlob): the value blob's hidden layers, the six scalar rows of the last
-// layer as Wt[k][8] with their biases, and the hidden layers transposed, WT_l[m][k] = W_l[m][k] zero-padded to H x H.
+// layer as Wt[k][8] with their biases, and the hidden layers transposed, WT_l[m][k] = W_l[m][k] zero-padded to H x 32 (l = 0)
+// or H x H.
 template <int H>
 std::vector<float> pack_grad_blob(int L, const int* dims, const float* const* W, const float* const* B,
                                   const std::vector<float>& value_blob) {
@@ -223,9 +224,10 @@ std::vector<float> pack_grad_blob(int L, const int* dims, const float* const* W,
   }
   for (int l = 0; l < L - 1; ++l) {
     const int in = dims[l], out = dims[l + 1];
-    float* wt = g.data() + GB::wt_off(L, l);
+    float* wt = g.data() + (l == 0 ? GB::wt0_off(L) : GB::wt_off(L, l));
+    const size_t ld = (l == 0) ? nfb::K0_PAD : H;
     for (int m = 0; m < out; ++m)
-      for (int k = 0; k < in; ++k) wt[size_t(m) * H + k] = W[l][size_t(m) * in + k];
+      for (int k = 0; k < in; ++k) wt[size_t(m) * ld + k] = W[l][size_t(m) * in + k];
   }
   return g;
 }

@@ -35,14 +35,43 @@ struct GradParams {
 };
 
 // Gradient blob (floats): the hidden layers of the value blob (layers 0 .. L-2 with their biases), then the scalar rows
-// of the last layer Wt[k][8] and their 8 biases, then the transposed layers WT_l[m][k] = W_l[m][k], l = 0 .. L-2, H x H each.
+// of the last layer Wt[k][8] and their 8 biases, then the transposed layers WT_l[m][k] = W_l[m][k]: WT_0 as H x 32, WT_1 .. WT_{L-2}
+// as H x H.
 template <int H>
 struct GradBlob {
   __host__ __device__ static constexpr size_t scal_off(int L) { return blob_layer_offset<H>(L - 1); }
   __host__ __device__ static constexpr size_t scal_bias_off(int L) { return scal_off(L) + size_t(H) * 8; }
-  __host__ __device__ static constexpr size_t wt_off(int L, int l) { return scal_bias_off(L) + 8 + size_t(l) * H * H; }
+  __host__ __device__ static constexpr size_t wt0_off(int L) { return scal_bias_off(L) + 8; }             // WT_0[m][32]
+  __host__ __device__ static constexpr size_t wt_off(int L, int l) {                                      // WT_l[m][H], l >= 1
+    return wt0_off(L) + size_t(H) * K0_PAD + size_t(l - 1) * H * H;
+  }
   __host__ __device__ static constexpr size_t total(int L) { return wt_off(L, L - 1); }
 };
+
+// d d2 / d x for the Mahalanobis term, everything in registers (the loops of nfb_jac.cuh: maha_gradient index g[] at run
+// time, i.e. through local memory: a 650-step dependent chain per query, which this kernel cannot hide).
+__device__ __forceinline__ void maha_gradient_regs(const double (&x)[N_IN], double (&g)[N_IN]) {
+  double d[N_IN];
+#pragma unroll
+  for (int i = 0; i < N_IN; ++i) {
+    d[i] = x[i] - c_mean[i];
+    g[i] = 0.0;
+  }
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < N_IN; ++i) {
+#pragma unroll
+    for (int j = i; j < N_IN; ++j) {
+      const double q = c_quad[idx++];
+      if (i == j) {
+        g[i] = fma(2.0 * q, d[i], g[i]);
+      } else {
+        g[i] = fma(q, d[j], g[i]);
+        g[j] = fma(q, d[i], g[j]);
+      }
+    }
+  }
+}
 
 template <class Cfg>
 struct GradCfg {
@@ -84,8 +113,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
     for (int l = 1; l < L - 1; ++l)
       for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(blob_layer_offset<H>(l)) + c * KC * H, KC * H * 4);
     table[j++] = make_uint2(uint32_t(GB::scal_off(L)), uint32_t(p.k_hidden) * 8 * 4);
-    for (int l = L - 2; l >= 0; --l)
+    for (int l = L - 2; l >= 1; --l)
       for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(GB::wt_off(L, l)) + c * KC * H, KC * H * 4);
+    for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(GB::wt0_off(L)) + c * KC * K0_PAD, KC * K0_PAD * 4);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, WARPS);
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
     group_bar();
 
     // ---------------- backward: d a_{l-1} = W_l^T d z_l ----------------
-    for (int l = L - 2; l >= 0; --l) {
+    for (int l = L - 2; l >= 1; --l) {
       float2 acc[8][TN / 2];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -283,7 +313,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
         release_slice(s);
       }
       group_bar();  // the group has finished reading d z_l
-      const float* const sl = slopes + size_t(l > 0 ? l - 1 : 0) * H * NC;
+      const float* const sl = slopes + size_t(l - 1) * H * NC;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
 #pragma unroll
@@ -292,12 +322,38 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
           for (int tw = 0; tw < 2; ++tw) {
             const float2 a0 = acc[i][tw * (TN / 4) + 2 * v], a1 = acc[i][tw * (TN / 4) + 2 * v + 1];
             const int off = tile_offset(i, v, tw == 1);
-            float4 d = make_float4(a0.x, a0.y, a1.x, a1.y);
-            if (l > 0) {  // d z_{l-1} = d a_{l-1} * SiLU'(z_{l-1}); this thread stored those slopes itself
-              const float4 m = __ldcg(reinterpret_cast<const float4*>(sl + off));
-              d.x *= m.x; d.y *= m.y; d.z *= m.z; d.w *= m.w;
+            // d z_{l-1} = d a_{l-1} * SiLU'(z_{l-1}); this thread stored those slopes itself
+            const float4 m = __ldcg(reinterpret_cast<const float4*>(sl + off));
+            *reinterpret_cast<float4*>(act + off) = make_float4(a0.x * m.x, a0.y * m.y, a1.x * m.z, a1.y * m.w);
+          }
+        }
+      }
+      group_bar();
+    }
+    {  // layer 0: d x = W_0^T d z_0 has 32 rows only -- a 4-row thread tile on the threads whose rows exist
+      const bool mine = h_row < K0_PAD;
+      float2 acc[4][TN / 2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(0.0f, 0.0f);
+      for (int c = 0; c < nkh; ++c) {
+        uint32_t s;
+        wait_slice(s);
+        if (mine) ffma_slice<4, TN, K0_PAD, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+        release_slice(s);
+      }
+      group_bar();
+      if (mine) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int v = 0; v < TN / 8; ++v) {
+#pragma unroll
+            for (int tw = 0; tw < 2; ++tw) {
+              const float2 a0 = acc[i][tw * (TN / 4) + 2 * v], a1 = acc[i][tw * (TN / 4) + 2 * v + 1];
+              *reinterpret_cast<float4*>(act + tile_offset(i, v, tw == 1)) = make_float4(a0.x, a0.y, a1.x, a1.y);
             }
-            *reinterpret_cast<float4*>(act + off) = d;
           }
         }
       }
@@ -309,7 +365,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
       const int c = wn * QG + t;
       const long long q = tile_q0 + c;
       if (q >= p.n) continue;
-      double x[N_IN], xt[N_IN], g[N_IN], gt[N_IN];
+      double x[N_IN], xt[N_IN];
       float m_unused, re_unused;
       featurise_query(p, q, true, false, x, m_unused, re_unused);
 #pragma unroll
@@ -317,14 +373,19 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
 #pragma unroll
       for (int i = 0; i < 8; ++i) { xt[i] = -x[8 + i]; xt[8 + i] = -x[i]; }  // main.py:253-265
       xt[16] = -x[16]; xt[18] = -x[18]; xt[23] = x[24]; xt[24] = x[23];
-      maha_gradient(x, g);
-      maha_gradient(xt, gt);
-      const double mq = double(maha[c]) / (2.0 * N_IN), mt = double(maha[NQ + c]) / (2.0 * N_IN);
       double G[N_IN], T[N_IN];
+#pragma unroll 1
+      for (int tw = 0; tw < 2; ++tw) {  // one copy of the 625 DFMAs for both twins
+        double xx[N_IN], gg[N_IN];
 #pragma unroll
-      for (int k = 0; k < N_IN; ++k) {
-        G[k] = double(act[k * NC + c]) + mq * g[k];
-        T[k] = double(act[k * NC + NQ + c]) + mt * gt[k];
+        for (int i = 0; i < N_IN; ++i) xx[i] = tw ? xt[i] : x[i];
+        maha_gradient_regs(xx, gg);
+        const double mc = double(maha[tw * NQ + c]) / (2.0 * N_IN);
+#pragma unroll
+        for (int k = 0; k < N_IN; ++k) {
+          const double val = double(act[k * NC + tw * NQ + c]) + mc * gg[k];
+          if (tw) T[k] = val; else G[k] = val;
+        }
       }
       // pull the twin's gradient back through the flip (its transpose: the same signed permutation)
 #pragma unroll
