@@ -22,7 +22,7 @@
 // objective that needs them uses nfb_eval_vjp_device.
 #pragma once
 #include "nfb_ffma_groups.cuh"
-#include "nfb_jac.cuh"  // maha_gradient
+#include "nfb_jac.cuh"  // maha_gradient_regs
 
 namespace nfb {
 
@@ -47,31 +47,6 @@ struct GradBlob {
   }
   __host__ __device__ static constexpr size_t total(int L) { return wt_off(L, L - 1); }
 };
-
-// d d2 / d x for the Mahalanobis term, everything in registers (the loops of nfb_jac.cuh: maha_gradient index g[] at run
-// time, i.e. through local memory: a 650-step dependent chain per query, which this kernel cannot hide).
-__device__ __forceinline__ void maha_gradient_regs(const double (&x)[N_IN], double (&g)[N_IN]) {
-  double d[N_IN];
-#pragma unroll
-  for (int i = 0; i < N_IN; ++i) {
-    d[i] = x[i] - c_mean[i];
-    g[i] = 0.0;
-  }
-  int idx = 0;
-#pragma unroll
-  for (int i = 0; i < N_IN; ++i) {
-#pragma unroll
-    for (int j = i; j < N_IN; ++j) {
-      const double q = c_quad[idx++];
-      if (i == j) {
-        g[i] = fma(2.0 * q, d[i], g[i]);
-      } else {
-        g[i] = fma(q, d[j], g[i]);
-        g[j] = fma(q, d[i], g[j]);
-      }
-    }
-  }
-}
 
 template <class Cfg>
 struct GradCfg {

@@ -46,8 +46,10 @@ struct JacCfg {
 };
 
 // d2 = sum_i S_ii d_i^2 + sum_{i<j} Q_ij d_i d_j (c_quad: packed upper triangle, off-diagonals pre-summed):
-// g_i = d d2 / d d_i = 2 S_ii d_i + sum_{j != i} Q_ij d_j
-__device__ __forceinline__ void maha_gradient(const double (&x)[N_IN], double* g) {
+// g_i = d d2 / d d_i = 2 S_ii d_i + sum_{j != i} Q_ij d_j.  Everything in registers: written as loops that index g[] at run time
+// it goes through local memory -- a 650-step dependent chain per query that nothing hides (it cost the reverse-mode kernel
+// of nfb_grad.cuh a factor 1.6 .. 2.9).
+__device__ __forceinline__ void maha_gradient_regs(const double (&x)[N_IN], double (&g)[N_IN]) {
   double d[N_IN];
 #pragma unroll
   for (int i = 0; i < N_IN; ++i) {
@@ -55,16 +57,19 @@ __device__ __forceinline__ void maha_gradient(const double (&x)[N_IN], double* g
     g[i] = 0.0;
   }
   int idx = 0;
-  for (int i = 0; i < N_IN; ++i)
-    for (int j = i; j < N_IN; ++j, ++idx) {
-      const double q = c_quad[idx];
+#pragma unroll
+  for (int i = 0; i < N_IN; ++i) {
+#pragma unroll
+    for (int j = i; j < N_IN; ++j) {
+      const double q = c_quad[idx++];
       if (i == j) {
-        g[i] += 2.0 * q * d[i];
+        g[i] = fma(2.0 * q, d[i], g[i]);
       } else {
-        g[i] += q * d[j];
-        g[j] += q * d[i];
+        g[i] = fma(q, d[j], g[i]);
+        g[j] = fma(q, d[i], g[j]);
       }
     }
+  }
 }
 
 __device__ __forceinline__ float silu_slope(float z) {  // d/dz [z sigmoid(z)]
@@ -100,7 +105,12 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, (H <= 256) ? 2 : 1) nfb_ja
     for (int k = 0; k < N_IN; ++k) col[k * JAC_COLS] = static_cast<float>(x[k]);
     dmaha[tid * JAC_HALF] = m;
     if (!twin) re_s[0] = re;
-    maha_gradient(x, grad + tid * N_IN);
+    {
+      double g[N_IN];
+      maha_gradient_regs(x, g);
+#pragma unroll
+      for (int k = 0; k < N_IN; ++k) grad[tid * N_IN + k] = g[k];
+    }
     // tangents of the query's features; for the twin row k of the flipped vector is sign * (row perm(k) of the query's)
     const double kdeg = 3.141592653589793238462643383279502884 / 180.0;
     const double alpha = p.in_f64 ? __ldg(static_cast<const double*>(p.in[18]) + q * p.in_stride[18])
