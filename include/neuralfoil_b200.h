@@ -147,6 +147,13 @@ int nfb_eval_scalar_grad_device(nfb_context* ctx, int model_id, int64_t n, const
                                 const int64_t* in_strides, int in_dtype, const void* cot, int64_t cot_ld,
                                 void* values, int64_t values_ld, void* grad, int64_t grad_ld, int out_dtype, void* stream);
 
+/* nfb_eval_vjp_device's result -- cotangents of all 198 outputs -- from the fused reverse pass (nfb_grad.cuh, FULL): same
+ * arguments, same meaning; about 3 forward passes of arithmetic per query instead of 24.  The kernel of choice from a few
+ * hundred queries up; the forward-mode kernel remains the one for an optimiser's single query. */
+int nfb_eval_vjp_reverse_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,
+                                const int64_t* in_strides, int in_dtype, const void* cot, int64_t cot_ld,
+                                void* values, int64_t values_ld, void* grad, int64_t grad_ld, int out_dtype, void* stream);
+
 /* Pinned host memory helpers for callers without their own allocator. */
 int nfb_host_alloc(void** out_ptr, int64_t bytes);
 int nfb_host_free(void* ptr);

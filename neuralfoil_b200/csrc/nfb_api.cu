@@ -208,7 +208,7 @@ std::vector<float> pack_model(int L, const int* dims, const float* const* W, con
   return blob;
 }
 
-// Blob of the reverse-mode kernel (nfb_grad.cuh: GradBlob): the value blob's hidden layers, the six scalar rows of the last
+// Blob of the reverse-mode kernels (nfb_grad.cuh: GradBlob): the value blob, the six scalar rows of the last
 // layer as Wt[k][8] with their biases, and the hidden layers transposed, WT_l[m][k] = W_l[m][k] zero-padded to H x 32 (l = 0)
 // or H x H.
 template <int H>
@@ -216,8 +216,13 @@ std::vector<float> pack_grad_blob(int L, const int* dims, const float* const* W,
                                   const std::vector<float>& value_blob) {
   using GB = nfb::GradBlob<H>;
   std::vector<float> g(GB::total(L), 0.0f);
-  std::copy(value_blob.begin(), value_blob.begin() + nfb::blob_layer_offset<H>(L - 1), g.begin());
+  std::copy(value_blob.begin(), value_blob.end(), g.begin());  // == SweepBlob<H>::total(L) floats
   const int in_last = dims[L - 1];
+  for (int pr = 0; pr < nfb::GRAD_LAST_ROWS; ++pr) {  // the last layer transposed by packed row
+    const int src_row = nfb::pack_last_layer_row(pr);
+    if (src_row < 0 || src_row >= dims[L]) continue;
+    for (int k = 0; k < in_last; ++k) g[GB::wst_off(L) + size_t(pr) * H + k] = W[L - 1][size_t(src_row) * in_last + k];
+  }
   for (int i = 0; i < 6; ++i) {
     for (int k = 0; k < in_last; ++k) g[GB::scal_off(L) + size_t(k) * 8 + i] = W[L - 1][size_t(i) * in_last + k];
     g[GB::scal_bias_off(L) + i] = B[L - 1][i];
@@ -377,23 +382,27 @@ int launch_ffma_groups(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t 
 
 int ensure(void** ptr, size_t* have, size_t need, bool pinned_host);
 
-template <class Cfg>
-int launch_scalar_grad(nfb_context* ctx, nfb::GradParams& gp, cudaStream_t stream) {
+template <class Cfg, bool FULL>
+int launch_grad(nfb_context* ctx, nfb::GradParams& gp, cudaStream_t stream) {
   using GC = nfb::GradCfg<Cfg>;
   static thread_local int configured_device = -1;
   if (configured_device != ctx->device) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_scalar_grad_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_grad_kernel<Cfg, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   int(GC::SMEM_BYTES)));
     configured_device = ctx->device;
   }
   const long long tiles = (gp.ev.n + Cfg::NQ - 1) / Cfg::NQ;
   const int grid = int(std::min<long long>(tiles, ctx->sm_count));
-  const size_t need = size_t(grid) * (gp.ev.n_layers - 1) * Cfg::H * Cfg::NC * sizeof(float);
-  if (need > ctx->grad_scratch_bytes) NFB_CUDA(cudaStreamSynchronize(stream));  // nothing may still read the old block
-  int rc = ensure(&ctx->grad_scratch, &ctx->grad_scratch_bytes, need, false);
-  if (rc != NFB_OK) return rc;
+  const size_t need = size_t(grid) * nfb::grad_scratch_floats<Cfg::H, Cfg::NC>(gp.ev.n_layers, FULL) * sizeof(float);
+  if (need > ctx->grad_scratch_bytes) {
+    NFB_CUDA(cudaDeviceSynchronize());  // nothing may still read the old block
+    int rc = ensure(&ctx->grad_scratch, &ctx->grad_scratch_bytes, need, false);
+    if (rc != NFB_OK) return rc;
+    // parked rows that no kernel writes (packed rows 198..207 of the narrow models) must read as zero, never as NaN
+    NFB_CUDA(cudaMemset(ctx->grad_scratch, 0, ctx->grad_scratch_bytes));
+  }
   gp.scratch = static_cast<float*>(ctx->grad_scratch);
-  nfb::nfb_scalar_grad_kernel<Cfg><<<grid, Cfg::THREADS, GC::SMEM_BYTES, stream>>>(gp);
+  nfb::nfb_grad_kernel<Cfg, FULL><<<grid, Cfg::THREADS, GC::SMEM_BYTES, stream>>>(gp);
   NFB_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return NFB_OK;
@@ -1009,15 +1018,16 @@ int nfb_eval_vjp_device(nfb_context* ctx, int model_id, int64_t n, const void* c
                               grad_ld, out_dtype, stream);
 }
 
-int nfb_eval_scalar_grad_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows, const int64_t* in_strides,
-                                int in_dtype, const void* cot, int64_t cot_ld, void* values, int64_t values_ld, void* grad,
-                                int64_t grad_ld, int out_dtype, void* stream) {
+namespace {
+int grad_device_impl(nfb_context* ctx, bool full, int model_id, int64_t n, const void* const* in_rows, const int64_t* in_strides,
+                     int in_dtype, const void* cot, int64_t cot_ld, void* values, int64_t values_ld, void* grad,
+                     int64_t grad_ld, int out_dtype, void* stream) {
   static char dummy_out;
   int rc = check_eval_args(ctx, model_id, NFB_VARIANT_FP32_FFMA, n, in_rows, in_strides, in_dtype, values ? values : &dummy_out,
                            values ? values_ld : n, out_dtype);
   if (rc != NFB_OK || n == 0) return rc;
   if (!cot || !grad || cot_ld < n || grad_ld < n)
-    return fail(NFB_ERR_INVALID_ARGUMENT, "scalar gradient: cot or grad is NULL, or a leading dimension is smaller than n");
+    return fail(NFB_ERR_INVALID_ARGUMENT, "reverse-mode gradient: cot or grad is NULL, or a leading dimension is smaller than n");
   NFB_CUDA(cudaSetDevice(ctx->device));
   const Model& m = ctx->models[model_id];
   nfb::GradParams gp;
@@ -1033,7 +1043,7 @@ int nfb_eval_scalar_grad_device(nfb_context* ctx, int model_id, int64_t n, const
   gp.ev.k_hidden = m.k_hidden;
   gp.ev.in_f64 = (in_dtype == NFB_F64);
   gp.ev.out_f64 = (out_dtype == NFB_F64);
-  gp.ev.scalars_only = 1;
+  gp.ev.scalars_only = full ? 0 : 1;
   gp.cot = cot;
   gp.grad = grad;
   gp.cot_ld = cot_ld;
@@ -1041,12 +1051,27 @@ int nfb_eval_scalar_grad_device(nfb_context* ctx, int model_id, int64_t n, const
   gp.scratch = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (m.h_pad) {
-    case 64: return launch_scalar_grad<Grp64>(ctx, gp, st);
-    case 128: return launch_scalar_grad<Grp128>(ctx, gp, st);
-    case 256: return launch_scalar_grad<Grp256>(ctx, gp, st);
-    case 512: return launch_scalar_grad<Grp512>(ctx, gp, st);
+    case 64: return full ? launch_grad<Grp64, true>(ctx, gp, st) : launch_grad<Grp64, false>(ctx, gp, st);
+    case 128: return full ? launch_grad<Grp128, true>(ctx, gp, st) : launch_grad<Grp128, false>(ctx, gp, st);
+    case 256: return full ? launch_grad<Grp256, true>(ctx, gp, st) : launch_grad<Grp256, false>(ctx, gp, st);
+    case 512: return full ? launch_grad<Grp512, true>(ctx, gp, st) : launch_grad<Grp512, false>(ctx, gp, st);
   }
   return fail(NFB_ERR_UNSUPPORTED_MODEL, "no kernel for padded width %d", m.h_pad);
+}
+}  // namespace
+
+int nfb_eval_scalar_grad_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows, const int64_t* in_strides,
+                                int in_dtype, const void* cot, int64_t cot_ld, void* values, int64_t values_ld, void* grad,
+                                int64_t grad_ld, int out_dtype, void* stream) {
+  return grad_device_impl(ctx, false, model_id, n, in_rows, in_strides, in_dtype, cot, cot_ld, values, values_ld, grad, grad_ld,
+                          out_dtype, stream);
+}
+
+int nfb_eval_vjp_reverse_device(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows, const int64_t* in_strides,
+                                int in_dtype, const void* cot, int64_t cot_ld, void* values, int64_t values_ld, void* grad,
+                                int64_t grad_ld, int out_dtype, void* stream) {
+  return grad_device_impl(ctx, true, model_id, n, in_rows, in_strides, in_dtype, cot, cot_ld, values, values_ld, grad, grad_ld,
+                          out_dtype, stream);
 }
 
 int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,

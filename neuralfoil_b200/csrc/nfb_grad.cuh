@@ -18,8 +18,11 @@
 //   finish    one thread per query: d x of the query + the twin's d x pulled back through the flip (a signed permutation),
 //             the Mahalanobis term of the confidence logit (fp64, as in the forward pass), the chain rule of the
 //             featurisation [main.py:171-184], 23 coalesced stores.
-// The boundary-layer rows are not differentiated here (192 more cotangent rows, a transposed sweep per sweep): an
-// objective that needs them uses nfb_eval_vjp_device.
+// FULL = true (nfb_eval_vjp_reverse_device) takes cotangents of all 198 outputs: the last layer's sweeps run as in the value
+// kernel, their epilogue pulls the cotangents of theta, H and ue/Vinf back to the latents of the query and of its twin
+// [main.py:274-316] and parks them in the scratch block; after the scalar pass (which parks its six rows there too) the
+// parked rows come back into the tile H at a time and W_last^T (packed rows, transposed) takes them to d a_{L-2}.  theta's
+// direct dependence on Re [main.py:309,314] is summed per query in a fixed order in the finish step.
 #pragma once
 #include "nfb_ffma_groups.cuh"
 #include "nfb_jac.cuh"  // maha_gradient_regs
@@ -34,33 +37,116 @@ struct GradParams {
   float* scratch;     // gridDim.x blocks of (L-1) * H * NC floats
 };
 
-// Gradient blob (floats): the hidden layers of the value blob (layers 0 .. L-2 with their biases), then the scalar rows
+// Gradient blob (floats): the whole value blob (nfb_ffma_groups.cuh: layers and last-layer sweeps), then the scalar rows
 // of the last layer Wt[k][8] and their 8 biases, then the transposed layers WT_l[m][k] = W_l[m][k]: WT_0 as H x 32, WT_1 .. WT_{L-2}
-// as H x H.
+// as H x H, then the last layer transposed by packed row, [208][H].
+constexpr int GRAD_LAST_ROWS = 208;  // packed rows of the last layer the reverse sweep contracts over (200 used; a multiple of KC)
+
 template <int H>
 struct GradBlob {
-  __host__ __device__ static constexpr size_t scal_off(int L) { return blob_layer_offset<H>(L - 1); }
+  __host__ __device__ static constexpr size_t scal_off(int L) { return SweepBlob<H>::total(L); }          // behind the whole value blob
   __host__ __device__ static constexpr size_t scal_bias_off(int L) { return scal_off(L) + size_t(H) * 8; }
   __host__ __device__ static constexpr size_t wt0_off(int L) { return scal_bias_off(L) + 8; }             // WT_0[m][32]
   __host__ __device__ static constexpr size_t wt_off(int L, int l) {                                      // WT_l[m][H], l >= 1
     return wt0_off(L) + size_t(H) * K0_PAD + size_t(l - 1) * H * H;
   }
-  __host__ __device__ static constexpr size_t total(int L) { return wt_off(L, L - 1); }
+  __host__ __device__ static constexpr size_t wst_off(int L) { return wt_off(L, L - 1); }                 // W_last^T: [packed row][k]
+  __host__ __device__ static constexpr size_t total(int L) { return wst_off(L) + size_t(GRAD_LAST_ROWS) * H; }
 };
+
+// per-CTA scratch (floats): SiLU slopes [L-1][H][NC]; FULL: parked latent cotangents [256][NC] and theta's d / d Re partials [32][NC]
+template <int H, int NC>
+__host__ __device__ constexpr size_t grad_scratch_floats(int L, bool full) {
+  return size_t(L - 1) * H * NC + (full ? size_t(256 + N_BL) * NC : 0);
+}
+
+// Boundary-layer row group g of decode_and_store, reverse mode: from the four packed rows of 4 queries (yf[i][0..3]) and
+// their twins (yf[i][4..7]) compute the outputs (stored if p.out), read their cotangents and return the cotangents of
+// the 32 latents in dl (same layout) plus, for theta, its direct d / d Re share per query.  Groups 48.. belong to the scalar pass.
+__device__ __forceinline__ void bl_group_vjp(const EvalParams& p, const GradParams& gp, int g, long long q0, int nvalid, bool vec_ok,
+                                             const float (&yf)[4][8], const float* __restrict__ re4, float (&dl)[4][8],
+                                             float (&re_part)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dl[i][j] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) re_part[j] = 0.0f;
+  if (g >= 48) return;
+  int r[4];
+  if (g < N_BL) {
+    r[0] = 6 + g; r[1] = 6 + 2 * N_BL + g; r[2] = 6 + 3 * N_BL + g; r[3] = 6 + 5 * N_BL + g;
+  } else {
+    const int s = 2 * (g - N_BL);
+    r[0] = 6 + N_BL + s; r[1] = r[0] + 1; r[2] = 6 + 4 * N_BL + s; r[3] = r[2] + 1;
+  }
+  float ct[4][4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ct[i][j] = 0.0f;
+      if (j < nvalid)
+        ct[i][j] = p.out_f64 ? float(__ldg(static_cast<const double*>(gp.cot) + r[i] * gp.cot_ld + q0 + j))
+                             : __ldg(static_cast<const float*>(gp.cot) + r[i] * gp.cot_ld + q0 + j);
+    }
+  if (g < N_BL) {  // theta_u, ue_u, theta_l, ue_l of station g
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float zt_u = 0.5f * (yf[0][j] + yf[2][4 + j]);
+      const float zu_u = 0.5f * (yf[1][j] - yf[3][4 + j]);
+      const float zt_l = 0.5f * (yf[2][j] + yf[0][4 + j]);
+      const float zu_l = 0.5f * (yf[3][j] - yf[1][4 + j]);
+      const float re = re4[j];
+      const float pu = exp10f(zt_u), pl = exp10f(zt_l);
+      const float th_u = (pu - 0.1f) / (fabsf(zu_u) * re), th_l = (pl - 0.1f) / (fabsf(zu_l) * re);
+      o[0][j] = th_u; o[1][j] = zu_u; o[2][j] = th_l; o[3][j] = zu_l;
+      const float g_ztu = ct[0][j] * 2.302585092994046f * pu / (fabsf(zu_u) * re);
+      const float g_zuu = ct[1][j] - ct[0][j] * th_u / zu_u;
+      const float g_ztl = ct[2][j] * 2.302585092994046f * pl / (fabsf(zu_l) * re);
+      const float g_zul = ct[3][j] - ct[2][j] * th_l / zu_l;
+      re_part[j] = -(ct[0][j] * th_u + ct[2][j] * th_l) / re;
+      dl[0][j] = 0.5f * g_ztu; dl[2][4 + j] = 0.5f * g_ztu;
+      dl[1][j] = 0.5f * g_zuu; dl[3][4 + j] = -0.5f * g_zuu;
+      dl[2][j] = 0.5f * g_ztl; dl[0][4 + j] = 0.5f * g_ztl;
+      dl[3][j] = 0.5f * g_zul; dl[1][4 + j] = -0.5f * g_zul;
+    }
+  } else {  // H_u, H_l of stations s, s + 1
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[0][j] = 2.6f * expf(0.5f * (yf[0][j] + yf[2][4 + j]));
+      o[1][j] = 2.6f * expf(0.5f * (yf[1][j] + yf[3][4 + j]));
+      o[2][j] = 2.6f * expf(0.5f * (yf[2][j] + yf[0][4 + j]));
+      o[3][j] = 2.6f * expf(0.5f * (yf[3][j] + yf[1][4 + j]));
+      const float g0 = 0.5f * ct[0][j] * o[0][j], g1 = 0.5f * ct[1][j] * o[1][j];
+      const float g2 = 0.5f * ct[2][j] * o[2][j], g3 = 0.5f * ct[3][j] * o[3][j];
+      dl[0][j] = g0; dl[2][4 + j] = g0;
+      dl[1][j] = g1; dl[3][4 + j] = g1;
+      dl[2][j] = g2; dl[0][4 + j] = g2;
+      dl[3][j] = g3; dl[1][4 + j] = g3;
+    }
+  }
+  if (p.out) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) store_row4(p, r[i], q0, nvalid, vec_ok, o[i]);
+  }
+}
 
 template <class Cfg>
 struct GradCfg {
-  static constexpr int MAX_SLICES = K0_PAD / Cfg::KC + 2 * (NFB_MAX_LAYERS_K - 1) * (Cfg::H / Cfg::KC) + 1;
+  static constexpr int MAX_SLICES = K0_PAD / Cfg::KC + (2 * (NFB_MAX_LAYERS_K - 1) + Cfg::NFULL + Cfg::NHALF) * (Cfg::H / Cfg::KC) + 1 +
+                                    GRAD_LAST_ROWS / Cfg::KC;
   static constexpr size_t SMEM_BYTES = sizeof(float) * (size_t(Cfg::H) * Cfg::NC + size_t(Cfg::STAGES) * Cfg::SLOT_FLOATS +
                                                         Cfg::NC + Cfg::NQ) + 16 * Cfg::STAGES + 8 * size_t(MAX_SLICES);
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit shared memory");
 };
 
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const GradParams gp) {
+template <class Cfg, bool FULL>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradParams gp) {
   constexpr int H = Cfg::H, NC = Cfg::NC, NQ = Cfg::NQ, KC = Cfg::KC, STAGES = Cfg::STAGES, TN = Cfg::TN;
   constexpr int WM = Cfg::WM, SLOT = Cfg::SLOT_FLOATS, LM = Cfg::LM, LN = Cfg::LN, QG = Cfg::QG;
   constexpr int WARPS = Cfg::WARPS, QT = TN / 2;
+  constexpr int NFULL = FULL ? Cfg::NFULL : 0, NHALF = FULL ? Cfg::NHALF : 0, NB = GRAD_LAST_ROWS;
   const EvalParams& p = gp.ev;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -77,17 +163,25 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
   const long long n_tiles = (p.n + NQ - 1) / NQ;
   using GB = GradBlob<H>;
   const int nkh = (p.k_hidden + KC - 1) / KC;
-  const uint32_t slices_per_tile = K0_PAD / KC + (L - 2) * nkh + 1 + (L - 1) * nkh;
+  const uint32_t slices_per_tile = K0_PAD / KC + (L - 2 + NFULL + NHALF) * nkh + 1 + (FULL ? NB / KC : 0) + (L - 1) * nkh;
   const uint32_t my_tiles = uint32_t((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const uint32_t total_slices = my_tiles * slices_per_tile;
-  float* const slopes = gp.scratch + size_t(blockIdx.x) * (L - 1) * H * NC;  // [L-1][H][NC]
+  float* const slopes = gp.scratch + size_t(blockIdx.x) * grad_scratch_floats<H, NC>(L, FULL);  // [L-1][H][NC]
+  float* const dlat = slopes + size_t(L - 1) * H * NC;  // FULL: [256][NC] parked latent cotangents, [32][NC] d theta / d Re partials
+  using SB = SweepBlob<H>;
 
   if (tid == 0) {
     uint32_t j = 0;
     for (int c = 0; c < K0_PAD / KC; ++c) table[j++] = make_uint2(c * KC * H, KC * H * 4);
     for (int l = 1; l < L - 1; ++l)
       for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(blob_layer_offset<H>(l)) + c * KC * H, KC * H * 4);
+    for (int sw = 0; sw < NFULL; ++sw)
+      for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(SB::full_off(L)) + (sw * H + c * KC) * H, KC * H * 4);
+    for (int sw = 0; sw < NHALF; ++sw)
+      for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(SB::half_off(L)) + c * KC * (H / 2), KC * (H / 2) * 4);
     table[j++] = make_uint2(uint32_t(GB::scal_off(L)), uint32_t(p.k_hidden) * 8 * 4);
+    if (FULL)
+      for (int c = 0; c < NB / KC; ++c) table[j++] = make_uint2(uint32_t(GB::wst_off(L)) + c * KC * H, KC * H * 4);
     for (int l = L - 2; l >= 1; --l)
       for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(GB::wt_off(L, l)) + c * KC * H, KC * H * 4);
     for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(GB::wt0_off(L)) + c * KC * K0_PAD, KC * K0_PAD * 4);
@@ -194,6 +288,79 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
       group_bar();  // also orders the slope stores before the reads of other threads of the group
     }
 
+    // ---------------- FULL: the last layer's sweeps; epilogue = outputs (if wanted) and the latents' cotangents, parked ----------------
+    if constexpr (FULL) {
+      const bool vec_ok =
+          p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
+                    : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+      auto vjp_rows = [&](const float2(&a4)[4][TN / 2], int g) {  // four packed rows 4g..4g+3 of this thread's columns
+#pragma unroll
+        for (int v = 0; v < TN / 8; ++v) {
+          float yf[4][8], dl[4][8], re_part[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            yf[i][0] = a4[i][2 * v].x; yf[i][1] = a4[i][2 * v].y;
+            yf[i][2] = a4[i][2 * v + 1].x; yf[i][3] = a4[i][2 * v + 1].y;
+            yf[i][4] = a4[i][TN / 4 + 2 * v].x; yf[i][5] = a4[i][TN / 4 + 2 * v].y;
+            yf[i][6] = a4[i][TN / 4 + 2 * v + 1].x; yf[i][7] = a4[i][TN / 4 + 2 * v + 1].y;
+          }
+          const int c4 = h_col + 4 * v;
+          const long long q0 = tile_q0 + c4;
+          const long long left = p.n - q0;
+          const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
+          bl_group_vjp(p, gp, g, q0, nvalid, vec_ok, yf, re_s + c4, dl, re_part);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float* const row = dlat + size_t(4 * g + i) * NC;
+            __stcg(reinterpret_cast<float4*>(row + c4), make_float4(dl[i][0], dl[i][1], dl[i][2], dl[i][3]));
+            __stcg(reinterpret_cast<float4*>(row + NQ + c4), make_float4(dl[i][4], dl[i][5], dl[i][6], dl[i][7]));
+          }
+          if (g < N_BL)
+            __stcg(reinterpret_cast<float4*>(dlat + size_t(256 + g) * NC + c4), make_float4(re_part[0], re_part[1], re_part[2], re_part[3]));
+        }
+      };
+      for (int sw = 0; sw < NFULL; ++sw) {
+        float2 acc[8][TN / 2];
+        const float* const sweep_bias = p.blob + SB::bias_off(L);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float b_lo = __ldg(sweep_bias + sw * H + h_row + i), b_hi = __ldg(sweep_bias + sw * H + H / 2 + h_row + i);
+#pragma unroll
+          for (int jj = 0; jj < TN / 2; ++jj) {
+            acc[i][jj] = make_float2(b_lo, b_lo);
+            acc[4 + i][jj] = make_float2(b_hi, b_hi);
+          }
+        }
+        for (int c = 0; c < nkh; ++c) {
+          uint32_t s;
+          wait_slice(s);
+          ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+          release_slice(s);
+        }
+        const int g = sw * (H / 4) + wm * LM + lm;
+        vjp_rows(reinterpret_cast<const float2(&)[4][TN / 2]>(acc[0]), g);
+        vjp_rows(reinterpret_cast<const float2(&)[4][TN / 2]>(acc[4]), g + H / 8);
+      }
+      if constexpr (NHALF > 0) {
+        float2 acc[4][TN / 2];
+        const float* const sweep_bias = p.blob + SB::bias_off(L);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float b = __ldg(sweep_bias + SB::HALF_ROW0 + h_row + i);
+#pragma unroll
+          for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(b, b);
+        }
+        for (int c = 0; c < nkh; ++c) {
+          uint32_t s;
+          wait_slice(s);
+          ffma_slice<4, TN, H / 2, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+          release_slice(s);
+        }
+        vjp_rows(acc, SB::HALF_ROW0 / 4 + wm * LM + lm);
+      }
+      group_bar();  // the parked rows of groups 48, 49 (zeros) are written before the scalar pass overwrites them
+    }
+
     // ---------------- turn: scalar latents, outputs, their cotangents, d a_{L-2} ----------------
     {
       uint32_t s;
@@ -259,20 +426,70 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
         const float dt[6] = {0.5f * g0, -0.5f * g1, 0.5f * g2, -0.5f * g3, 0.5f * g5, 0.5f * g4};
         maha[c] = -0.5f * g0;       // cotangent of the query's d2 / 50
         maha[NQ + c] = -0.5f * g0;  // ... and of the twin's
-        const float* const sl = slopes + size_t(L - 2) * H * NC + c;
+        if constexpr (FULL) {  // park the six rows (packed rows 192..197) with the others
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            __stcg(dlat + size_t(SB::SCAL_ROW0 + i) * NC + c, dq[i]);
+            __stcg(dlat + size_t(SB::SCAL_ROW0 + i) * NC + NQ + c, dt[i]);
+          }
+        } else {
+          const float* const sl = slopes + size_t(L - 2) * H * NC + c;
 #pragma unroll 4
-        for (int k = 0; k < kh; ++k) {
-          const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * k);
-          const float2 w1 = *reinterpret_cast<const float2*>(w + 8 * k + 4);
-          const float sq = w0.x * dq[0] + w0.y * dq[1] + w0.z * dq[2] + w0.w * dq[3] + w1.x * dq[4] + w1.y * dq[5];
-          const float st = w0.x * dt[0] + w0.y * dt[1] + w0.z * dt[2] + w0.w * dt[3] + w1.x * dt[4] + w1.y * dt[5];
-          aq[k * NC] = sq * __ldcg(sl + k * NC);
-          aq[k * NC + NQ] = st * __ldcg(sl + k * NC + NQ);
+          for (int k = 0; k < kh; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w + 8 * k);
+            const float2 w1 = *reinterpret_cast<const float2*>(w + 8 * k + 4);
+            const float sq = w0.x * dq[0] + w0.y * dq[1] + w0.z * dq[2] + w0.w * dq[3] + w1.x * dq[4] + w1.y * dq[5];
+            const float st = w0.x * dt[0] + w0.y * dt[1] + w0.z * dt[2] + w0.w * dt[3] + w1.x * dt[4] + w1.y * dt[5];
+            aq[k * NC] = sq * __ldcg(sl + k * NC);
+            aq[k * NC + NQ] = st * __ldcg(sl + k * NC + NQ);
+          }
         }
       }
       release_slice(s);
     }
     group_bar();
+
+    // ---------------- FULL: d a_{L-2} = W_last^T d latent, the parked rows brought back H at a time ----------------
+    if constexpr (FULL) {
+      float2 acc[8][TN / 2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(0.0f, 0.0f);
+      for (int r0 = 0; r0 < NB; r0 += H) {
+        const int rows_here = (NB - r0 < H) ? NB - r0 : H;
+        if (r0 > 0) group_bar();  // the previous chunk has been read
+        constexpr int V4 = 2 * QG / 4;  // float4s per row of the group's columns: queries, then twins
+        for (int idx = gtid; idx < rows_here * V4; idx += Cfg::GROUP_THREADS) {
+          const int r = idx / V4, cc = idx % V4;
+          const int col = (cc < QG / 4) ? wn * QG + 4 * cc : NQ + wn * QG + 4 * (cc - QG / 4);
+          *reinterpret_cast<float4*>(act + r * NC + col) = __ldcg(reinterpret_cast<const float4*>(dlat + size_t(r0 + r) * NC + col));
+        }
+        group_bar();
+        for (int c = 0; c < rows_here / KC; ++c) {
+          uint32_t s;
+          wait_slice(s);
+          ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
+          release_slice(s);
+        }
+      }
+      group_bar();
+      const float* const sl = slopes + size_t(L - 2) * H * NC;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int v = 0; v < TN / 8; ++v) {
+#pragma unroll
+          for (int tw = 0; tw < 2; ++tw) {
+            const float2 a0 = acc[i][tw * (TN / 4) + 2 * v], a1 = acc[i][tw * (TN / 4) + 2 * v + 1];
+            const int off = tile_offset(i, v, tw == 1);
+            const float4 m = __ldcg(reinterpret_cast<const float4*>(sl + off));
+            *reinterpret_cast<float4*>(act + off) = make_float4(a0.x * m.x, a0.y * m.y, a1.x * m.z, a1.y * m.w);
+          }
+        }
+      }
+      group_bar();
+    }
 
     // ---------------- backward: d a_{l-1} = W_l^T d z_l ----------------
     for (int l = L - 2; l >= 1; --l) {
@@ -380,6 +597,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_scalar_grad_kernel(const 
       out[17] = 50.0 * G[17];
       out[18] = kdeg * (2.0 * cos(2.0 * a) * G[18] - sin(a) * G[19] + 2.0 * cos(a) * sin(a) * G[20]);
       out[19] = G[21] / (3.5 * rey);
+      if constexpr (FULL) {  // theta = (10^z - 0.1) / (|ue| Re): the direct dependence, station by station in a fixed order
+        float sre = 0.0f;
+        for (int g = 0; g < N_BL; ++g) sre += __ldcg(dlat + size_t(256 + g) * NC + c);
+        out[19] += double(sre);
+      }
       out[20] = G[22] / 4.5;
       out[21] = G[23];
       out[22] = G[24];

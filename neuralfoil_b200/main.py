@@ -281,12 +281,14 @@ class Evaluator:
         )
         return values[:, :n], jac
 
-    def evaluate_vjp_device(self, raw, cotangent, model_size: str = "xlarge"):
+    def evaluate_vjp_device(self, raw, cotangent, model_size: str = "xlarge", reverse: bool | None = None):
         """
         Vector-Jacobian product: raw (23, N) and cotangent (198, N) CUDA tensors (same float dtype for the outputs;
         contiguous rows) -> (values (198, N), grad (23, N)), grad[t] = sum_row cotangent[row] * d output_row / d raw_t:
         the gradient with respect to the raw inputs of any scalar objective of the outputs, without materialising the
         198 x 23 Jacobian (18 KB per query).  Enqueues on torch's current stream.
+        `reverse`: True = the fused reverse pass (nfb_grad.cuh; ~3 forward passes per query), False = the forward-mode
+        kernel (24 passes per query, but the lower latency for a handful of queries); None = reverse from 256 queries up.
         """
         import torch
 
@@ -303,8 +305,11 @@ class Evaluator:
         values = torch.empty((_lib.N_OUTPUT_ROWS, ld), dtype=cotangent.dtype, device=dev)
         grad = torch.empty((_lib.N_RAW_ROWS, ld), dtype=cotangent.dtype, device=dev)
         ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].data_ptr() for i in range(_lib.N_RAW_ROWS)])
+        if reverse is None:
+            reverse = n >= 256
+        entry = self._lib.nfb_eval_vjp_reverse_device if reverse else self._lib.nfb_eval_vjp_device
         _lib.check(
-            self._lib.nfb_eval_vjp_device(
+            entry(
                 self._ctx, self._model_id(model_size), n, ptrs, _ONES_23,
                 _lib.F64 if raw.dtype == torch.float64 else _lib.F32,
                 C.c_void_p(cotangent.data_ptr()), int(cotangent.stride(0)),
@@ -361,14 +366,14 @@ class Evaluator:
         torch.cuda.synchronize(self.device)
         return values.cpu().numpy(), grad.cpu().numpy()
 
-    def evaluate_vjp_host(self, raw: np.ndarray, cotangent: np.ndarray, model_size: str = "xlarge"):
+    def evaluate_vjp_host(self, raw: np.ndarray, cotangent: np.ndarray, model_size: str = "xlarge", reverse: bool | None = None):
         """NumPy front door of `evaluate_vjp_device` (moves the arrays with torch): -> (values (198, N), grad (23, N)) float64."""
         import torch
 
         dev = f"cuda:{self.device}"
         r = torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float64)).to(dev)
         c = torch.from_numpy(np.ascontiguousarray(cotangent, dtype=np.float64)).to(dev)
-        values, grad = self.evaluate_vjp_device(r, c, model_size)
+        values, grad = self.evaluate_vjp_device(r, c, model_size, reverse=reverse)
         return values.cpu().numpy(), grad.cpu().numpy()
 
     def get_aero_and_jacobian_from_kulfan_parameters(

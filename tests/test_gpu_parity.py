@@ -821,3 +821,56 @@ def test_scalar_gradient_float32_device_api_and_symmetry(evaluator):
     _, g = evaluator.evaluate_scalar_grad_host(sym, c, "large")
     assert np.all(g[19] == 0.0) and np.all(g[20] == 0.0) and np.all(g[17] == 0.0)
     np.testing.assert_array_equal(g[0:8], g[8:16])
+
+
+@pytest.mark.parametrize("size", list(MODEL_SIZES) + ["xxxlarge"])
+def test_reverse_vjp_all_outputs_matches_forward_mode_and_oracle(evaluator, oracle, size):
+    """nfb_eval_vjp_reverse_device (fused reverse pass, cotangents of all 198 outputs) against the forward-mode VJP kernel and
+    against the oracle's analytic float64 Jacobian; the 198 values are the value kernel's bits."""
+    n = 1_001 if size != "xxxlarge" else 403
+    raw = synthetic.sample_training_distribution(n, seed=61)
+    rng = np.random.default_rng(8)
+    cot = np.zeros((198, n))
+    cot[:6] = rng.normal(size=(6, n)) * np.array([1.0, 1.0, 50.0, 1.0, 1.0, 1.0])[:, None]
+    cot[parity.ROW_THETA] = 10.0 * rng.normal(size=(64, n))
+    cot[parity.ROW_H] = 0.1 * rng.normal(size=(64, n))
+    cot[parity.ROW_UE] = 0.1 * rng.normal(size=(64, n))
+    values, grad = evaluator.evaluate_vjp_host(raw, cot, size, reverse=True)
+    assert values.shape == (198, n) and grad.shape == (23, n)
+    np.testing.assert_array_equal(values, evaluator.evaluate_host(raw, size, out_dtype=np.float64))
+    _, forward_mode = evaluator.evaluate_vjp_host(raw, cot, size, reverse=False)
+    scale = parity.JAC_INPUT_SCALE.copy()[:, None] * np.ones((1, n))
+    scale[19] = raw[19]
+    want_v, want_j = oracle.jacobian_raw(raw, size)
+    want = np.einsum("rtq,rq->tq", want_j, cot)
+    ref = np.abs(want) * scale + np.einsum("rq,rq->q", np.abs(cot), np.abs(want_v))[None, :] * 1e-1
+    err = np.abs(grad - want) * scale
+    err_fwd = np.abs(forward_mode - want) * scale
+    ok, ok_fwd = (err <= 5e-3 * ref + 1e-6), (err_fwd <= 5e-3 * ref + 1e-6)
+    assert ok.mean() >= ok_fwd.mean() - 1e-3 and ok.mean() > 0.98, (ok.mean(), ok_fwd.mean())
+    assert np.median(err / np.maximum(ref, 1e-30)) < 1e-5
+    between = np.abs(grad - forward_mode) * scale  # two fp32 evaluations of the same derivative
+    assert (between <= 5e-3 * ref + 1e-6).mean() > 0.999 and np.median(between / np.maximum(ref, 1e-30)) < 1e-5
+
+
+def test_reverse_vjp_device_api_ragged_and_position_independent(evaluator):
+    import torch
+
+    n = 40_013
+    raw = torch.from_numpy(synthetic.sample_training_distribution(n, seed=62).astype(np.float32)).cuda()
+    cot = torch.randn((198, n), dtype=torch.float32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5)).cuda()
+    for size in ("xsmall", "large", "xxlarge"):
+        values, grad = evaluator.evaluate_vjp_device(raw, cot, size)   # n >= 256: the reverse kernel
+        v_p, g_p = evaluator.evaluate_vjp_device(raw[:, perm].contiguous(), cot[:, perm].contiguous(), size, reverse=True)
+        torch.cuda.synchronize()
+        assert torch.equal(values, evaluator.evaluate_device(raw, size))
+        assert torch.equal(v_p, values[:, perm]) and torch.equal(g_p, grad[:, perm]), size
+        # cotangents of the six scalars only: the scalar-gradient kernel must agree to fp32 summation order
+        cot6 = torch.zeros_like(cot)
+        cot6[:6] = cot[:6]
+        _, g_full = evaluator.evaluate_vjp_device(raw, cot6, size, reverse=True)
+        _, g_scal = evaluator.evaluate_scalar_grad_device(raw, cot[:6].contiguous(), size, with_values=False)
+        torch.cuda.synchronize()
+        denom = g_scal.abs().amax(dim=1, keepdim=True) + 1e-30
+        assert float(((g_full - g_scal).abs() / denom).max()) < 1e-3, size
