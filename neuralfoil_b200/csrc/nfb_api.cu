@@ -120,6 +120,14 @@ using Grp64 = nfb::GroupCfg<64, NFB_GRP_KC_64, NFB_GRP_STAGES_64, NFB_TN_NARROW>
 #endif
 using Grp128 = nfb::GroupCfg<128, NFB_GRP_KC_128, NFB_GRP_STAGES_128, NFB_GRP_TN_128>;
 using Grp256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, NFB_TN_WIDE>;
+#ifndef NFB_GRAD_TN_128
+#define NFB_GRAD_TN_128 NFB_GRP_TN_128
+#endif
+using Grad128 = nfb::GroupCfg<128, NFB_GRP_KC_128, NFB_GRP_STAGES_128, NFB_GRAD_TN_128>;  // the reverse-mode kernels' 128-wide configuration
+#ifndef NFB_GRAD_TN_WIDE
+#define NFB_GRAD_TN_WIDE 8  // 16 warps hide the single-warp steps of the reverse pass better: xxxlarge +7 % (at 128: 8 x 16 tile -19 %)
+#endif
+using Grad256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, NFB_GRAD_TN_WIDE>;
 #ifndef NFB_GRP_STAGES_512
 #define NFB_GRP_STAGES_512 5
 #endif
@@ -127,6 +135,7 @@ using Grp256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, NFB_TN_WID
 #define NFB_GRP_LEAD_512 0
 #endif
 using Grp512 = nfb::GroupCfg<512, 8, NFB_GRP_STAGES_512, NFB_TN_WIDE, 16, NFB_GRP_LEAD_512>;
+using Grad512 = nfb::GroupCfg<512, 8, NFB_GRP_STAGES_512, NFB_GRAD_TN_WIDE, 16, NFB_GRP_LEAD_512>;
 
 struct HostSlot {  // one in-flight chunk of nfb_eval_host
   cudaStream_t stream = nullptr;
@@ -1052,9 +1061,9 @@ int grad_device_impl(nfb_context* ctx, bool full, int model_id, int64_t n, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (m.h_pad) {
     case 64: return full ? launch_grad<Grp64, true>(ctx, gp, st) : launch_grad<Grp64, false>(ctx, gp, st);
-    case 128: return full ? launch_grad<Grp128, true>(ctx, gp, st) : launch_grad<Grp128, false>(ctx, gp, st);
-    case 256: return full ? launch_grad<Grp256, true>(ctx, gp, st) : launch_grad<Grp256, false>(ctx, gp, st);
-    case 512: return full ? launch_grad<Grp512, true>(ctx, gp, st) : launch_grad<Grp512, false>(ctx, gp, st);
+    case 128: return full ? launch_grad<Grad128, true>(ctx, gp, st) : launch_grad<Grad128, false>(ctx, gp, st);
+    case 256: return full ? launch_grad<Grad256, true>(ctx, gp, st) : launch_grad<Grad256, false>(ctx, gp, st);
+    case 512: return full ? launch_grad<Grad512, true>(ctx, gp, st) : launch_grad<Grad512, false>(ctx, gp, st);
   }
   return fail(NFB_ERR_UNSUPPORTED_MODEL, "no kernel for padded width %d", m.h_pad);
 }
