@@ -692,6 +692,7 @@ void nfb_destroy(nfb_context* ctx) {
   cudaSetDevice(ctx->device);
   for (auto& m : ctx->models) {
     if (m.blob) cudaFree(m.blob);
+    if (m.grad_blob) cudaFree(m.grad_blob);
     if (m.tc_w) cudaFree(m.tc_w);
     if (m.tc3_w) cudaFree(m.tc3_w);
     if (m.tc2_w) cudaFree(m.tc2_w);
