@@ -101,11 +101,13 @@ __device__ __forceinline__ void bl_group_vjp(const EvalParams& p, const GradPara
       const float pu = exp10f(zt_u), pl = exp10f(zt_l);
       const float th_u = (pu - 0.1f) / (fabsf(zu_u) * re), th_l = (pl - 0.1f) / (fabsf(zu_l) * re);
       o[0][j] = th_u; o[1][j] = zu_u; o[2][j] = th_l; o[3][j] = zu_l;
-      const float g_ztu = ct[0][j] * 2.302585092994046f * pu / (fabsf(zu_u) * re);
-      const float g_zuu = ct[1][j] - ct[0][j] * th_u / zu_u;
-      const float g_ztl = ct[2][j] * 2.302585092994046f * pl / (fabsf(zu_l) * re);
-      const float g_zul = ct[3][j] - ct[2][j] * th_l / zu_l;
-      re_part[j] = -(ct[0][j] * th_u + ct[2][j] * th_l) / re;
+      // a zero cotangent contributes zero even where theta or its derivative is infinite (|ue| -> 0, 10^z overflow)
+      const bool cu = ct[0][j] != 0.0f, cl = ct[2][j] != 0.0f;
+      const float g_ztu = cu ? ct[0][j] * 2.302585092994046f * pu / (fabsf(zu_u) * re) : 0.0f;
+      const float g_zuu = ct[1][j] - (cu ? ct[0][j] * th_u / zu_u : 0.0f);
+      const float g_ztl = cl ? ct[2][j] * 2.302585092994046f * pl / (fabsf(zu_l) * re) : 0.0f;
+      const float g_zul = ct[3][j] - (cl ? ct[2][j] * th_l / zu_l : 0.0f);
+      re_part[j] = -((cu ? ct[0][j] * th_u : 0.0f) + (cl ? ct[2][j] * th_l : 0.0f)) / re;
       dl[0][j] = 0.5f * g_ztu; dl[2][4 + j] = 0.5f * g_ztu;
       dl[1][j] = 0.5f * g_zuu; dl[3][4 + j] = -0.5f * g_zuu;
       dl[2][j] = 0.5f * g_ztl; dl[0][4 + j] = 0.5f * g_ztl;
@@ -118,8 +120,8 @@ __device__ __forceinline__ void bl_group_vjp(const EvalParams& p, const GradPara
       o[1][j] = 2.6f * expf(0.5f * (yf[1][j] + yf[3][4 + j]));
       o[2][j] = 2.6f * expf(0.5f * (yf[2][j] + yf[0][4 + j]));
       o[3][j] = 2.6f * expf(0.5f * (yf[3][j] + yf[1][4 + j]));
-      const float g0 = 0.5f * ct[0][j] * o[0][j], g1 = 0.5f * ct[1][j] * o[1][j];
-      const float g2 = 0.5f * ct[2][j] * o[2][j], g3 = 0.5f * ct[3][j] * o[3][j];
+      const float g0 = ct[0][j] != 0.0f ? 0.5f * ct[0][j] * o[0][j] : 0.0f, g1 = ct[1][j] != 0.0f ? 0.5f * ct[1][j] * o[1][j] : 0.0f;
+      const float g2 = ct[2][j] != 0.0f ? 0.5f * ct[2][j] * o[2][j] : 0.0f, g3 = ct[3][j] != 0.0f ? 0.5f * ct[3][j] * o[3][j] : 0.0f;
       dl[0][j] = g0; dl[2][4 + j] = g0;
       dl[1][j] = g1; dl[3][4 + j] = g1;
       dl[2][j] = g2; dl[0][4 + j] = g2;
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
         // cotangents of z0..z5, then of the latents of the query (dq) and of its twin (dt)
         const float g0 = ct[0] * conf * (1.0f - conf);
         const float g1 = ct[1] * 0.5f;
-        const float g2 = ct[2] * 2.0f * cd;
+        const float g2 = ct[2] != 0.0f ? ct[2] * 2.0f * cd : 0.0f;  // CD = exp(.) may overflow far from the training data
         const float g3 = ct[3] / 20.0f;
         const float g4 = (z4 > 0.0f && z4 < 1.0f) ? ct[4] : 0.0f;
         const float g5 = (z5 > 0.0f && z5 < 1.0f) ? ct[5] : 0.0f;
@@ -431,6 +433,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           for (int i = 0; i < 6; ++i) {
             __stcg(dlat + size_t(SB::SCAL_ROW0 + i) * NC + c, dq[i]);
             __stcg(dlat + size_t(SB::SCAL_ROW0 + i) * NC + NQ + c, dt[i]);
+          }
+          // rows 198..207 are padding of the reverse sweep (zero weights): they must read as zero, never as whatever an
+          // earlier launch left in the scratch block (a NaN there would poison this column: NaN * 0)
+#pragma unroll
+          for (int i = 6; i < NB - SB::SCAL_ROW0; ++i) {
+            __stcg(dlat + size_t(SB::SCAL_ROW0 + i) * NC + c, 0.0f);
+            __stcg(dlat + size_t(SB::SCAL_ROW0 + i) * NC + NQ + c, 0.0f);
           }
         } else {
           const float* const sl = slopes + size_t(L - 2) * H * NC + c;

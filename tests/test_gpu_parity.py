@@ -874,3 +874,30 @@ def test_reverse_vjp_device_api_ragged_and_position_independent(evaluator):
         torch.cuda.synchronize()
         denom = g_scal.abs().amax(dim=1, keepdim=True) + 1e-30
         assert float(((g_full - g_scal).abs() / denom).max()) < 1e-3, size
+
+
+def test_reverse_kernels_contain_nan_queries(evaluator):
+    """A NaN / Re <= 0 query poisons its own gradient only: the columns of a tile are independent in the reverse pass too."""
+    import torch
+
+    n = 5_000
+    raw = synthetic.sample_training_distribution(n, seed=63).astype(np.float32)
+    bad = raw.copy()
+    bad[18, 5] = np.nan      # alpha
+    bad[19, 9] = -1.0        # Re <= 0 -> log(Re) = NaN in the reference, too
+    bad[3, 4000] = np.nan    # a Kulfan weight
+    poisoned = [5, 9, 4000]
+    cot = torch.randn((198, n), dtype=torch.float32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+    for size in ("medium", "xlarge"):
+        _, g_ref = evaluator.evaluate_vjp_device(torch.from_numpy(raw).cuda(), cot, size, reverse=True)
+        v_bad, g_bad = evaluator.evaluate_vjp_device(torch.from_numpy(bad).cuda(), cot, size, reverse=True)
+        _, s_ref = evaluator.evaluate_scalar_grad_device(torch.from_numpy(raw).cuda(), cot[:6].contiguous(), size, with_values=False)
+        _, s_bad = evaluator.evaluate_scalar_grad_device(torch.from_numpy(bad).cuda(), cot[:6].contiguous(), size, with_values=False)
+        torch.cuda.synchronize()
+        keep = torch.ones(n, dtype=torch.bool, device="cuda")
+        keep[poisoned] = False
+        assert torch.equal(g_bad[:, keep], g_ref[:, keep]) and torch.equal(s_bad[:, keep], s_ref[:, keep]), size
+        assert torch.isfinite(g_ref).all() and torch.isfinite(s_ref).all()
+        for q in poisoned:
+            assert not torch.isfinite(g_bad[:, q]).all() and not torch.isfinite(s_bad[:, q]).all(), (size, q)
+            assert torch.isnan(v_bad[1, q])
