@@ -651,7 +651,7 @@ int ensure(void** ptr, size_t* have, size_t need, bool pinned_host) {
 
 extern "C" {
 
-const char* nfb_version(void) { return "neuralfoil_b200 0.3 (sm_100a; fused evaluator: fp32 FFMA2, tcgen05 cta_group::2 fp16-operand variants, forward-mode Jacobian)"; }
+const char* nfb_version(void) { return "neuralfoil_b200 0.4 (sm_100a; fused evaluator: fp32 FFMA2 column groups, tcgen05 cta_group::2 fp16-operand variants, forward-mode Jacobian, fused reverse pass)"; }
 
 const char* nfb_last_error(void) { return g_err; }
 
