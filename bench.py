@@ -374,22 +374,25 @@ def main():
     # ---- the reverse-mode kernel: gradients of an objective of the six scalars, device-resident ----
     scalar_grad_extra = None
     if variant == "fp32" and not args.no_tensor_extra:
-        ng = min(n, 2_000_000)
-        rg = raw_dev[:, :ng].contiguous()
-        cot = torch.randn((6, ng), dtype=torch.float32, device="cuda")
-        for _ in range(2):
-            ev.evaluate_scalar_grad_device(rg, cot, size)
-        barrier()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0e.record()
-        for _ in range(3):
-            ev.evaluate_scalar_grad_device(rg, cot, size)
-        t1e.record()
-        barrier()
-        t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / 3
-        scalar_grad_extra = {"value": world * ng / (t_ms * 1e-3), "unit": "gradients/s", "queries_per_launch": ng, "ms_per_launch": t_ms,
-                             "kernel": "nfb_scalar_grad_kernel (fused forward + reverse pass, fp32 FFMA2; six scalar values + d objective / d 23 raw inputs per query)"}
-        del rg, cot
+        try:  # an extra: it must never cost the headline line
+            ng = min(n, 2_000_000)
+            rg = raw_dev[:, :ng].contiguous()
+            cot = torch.randn((6, ng), dtype=torch.float32, device="cuda")
+            for _ in range(2):
+                ev.evaluate_scalar_grad_device(rg, cot, size)
+            barrier()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(3):
+                ev.evaluate_scalar_grad_device(rg, cot, size)
+            t1e.record()
+            barrier()
+            t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / 3
+            scalar_grad_extra = {"value": world * ng / (t_ms * 1e-3), "unit": "gradients/s", "queries_per_launch": ng, "ms_per_launch": t_ms,
+                                 "kernel": "nfb_grad_kernel<., false> (fused forward + reverse pass, fp32 FFMA2; six scalar values + d objective / d 23 raw inputs per query)"}
+            del rg, cot
+        except Exception as e:  # noqa: BLE001
+            scalar_grad_extra = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
