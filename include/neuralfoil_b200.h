@@ -62,7 +62,29 @@ enum nfb_variant { NFB_VARIANT_FP32_FFMA = 0, NFB_VARIANT_TENSOR_FP16 = 1, NFB_V
  * query travel back over PCIe in nfb_eval_host, which is what bounds every model but the largest there. */
 #define NFB_OUTPUT_SCALARS 0x100
 
+/* Cross-check kernels, for tests and A/B measurements only; may be OR-ed into `variant`.  Both are complete, independent
+ * implementations of the same arithmetic that the parity tests hold against the production kernels.
+ *   NFB_DEBUG_FFMA_TILED  FP32_FFMA: the CTA-synchronous first implementation (nfb_ffma.cuh), for every batch size;
+ *                         must agree with the column-group kernels bit for bit.
+ *   NFB_DEBUG_TC_ONE_SM   TENSOR_*: the one-SM (cta_group::1) tcgen05 kernels (nfb_tc.cuh): same operands, another K order,
+ *                         so they agree with the CTA-pair kernels to the variant's tolerance, not bit for bit. */
+#define NFB_DEBUG_FFMA_TILED 0x1000
+#define NFB_DEBUG_TC_ONE_SM 0x2000
+#define NFB_VARIANT_FLAGS (NFB_OUTPUT_SCALARS | NFB_DEBUG_FFMA_TILED | NFB_DEBUG_TC_ONE_SM)
+
+#define NFB_VERSION "0.5.0"
+
 typedef struct nfb_context nfb_context;
+typedef struct nfb_multi nfb_multi;
+
+/* Threading contract.  A context serialises its own entry points with an internal mutex: any number of host threads may
+ * call into the same context, the *_host calls then run one after the other (they share the context's staging buffers and
+ * streams), the *_device calls hold the lock only while they enqueue.  The reverse-mode kernels (nfb_eval_scalar_grad_device,
+ * nfb_eval_vjp_reverse_device) share one scratch block per context: launches on different streams of one context are chained
+ * by an event, i.e. they are correct but do not overlap -- use one context per stream for concurrency.  Different contexts
+ * never share state (the distribution statistics travel in each launch's parameters), so one context per thread, per stream
+ * or per device needs no coordination at all.  The first reverse-mode call for a larger model or batch than any before
+ * allocates (cudaMalloc): warm the context up with one eager call of the same shape before capturing a CUDA graph. */
 
 /* Library / build identification (static string, never NULL). */
 const char* nfb_version(void);
@@ -74,6 +96,13 @@ const char* nfb_last_error(void);
  * import-time state (main.py:25-44).  Fails with NFB_ERR_NO_DEVICE when no sm_100 GPU is present. */
 int nfb_create(int device, nfb_context** out_ctx);
 void nfb_destroy(nfb_context* ctx);
+
+/* Tuning knobs for experiments and tests (the defaults are the measured optima):
+ *   NFB_TUNE_SMALL_BATCH_MAX  batches of at most `value` queries use the small-batch kernel (-1 = default per width)
+ *   NFB_TUNE_TC2_MAX_GRID     at most `value` CTAs (rounded down to whole pairs) for the CTA-pair tensor kernels (0 = all SMs)
+ *   NFB_TUNE_HOST_THREADS     at most `value` host threads stage pageable caller memory in nfb_eval_host (0 = all cores, max 32) */
+enum nfb_tuning { NFB_TUNE_SMALL_BATCH_MAX = 0, NFB_TUNE_TC2_MAX_GRID = 1, NFB_TUNE_HOST_THREADS = 2 };
+int nfb_set_tuning(nfb_context* ctx, int key, int64_t value);
 
 /* Number of SMs / device ordinal the context runs on. */
 int nfb_device_info(const nfb_context* ctx, int* device, int* sm_count, int* cc_major, int* cc_minor);
@@ -154,9 +183,43 @@ int nfb_eval_vjp_reverse_device(nfb_context* ctx, int model_id, int64_t n, const
                                 const int64_t* in_strides, int in_dtype, const void* cot, int64_t cot_ld,
                                 void* values, int64_t values_ld, void* grad, int64_t grad_ld, int out_dtype, void* stream);
 
+/* ---- several GPUs of one box behind one call (BASELINE configs[2] and [4]) ---------------------------------
+ * Queries are independent (main.py:198-201: every row of the stacked input is its own case) and the weights are a few MB,
+ * so the path shards by contiguous index range with NO collective: device i of G evaluates queries
+ * [i * ceil4(n / G), ...) -- nfb_shard_range -- with the replicated model and copies its results device->host straight
+ * into its own column range of the caller's single 198 x out_ld block.  The "host gather of outputs" is therefore free:
+ * when the call returns the block is complete.  One host thread per device drives that device's nfb_eval_host (its own
+ * streams and pinned staging buffers), pinned to the CPUs the device is attached to (sysfs local_cpulist) so that staging
+ * copies and first-touch page placement stay on the device's NUMA node.
+ *
+ * nfb_multi_create      `devices` = n_devices CUDA ordinals (NULL = every visible sm_100 device, n_devices ignored).
+ * nfb_multi_context     the i-th device's context (borrowed: do not destroy) for device-resident work on that GPU.
+ * nfb_multi_set_distribution / nfb_multi_load_model   as the single-device calls, applied to every device.
+ * nfb_multi_eval_host   as nfb_eval_host; bit-identical to the single-device result (a query's arithmetic does not depend
+ *                       on its position in a batch), for any n -- including n smaller than the number of devices.
+ * nfb_shard_range       the rule itself: [*begin, *end) of shard `index` of `count` over n queries; shard boundaries are
+ *                       multiples of 4 queries so that every shard's rows stay 16-byte aligned. */
+int nfb_multi_create(const int* devices, int n_devices, nfb_multi** out_multi);
+void nfb_multi_destroy(nfb_multi* multi);
+int nfb_multi_device_count(const nfb_multi* multi);
+nfb_context* nfb_multi_context(nfb_multi* multi, int index);
+int nfb_multi_set_distribution(nfb_multi* multi, const double* mean25, const double* inv_cov_25x25);
+int nfb_multi_load_model(nfb_multi* multi, int model_id, int n_layers, const int* dims,
+                         const float* const* weights, const float* const* biases);
+int nfb_multi_eval_host(nfb_multi* multi, int model_id, int variant, int64_t n,
+                        const void* const* in_rows, const int64_t* in_strides, int in_dtype,
+                        void* out, int64_t out_ld, int out_dtype, int64_t chunk);
+int nfb_shard_range(int64_t n, int index, int count, int64_t* begin, int64_t* end);
+int64_t nfb_multi_launch_count(const nfb_multi* multi);
+
 /* Pinned host memory helpers for callers without their own allocator. */
 int nfb_host_alloc(void** out_ptr, int64_t bytes);
 int nfb_host_free(void* ptr);
+/* Page-lock memory the caller already owns (cudaHostRegister, portable to every device) -- e.g. a POSIX shared-memory
+ * block that the ranks of a one-process-per-GPU job all map: each rank then copies its shard device->host straight into
+ * rank 0's result block (neuralfoil_b200/sharding.py: SharedHostBlock). */
+int nfb_host_register(void* ptr, int64_t bytes);
+int nfb_host_unregister(void* ptr);
 
 /* Number of kernel launches this context has enqueued so far (bench.py's `gpu_launches`). */
 int64_t nfb_launch_count(const nfb_context* ctx);

@@ -6,7 +6,7 @@ plus its three geometry front doors and `bl_x_points`.  Importing the package ne
 and raises if the library or a B200 is missing (there is no CPU fallback).
 """
 
-from .geometry import Airfoil  # noqa: F401
+from .geometry import Airfoil, KulfanAirfoil  # noqa: F401
 from .main import (  # noqa: F401
     JACOBIAN_INPUTS,
     MODEL_SIZES,
@@ -21,4 +21,4 @@ from .main import (  # noqa: F401
     output_keys,
 )
 
-__version__ = "0.1.0"
+__version__ = "0.5.0"  # == NFB_VERSION of include/neuralfoil_b200.h (tests/test_cabi_symbols.py)

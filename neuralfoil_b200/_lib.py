@@ -21,6 +21,10 @@ VARIANT_FP32_FFMA = 0
 VARIANT_TENSOR_FP16 = 1
 VARIANT_TENSOR_FP16X3 = 2
 OUTPUT_SCALARS = 0x100  # NFB_OUTPUT_SCALARS: OR-ed into the variant, only the six scalar rows are written
+DEBUG_FFMA_TILED = 0x1000  # cross-check kernels (tests / A-B only), OR-ed into the variant
+DEBUG_TC_ONE_SM = 0x2000
+DEBUG_FLAGS = {"ffma_tiled": DEBUG_FFMA_TILED, "tc_one_sm": DEBUG_TC_ONE_SM}
+TUNE_SMALL_BATCH_MAX, TUNE_TC2_MAX_GRID, TUNE_HOST_THREADS = 0, 1, 2
 N_SCALAR_ROWS = 6
 VARIANTS = {"fp32": VARIANT_FP32_FFMA, "tensor": VARIANT_TENSOR_FP16, "tensor_fp32": VARIANT_TENSOR_FP16X3}
 
@@ -78,8 +82,27 @@ _SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
          C.c_void_p, C.c_int64, C.c_void_p, C.c_int],
     ),
+    "nfb_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "nfb_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "nfb_multi_destroy": (None, [C.c_void_p]),
+    "nfb_multi_device_count": (C.c_int, [C.c_void_p]),
+    "nfb_multi_context": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "nfb_multi_set_distribution": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "nfb_multi_load_model": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)],
+    ),
+    "nfb_multi_eval_host": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+         C.c_void_p, C.c_int64, C.c_int, C.c_int64],
+    ),
+    "nfb_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nfb_multi_launch_count": (C.c_int64, [C.c_void_p]),
     "nfb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "nfb_host_free": (C.c_int, [C.c_void_p]),
+    "nfb_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "nfb_host_unregister": (C.c_int, [C.c_void_p]),
     "nfb_launch_count": (C.c_int64, [C.c_void_p]),
     "nfb_debug_tc_stamps": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]),
     "nfb_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),

@@ -9,8 +9,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <cctype>
+#include <mutex>
+#include <string>
 #include <thread>
+#include <unordered_set>
 #include <vector>
+
+#include <sched.h>
 
 #include "nfb_ffma.cuh"
 #include "nfb_ffma_groups.cuh"
@@ -155,15 +161,28 @@ struct nfb_context {
   int device = 0;
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
+  // Serialises every entry point that touches this context's mutable state (the host entry points' staging slots, the
+  // reverse-mode scratch block, the set of configured kernels).  Device entry points hold it only while they enqueue.
+  // Recursive: the host entry points call the device ones.
+  std::recursive_mutex mu;
   bool have_distribution = false;
+  double mean[nfb::N_IN] = {0};   // main.py:27-32; copied into every launch's parameters (nfb_common.cuh: EvalParams)
+  double quad[nfb::N_MAHA] = {0};
+  std::unordered_set<const void*> configured;  // kernels whose dynamic shared memory limit has been raised on this device
+  int64_t tune_small_batch_max = -1;  // nfb_set_tuning; -1 = the measured defaults
+  int tune_tc2_max_grid = 0;
+  int host_thread_cap = 0;            // 0 = all; nfb_multi_* divides the host cores among its devices
   Model models[NFB_MAX_MODELS];
   HostSlot slots[2];
-  void* grad_scratch = nullptr;  // nfb_eval_scalar_grad_device: SiLU slopes, one block per CTA
+  void* grad_scratch = nullptr;  // nfb_grad.cuh: SiLU slopes and parked cotangents, one block per CTA
   size_t grad_scratch_bytes = 0;
+  cudaEvent_t grad_event = nullptr;      // recorded behind the last launch that uses grad_scratch ...
+  cudaStream_t grad_stream = nullptr;    // ... on this stream: a launch on another stream waits for it first
+  bool grad_event_recorded = false;
   void* jac_dev = nullptr;   // nfb_eval_jacobian_host: [inputs | values | jac] device block and its pinned host mirror
   void* jac_host = nullptr;
   size_t jac_dev_bytes = 0, jac_host_bytes = 0;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};
   long long* tc_debug = nullptr;  // device buffer for nfb_debug_tc_stamps (64 x clock64), normally NULL
 };
 
@@ -357,14 +376,24 @@ std::vector<__half> pack_model_tc2(int L, const int* dims, const float* const* W
   return out;
 }
 
+// Raise a kernel's dynamic shared memory limit once per context (the attribute is per device and per function).
+template <class K>
+int configure(nfb_context* ctx, K kernel, size_t smem_bytes) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (ctx->configured.count(key)) return NFB_OK;
+  NFB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+  ctx->configured.insert(key);
+  return NFB_OK;
+}
+#define NFB_CONFIGURE(kernel, bytes)                          \
+  do {                                                        \
+    int rc_ = configure(ctx, kernel, bytes);                  \
+    if (rc_ != NFB_OK) return rc_;                            \
+  } while (0)
+
 template <class Cfg>
 int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
-  static thread_local int configured_device = -1;
-  if (configured_device != ctx->device) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_ffma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  int(Cfg::SMEM_BYTES)));
-    configured_device = ctx->device;
-  }
+  NFB_CONFIGURE(nfb::nfb_ffma_kernel<Cfg>, Cfg::SMEM_BYTES);
   const long long tiles = (p.n + Cfg::NQ - 1) / Cfg::NQ;
   const int grid = int(std::min<long long>(tiles, ctx->sm_count));
   nfb::nfb_ffma_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
@@ -375,12 +404,7 @@ int launch_ffma(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream)
 
 template <class Cfg>
 int launch_ffma_groups(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
-  static thread_local int configured_device = -1;
-  if (configured_device != ctx->device) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_ffma_groups_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  int(Cfg::SMEM_BYTES)));
-    configured_device = ctx->device;
-  }
+  NFB_CONFIGURE(nfb::nfb_ffma_groups_kernel<Cfg>, Cfg::SMEM_BYTES);
   const long long tiles = (p.n + Cfg::NQ - 1) / Cfg::NQ;
   const int grid = int(std::min<long long>(tiles, ctx->sm_count));
   nfb::nfb_ffma_groups_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(p);
@@ -394,43 +418,44 @@ int ensure(void** ptr, size_t* have, size_t need, bool pinned_host);
 template <class Cfg, bool FULL>
 int launch_grad(nfb_context* ctx, nfb::GradParams& gp, cudaStream_t stream) {
   using GC = nfb::GradCfg<Cfg>;
-  static thread_local int configured_device = -1;
-  if (configured_device != ctx->device) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_grad_kernel<Cfg, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  int(GC::SMEM_BYTES)));
-    configured_device = ctx->device;
-  }
+  NFB_CONFIGURE((nfb::nfb_grad_kernel<Cfg, FULL>), GC::SMEM_BYTES);
   const long long tiles = (gp.ev.n + Cfg::NQ - 1) / Cfg::NQ;
   const int grid = int(std::min<long long>(tiles, ctx->sm_count));
   const size_t need = size_t(grid) * nfb::grad_scratch_floats<Cfg::H, Cfg::NC>(gp.ev.n_layers, FULL) * sizeof(float);
+  // The scratch block belongs to the context, not to the stream: launches that use it are chained by an event, so two
+  // streams of one context cannot overwrite each other's slopes; concurrency needs one context per stream.
   if (need > ctx->grad_scratch_bytes) {
-    NFB_CUDA(cudaDeviceSynchronize());  // nothing may still read the old block
+    // Growing happens when a model or batch larger than any before comes along, never in steady state; cudaMalloc/cudaFree
+    // cannot be captured in a graph, so warm the context up with one eager call of the same shape before capturing.
+    if (ctx->grad_event_recorded) NFB_CUDA(cudaEventSynchronize(ctx->grad_event));  // nothing may still use the old block
     int rc = ensure(&ctx->grad_scratch, &ctx->grad_scratch_bytes, need, false);
     if (rc != NFB_OK) return rc;
-    // parked rows that no kernel writes (packed rows 198..207 of the narrow models) must read as zero, never as NaN
-    NFB_CUDA(cudaMemset(ctx->grad_scratch, 0, ctx->grad_scratch_bytes));
+    // parked rows that no kernel writes (packed rows 198..207 of the narrow models) must read as zero, never as NaN;
+    // on the caller's stream, i.e. ordered before the kernel below
+    NFB_CUDA(cudaMemsetAsync(ctx->grad_scratch, 0, ctx->grad_scratch_bytes, stream));
+    ctx->grad_event_recorded = false;
   }
+  if (!ctx->grad_event) NFB_CUDA(cudaEventCreateWithFlags(&ctx->grad_event, cudaEventDisableTiming));
+  if (ctx->grad_event_recorded && ctx->grad_stream != stream) NFB_CUDA(cudaStreamWaitEvent(stream, ctx->grad_event, 0));
   gp.scratch = static_cast<float*>(ctx->grad_scratch);
   nfb::nfb_grad_kernel<Cfg, FULL><<<grid, Cfg::THREADS, GC::SMEM_BYTES, stream>>>(gp);
   NFB_CUDA(cudaGetLastError());
+  NFB_CUDA(cudaEventRecord(ctx->grad_event, stream));
+  ctx->grad_event_recorded = true;
+  ctx->grad_stream = stream;
   ctx->launches += 1;
   return NFB_OK;
 }
 
 // Batches up to this size go to the small-batch kernel (4 queries per CTA); measured crossover, DESIGN.md section 6.
-int64_t small_batch_limit(int h_pad) {
-  static const char* env = getenv("NFB_SMALL_MAX");  // tuning experiments only
-  if (env) return atoll(env);
+int64_t small_batch_limit(const nfb_context* ctx, int h_pad) {
+  if (ctx->tune_small_batch_max >= 0) return ctx->tune_small_batch_max;  // nfb_set_tuning(NFB_TUNE_SMALL_BATCH_MAX)
   return h_pad >= 512 ? 512 : h_pad >= 256 ? 1024 : 2048;
 }
 
 template <class Cfg>
 int launch_tc(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream) {
-  static thread_local int configured_device = -1;
-  if (configured_device != ctx->device) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::tc::nfb_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
-    configured_device = ctx->device;
-  }
+  NFB_CONFIGURE(nfb::tc::nfb_tc_kernel<Cfg>, Cfg::SMEM_BYTES);
   const long long tiles = (tp.ev.n + Cfg::NQT - 1) / Cfg::NQT;
   const int grid = int(std::min<long long>((tiles + 1) & ~1LL, ctx->sm_count & ~1));  // whole CTA pairs
   nfb::tc::nfb_tc_kernel<Cfg><<<grid, nfb::tc::THREADS, Cfg::SMEM_BYTES, stream>>>(tp);
@@ -442,14 +467,9 @@ int launch_tc(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream
 // the tensor-core kernels on CTA pairs (nfb_tc2.cuh)
 template <class Cfg>
 int launch_tc2(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream) {
-  static thread_local int configured_device = -1;
-  if (configured_device != ctx->device) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::tc2::nfb_tc2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
-    configured_device = ctx->device;
-  }
+  NFB_CONFIGURE(nfb::tc2::nfb_tc2_kernel<Cfg>, Cfg::SMEM_BYTES);
   const long long tiles = (tp.ev.n + Cfg::NQT - 1) / Cfg::NQT;
-  static const char* grid_env = getenv("NFB_TC2_GRID");  // contention experiments only
-  const int max_grid = grid_env ? atoi(grid_env) : ctx->sm_count;
+  const int max_grid = ctx->tune_tc2_max_grid > 1 ? std::min(ctx->tune_tc2_max_grid, ctx->sm_count) : ctx->sm_count;  // NFB_TUNE_TC2_MAX_GRID
   const int grid = int(std::min<long long>((tiles + 1) & ~1LL, max_grid & ~1));  // whole CTA pairs
   nfb::tc2::nfb_tc2_kernel<Cfg><<<grid, nfb::tc2::THREADS2, Cfg::SMEM_BYTES, stream>>>(tp);
   NFB_CUDA(cudaGetLastError());
@@ -470,11 +490,7 @@ int launch_small(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream
 template <int H>
 int launch_jac(nfb_context* ctx, const nfb::JacParams& jp, cudaStream_t stream) {
   using Cfg = nfb::JacCfg<H>;
-  static thread_local int configured_device = -1;
-  if (configured_device != ctx->device) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::nfb_jac_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM_BYTES)));
-    configured_device = ctx->device;
-  }
+  NFB_CONFIGURE(nfb::nfb_jac_kernel<H>, Cfg::SMEM_BYTES);
   nfb::nfb_jac_kernel<H><<<unsigned(jp.ev.n), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(jp);  // one CTA per query
   NFB_CUDA(cudaGetLastError());
   ctx->launches += 1;
@@ -489,7 +505,7 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   if (!ctx->models[model_id].loaded) return fail(NFB_ERR_NOT_LOADED, "model slot %d is empty", model_id);
   if (!ctx->have_distribution)
     return fail(NFB_ERR_NOT_LOADED, "nfb_set_distribution has not been called");
-  variant &= ~NFB_OUTPUT_SCALARS;
+  variant &= ~NFB_VARIANT_FLAGS;
   if (variant != NFB_VARIANT_FP32_FFMA && variant != NFB_VARIANT_TENSOR_FP16 && variant != NFB_VARIANT_TENSOR_FP16X3)
     return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
   if (variant != NFB_VARIANT_FP32_FFMA && !ctx->models[model_id].tc_w)
@@ -509,11 +525,9 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   return NFB_OK;
 }
 
-int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
-                     const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
-                     cudaStream_t stream) {
-  const Model& m = ctx->models[model_id];
-  nfb::EvalParams p;
+// What every kernel's parameters share: the query rows, the model and the context's distribution statistics.
+void fill_eval_params(const nfb_context* ctx, const Model& m, const float* blob, int64_t n, const void* const* in_rows,
+                      const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype, nfb::EvalParams& p) {
   for (int i = 0; i < nfb::N_RAW; ++i) {
     p.in[i] = in_rows[i];
     p.in_stride[i] = in_strides[i];
@@ -521,18 +535,30 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
   p.out = out;
   p.out_ld = out_ld;
   p.n = n;
-  p.blob = m.blob;
+  p.blob = blob;
   p.n_layers = m.n_layers;
   p.k_hidden = m.k_hidden;
   p.in_f64 = (in_dtype == NFB_F64);
   p.out_f64 = (out_dtype == NFB_F64);
+  p.scalars_only = 0;
+  memcpy(p.mean, ctx->mean, sizeof(p.mean));
+  memcpy(p.quad, ctx->quad, sizeof(p.quad));
+}
+
+int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
+                     const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
+                     cudaStream_t stream) {
+  const Model& m = ctx->models[model_id];
+  nfb::EvalParams p;
+  fill_eval_params(ctx, m, m.blob, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype, p);
   p.scalars_only = (variant & NFB_OUTPUT_SCALARS) ? 1 : 0;
-  variant &= ~NFB_OUTPUT_SCALARS;
+  const bool one_sm = (variant & NFB_DEBUG_TC_ONE_SM) != 0;      // cross-check: the one-SM kernels of nfb_tc.cuh
+  const bool tiled_only = (variant & NFB_DEBUG_FFMA_TILED) != 0;  // cross-check: the CTA-synchronous kernel, every batch size
+  variant &= ~NFB_VARIANT_FLAGS;
   if (variant == NFB_VARIANT_TENSOR_FP16 || variant == NFB_VARIANT_TENSOR_FP16X3) {
     const bool x3 = (variant == NFB_VARIANT_TENSOR_FP16X3);
     nfb::tc::TcParams tp;
     tp.ev = p;
-    static const bool one_sm = getenv("NFB_TC_ONE_SM") != nullptr;  // A/B experiments: the one-SM kernels of nfb_tc.cuh
     tp.wblob = one_sm ? (x3 ? m.tc3_w : m.tc_w) : (x3 ? m.tc2_w3 : m.tc2_w);
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
@@ -546,7 +572,7 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
       return x3 ? launch_tc<nfb::tc::TcCfg<512, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<512, 1>>(ctx, tp, stream);
     return x3 ? launch_tc<nfb::tc::TcCfg<256, 3>>(ctx, tp, stream) : launch_tc<nfb::tc::TcCfg<256, 1>>(ctx, tp, stream);
   }
-  if (n <= small_batch_limit(m.h_pad)) {
+  if (!tiled_only && n <= small_batch_limit(ctx, m.h_pad)) {
     switch (m.h_pad) {
       case 64: return launch_small<64>(ctx, p, stream);
       case 128: return launch_small<128>(ctx, p, stream);
@@ -554,7 +580,6 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
       case 512: return launch_small<512>(ctx, p, stream);
     }
   }
-  static const bool tiled_only = getenv("NFB_FFMA_TILED") != nullptr;  // A/B: the CTA-synchronous kernel for every width
   if (!tiled_only) {
     switch (m.h_pad) {
       case 64: return launch_ffma_groups<Grp64>(ctx, p, stream);
@@ -579,17 +604,13 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
 // (first-touch page faults of a freshly allocated result included) and lets the GPU write float32 even when the
 // caller wants float64: the widening happens in that copy, and half the bytes cross PCIe.
 int host_threads() {
-  static const int n = [] {
-    const char* e = getenv("NFB_HOST_THREADS");
-    int v = e ? atoi(e) : int(std::thread::hardware_concurrency());
-    return std::max(1, std::min(v, 32));
-  }();
+  static const int n = std::max(1, std::min(int(std::thread::hardware_concurrency()), 32));
   return n;
 }
 
 template <class F>
 void parallel_units(int64_t units, F&& f, int max_threads = 1 << 30) {  // f(unit) for unit in [0, units), dynamically scheduled
-  const int nt = int(std::min<int64_t>(std::min(host_threads(), max_threads), units));
+  const int nt = int(std::min<int64_t>(std::min(host_threads(), std::max(1, max_threads)), units));
   if (nt <= 1) {
     for (int64_t u = 0; u < units; ++u) f(u);
     return;
@@ -617,9 +638,9 @@ bool is_pageable(const void* p) {
 constexpr int64_t STAGE_BLOCK = 1 << 16;  // elements per copy unit
 
 // rows x cn block of float32 in pinned memory (row stride src_ld) -> the caller's block (row stride dst_ld, float32 or float64)
-void unstage_output(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, bool dst_f64, int rows, int64_t cn) {
+void unstage_output(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, bool dst_f64, int rows, int64_t cn, int thread_cap) {
   const int64_t blocks = (cn + STAGE_BLOCK - 1) / STAGE_BLOCK;
-  const int max_threads = int(rows * cn / (1 << 19)) + 1;  // a thread costs ~30 us to start: one per 512 Ki elements
+  const int max_threads = std::min(thread_cap, int(rows * cn / (1 << 19)) + 1);  // a thread costs ~30 us to start: one per 512 Ki elements
   parallel_units(rows * blocks, [&](int64_t u) {
     const int64_t r = u / blocks, i0 = (u % blocks) * STAGE_BLOCK, i1 = std::min(cn, i0 + STAGE_BLOCK);
     const float* sp = src + r * src_ld;
@@ -651,7 +672,7 @@ int ensure(void** ptr, size_t* have, size_t need, bool pinned_host) {
 
 extern "C" {
 
-const char* nfb_version(void) { return "neuralfoil_b200 0.4 (sm_100a; fused evaluator: fp32 FFMA2 column groups, tcgen05 cta_group::2 fp16-operand variants, forward-mode Jacobian, fused reverse pass)"; }
+const char* nfb_version(void) { return "neuralfoil_b200 " NFB_VERSION " (sm_100a; fused evaluator: fp32 FFMA2 column groups, tcgen05 cta_group::2 fp16-operand variants, forward-mode Jacobian, fused reverse pass)"; }
 
 const char* nfb_last_error(void) { return g_err; }
 
@@ -714,6 +735,7 @@ void nfb_destroy(nfb_context* ctx) {
   if (ctx->tc_debug) cudaFree(ctx->tc_debug);
   if (ctx->jac_dev) cudaFree(ctx->jac_dev);
   if (ctx->grad_scratch) cudaFree(ctx->grad_scratch);
+  if (ctx->grad_event) cudaEventDestroy(ctx->grad_event);
   if (ctx->jac_host) cudaFreeHost(ctx->jac_host);
   delete ctx;
 }
@@ -729,14 +751,12 @@ int nfb_device_info(const nfb_context* ctx, int* device, int* sm_count, int* cc_
 
 int nfb_set_distribution(nfb_context* ctx, const double* mean25, const double* inv_cov) {
   if (!ctx || !mean25 || !inv_cov) return fail(NFB_ERR_INVALID_ARGUMENT, "NULL argument");
-  double quad[nfb::N_MAHA];
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   int idx = 0;
   for (int i = 0; i < nfb::N_IN; ++i)
     for (int j = i; j < nfb::N_IN; ++j)
-      quad[idx++] = (i == j) ? inv_cov[i * nfb::N_IN + i] : inv_cov[i * nfb::N_IN + j] + inv_cov[j * nfb::N_IN + i];
-  NFB_CUDA(cudaSetDevice(ctx->device));
-  NFB_CUDA(cudaMemcpyToSymbol(nfb::c_mean, mean25, sizeof(double) * nfb::N_IN));
-  NFB_CUDA(cudaMemcpyToSymbol(nfb::c_quad, quad, sizeof(quad)));
+      ctx->quad[idx++] = (i == j) ? inv_cov[i * nfb::N_IN + i] : inv_cov[i * nfb::N_IN + j] + inv_cov[j * nfb::N_IN + i];
+  memcpy(ctx->mean, mean25, sizeof(ctx->mean));
   ctx->have_distribution = true;
   return NFB_OK;
 }
@@ -768,6 +788,7 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
     case 256: blob = pack_model<256>(n_layers, dims, weights, biases); break;
     default: blob = pack_model<512>(n_layers, dims, weights, biases); break;
   }
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   NFB_CUDA(cudaSetDevice(ctx->device));
   Model& m = ctx->models[model_id];
   if (m.blob) {
@@ -830,6 +851,7 @@ int nfb_eval_device(nfb_context* ctx, int model_id, int variant, int64_t n, cons
                     void* stream) {
   int rc = check_eval_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype);
   if (rc != NFB_OK || n == 0) return rc;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   NFB_CUDA(cudaSetDevice(ctx->device));
   return eval_device_impl(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype,
                           static_cast<cudaStream_t>(stream));
@@ -840,7 +862,9 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
                   int64_t chunk) {
   int rc = check_eval_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype);
   if (rc != NFB_OK || n == 0) return rc;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);  // the staging slots below belong to the context
   NFB_CUDA(cudaSetDevice(ctx->device));
+  const int thread_cap = ctx->host_thread_cap > 0 ? ctx->host_thread_cap : (1 << 30);
   const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
   // Small batches (a design optimiser's per-iteration call): pack everything into one pinned block so
   // that there is exactly one H2D copy, one launch and one D2H copy.
@@ -870,7 +894,7 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
     if (!landed.slot) return NFB_OK;
     NFB_CUDA(cudaStreamSynchronize(landed.slot->stream));
     unstage_output(static_cast<const float*>(landed.slot->h_out), chunk, static_cast<char*>(out) + size_t(landed.c0) * osz,
-                   out_ld, out_dtype == NFB_F64, out_rows, landed.cn);
+                   out_ld, out_dtype == NFB_F64, out_rows, landed.cn, thread_cap);
     landed.slot = nullptr;
     return NFB_OK;
   };
@@ -918,7 +942,7 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
         } else {
           for (int64_t i = i0; i < i1; ++i) memcpy(dst + i * isz, src + size_t(c0 + i) * in_strides[r] * isz, isz);
         }
-      });
+      }, thread_cap);
       for (int r = 0; r < nfb::N_RAW; ++r) {
         d_rows[r] = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
         d_strides[r] = in_strides[r] == 0 ? 0 : 1;
@@ -950,7 +974,7 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
       NFB_CUDA(cudaMemcpyAsync(hs_out, s.d_out, dev_out_need, cudaMemcpyDeviceToHost, s.stream));
       NFB_CUDA(cudaStreamSynchronize(s.stream));
       if (small_widen) {
-        unstage_output(reinterpret_cast<const float*>(hs_out), chunk, out_c, out_ld, true, out_rows, cn);
+        unstage_output(reinterpret_cast<const float*>(hs_out), chunk, out_c, out_ld, true, out_rows, cn, thread_cap);
       } else {
         for (int r = 0; r < out_rows; ++r)
           memcpy(out_c + size_t(r) * out_ld * osz, hs_out + size_t(r) * chunk * osz, size_t(cn) * osz);
@@ -981,22 +1005,11 @@ int jacobian_device_impl(nfb_context* ctx, int model_id, int64_t n, const void* 
   if (!jac && !cot) return fail(NFB_ERR_INVALID_ARGUMENT, "jac is NULL");
   if (cot && (!grad || cot_ld < n || grad_ld < n)) return fail(NFB_ERR_INVALID_ARGUMENT, "VJP: grad is NULL or a leading dimension is smaller than n");
   if (n > (int64_t(1) << 30)) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld: the Jacobian kernel takes at most 2^30 queries per call", (long long)n);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   NFB_CUDA(cudaSetDevice(ctx->device));
   const Model& m = ctx->models[model_id];
   nfb::JacParams jp;
-  for (int i = 0; i < nfb::N_RAW; ++i) {
-    jp.ev.in[i] = in_rows[i];
-    jp.ev.in_stride[i] = in_strides[i];
-  }
-  jp.ev.out = values;
-  jp.ev.out_ld = values_ld;
-  jp.ev.n = n;
-  jp.ev.blob = m.blob;
-  jp.ev.n_layers = m.n_layers;
-  jp.ev.k_hidden = m.k_hidden;
-  jp.ev.in_f64 = (in_dtype == NFB_F64);
-  jp.ev.out_f64 = (out_dtype == NFB_F64);
-  jp.ev.scalars_only = 0;
+  fill_eval_params(ctx, m, m.blob, n, in_rows, in_strides, in_dtype, values, values_ld, out_dtype, jp.ev);
   jp.jac = jac;
   jp.cot = cot;
   jp.grad = grad;
@@ -1038,21 +1051,11 @@ int grad_device_impl(nfb_context* ctx, bool full, int model_id, int64_t n, const
   if (rc != NFB_OK || n == 0) return rc;
   if (!cot || !grad || cot_ld < n || grad_ld < n)
     return fail(NFB_ERR_INVALID_ARGUMENT, "reverse-mode gradient: cot or grad is NULL, or a leading dimension is smaller than n");
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   NFB_CUDA(cudaSetDevice(ctx->device));
   const Model& m = ctx->models[model_id];
   nfb::GradParams gp;
-  for (int i = 0; i < nfb::N_RAW; ++i) {
-    gp.ev.in[i] = in_rows[i];
-    gp.ev.in_stride[i] = in_strides[i];
-  }
-  gp.ev.out = values;
-  gp.ev.out_ld = values_ld;
-  gp.ev.n = n;
-  gp.ev.blob = m.grad_blob;
-  gp.ev.n_layers = m.n_layers;
-  gp.ev.k_hidden = m.k_hidden;
-  gp.ev.in_f64 = (in_dtype == NFB_F64);
-  gp.ev.out_f64 = (out_dtype == NFB_F64);
+  fill_eval_params(ctx, m, m.grad_blob, n, in_rows, in_strides, in_dtype, values, values_ld, out_dtype, gp.ev);
   gp.ev.scalars_only = full ? 0 : 1;
   gp.cot = cot;
   gp.grad = grad;
@@ -1093,6 +1096,7 @@ int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void
   if (rc != NFB_OK || n == 0) return rc;
   if (!jac) return fail(NFB_ERR_INVALID_ARGUMENT, "jac is NULL");
   if (n > (int64_t(1) << 22)) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld: at most 2^22 queries per host call (72 KB of derivatives each)", (long long)n);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   NFB_CUDA(cudaSetDevice(ctx->device));
   const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
   const int64_t ld = (n + 3) & ~int64_t(3);
@@ -1148,6 +1152,197 @@ int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void
   return NFB_OK;
 }
 
+int nfb_set_tuning(nfb_context* ctx, int key, int64_t value) {
+  if (!ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  switch (key) {
+    case NFB_TUNE_SMALL_BATCH_MAX: ctx->tune_small_batch_max = value; return NFB_OK;
+    case NFB_TUNE_TC2_MAX_GRID: ctx->tune_tc2_max_grid = int(value); return NFB_OK;
+    case NFB_TUNE_HOST_THREADS: ctx->host_thread_cap = int(std::max<int64_t>(0, value)); return NFB_OK;
+  }
+  return fail(NFB_ERR_INVALID_ARGUMENT, "unknown tuning key %d", key);
+}
+
+// ---- several devices behind one call ------------------------------------------------------------------------------
+int nfb_shard_range(int64_t n, int index, int count, int64_t* begin, int64_t* end) {
+  if (count < 1 || index < 0 || index >= count || n < 0 || !begin || !end)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "shard %d of %d over %lld queries", index, count, (long long)n);
+  const int64_t per = ((n + count - 1) / count + 3) & ~int64_t(3);  // ceil(n / count), rounded up to 4 queries
+  *begin = std::min<int64_t>(n, per * index);
+  *end = std::min<int64_t>(n, per * (index + 1));
+  return NFB_OK;
+}
+
+}  // extern "C"
+
+struct nfb_multi {
+  std::vector<nfb_context*> ctx;
+  std::vector<cpu_set_t> cpus;     // CPUs each device is attached to (empty set = unknown: no binding)
+  std::vector<bool> have_cpus;
+  std::mutex mu;                   // one multi-device call at a time
+};
+
+namespace {
+// CPUs local to a CUDA device: /sys/bus/pci/devices/<domain:bus:device.function>/local_cpulist ("0-31,64-95").
+bool device_local_cpus(int device, cpu_set_t* set) {
+  char bus_id[32] = "";
+  if (cudaDeviceGetPCIBusId(bus_id, sizeof(bus_id), device) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  for (char* c = bus_id; *c; ++c) *c = char(tolower(*c));
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus_id);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  char line[1024] = "";
+  const bool got = fgets(line, sizeof(line), f) != nullptr;
+  fclose(f);
+  if (!got) return false;
+  CPU_ZERO(set);
+  int n_set = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k < 1 || a < 0 || b < a) continue;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) {
+      CPU_SET(c, set);
+      ++n_set;
+    }
+  }
+  return n_set > 0;
+}
+}  // namespace
+
+extern "C" {
+
+int nfb_multi_create(const int* devices, int n_devices, nfb_multi** out_multi) {
+  if (!out_multi) return fail(NFB_ERR_INVALID_ARGUMENT, "out_multi is NULL");
+  *out_multi = nullptr;
+  std::vector<int> ids;
+  if (devices) {
+    if (n_devices < 1) return fail(NFB_ERR_INVALID_ARGUMENT, "n_devices = %d", n_devices);
+    ids.assign(devices, devices + n_devices);
+    for (size_t i = 0; i < ids.size(); ++i)
+      for (size_t j = 0; j < i; ++j)
+        if (ids[i] == ids[j]) return fail(NFB_ERR_INVALID_ARGUMENT, "device %d listed twice", ids[i]);
+  } else {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      return fail(NFB_ERR_NO_DEVICE, "no CUDA device visible (%s); neuralfoil_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    for (int d = 0; d < count; ++d) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ids.push_back(d);
+    }
+    if (ids.empty()) return fail(NFB_ERR_NO_DEVICE, "none of the %d visible devices is sm_100", count);
+  }
+  nfb_multi* m = new nfb_multi();
+  const int per_device_threads = std::max(2, host_threads() / int(ids.size()));
+  for (int d : ids) {
+    nfb_context* c = nullptr;
+    const int rc = nfb_create(d, &c);
+    if (rc != NFB_OK) {
+      nfb_multi_destroy(m);
+      return rc;
+    }
+    c->host_thread_cap = per_device_threads;
+    m->ctx.push_back(c);
+    cpu_set_t set;
+    const bool ok = device_local_cpus(d, &set);
+    m->cpus.push_back(set);
+    m->have_cpus.push_back(ok);
+  }
+  *out_multi = m;
+  return NFB_OK;
+}
+
+void nfb_multi_destroy(nfb_multi* multi) {
+  if (!multi) return;
+  for (nfb_context* c : multi->ctx) nfb_destroy(c);
+  delete multi;
+}
+
+int nfb_multi_device_count(const nfb_multi* multi) { return multi ? int(multi->ctx.size()) : 0; }
+
+nfb_context* nfb_multi_context(nfb_multi* multi, int index) {
+  if (!multi || index < 0 || index >= int(multi->ctx.size())) return nullptr;
+  return multi->ctx[index];
+}
+
+int nfb_multi_set_distribution(nfb_multi* multi, const double* mean25, const double* inv_cov) {
+  if (!multi) return fail(NFB_ERR_INVALID_ARGUMENT, "multi is NULL");
+  for (nfb_context* c : multi->ctx) {
+    const int rc = nfb_set_distribution(c, mean25, inv_cov);
+    if (rc != NFB_OK) return rc;
+  }
+  return NFB_OK;
+}
+
+int nfb_multi_load_model(nfb_multi* multi, int model_id, int n_layers, const int* dims, const float* const* weights,
+                         const float* const* biases) {
+  if (!multi) return fail(NFB_ERR_INVALID_ARGUMENT, "multi is NULL");
+  for (nfb_context* c : multi->ctx) {
+    const int rc = nfb_load_model(c, model_id, n_layers, dims, weights, biases);
+    if (rc != NFB_OK) return rc;
+  }
+  return NFB_OK;
+}
+
+int nfb_multi_eval_host(nfb_multi* multi, int model_id, int variant, int64_t n, const void* const* in_rows,
+                        const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype, int64_t chunk) {
+  if (!multi || multi->ctx.empty()) return fail(NFB_ERR_INVALID_ARGUMENT, "multi is NULL");
+  // argument errors are reported once, by the first device's checks, before any thread starts
+  int rc = check_eval_args(multi->ctx[0], model_id, variant, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype);
+  if (rc != NFB_OK || n == 0) return rc;
+  std::lock_guard<std::mutex> lock(multi->mu);
+  const int G = int(multi->ctx.size());
+  const size_t isz = in_dtype == NFB_F64 ? 8 : 4, osz = out_dtype == NFB_F64 ? 8 : 4;
+  std::vector<int> codes(G, NFB_OK);
+  std::vector<std::string> messages(G);
+  auto run_shard = [&](int g) {
+    int64_t b = 0, e = 0;
+    nfb_shard_range(n, g, G, &b, &e);
+    if (e <= b) return;
+    if (multi->have_cpus[g]) sched_setaffinity(0, sizeof(cpu_set_t), &multi->cpus[g]);  // this thread only; best effort
+    const void* rows[nfb::N_RAW];
+    for (int r = 0; r < nfb::N_RAW; ++r)
+      rows[r] = static_cast<const char*>(in_rows[r]) + size_t(b) * size_t(in_strides[r]) * isz;
+    codes[g] = nfb_eval_host(multi->ctx[g], model_id, variant, e - b, rows, in_strides, in_dtype,
+                             static_cast<char*>(out) + size_t(b) * osz, out_ld, out_dtype, chunk);
+    if (codes[g] != NFB_OK) messages[g] = g_err;  // the error text is thread-local: carry it to the caller's thread
+  };
+  {
+    std::vector<std::thread> workers;
+    workers.reserve(G);
+    for (int g = 0; g < G; ++g) workers.emplace_back(run_shard, g);  // fresh threads: the caller's affinity is untouched
+    for (auto& t : workers) t.join();
+  }
+  for (int g = 0; g < G; ++g)
+    if (codes[g] != NFB_OK) return fail(codes[g], "device %d: %s", multi->ctx[g]->device, messages[g].c_str());
+  return NFB_OK;
+}
+
+int64_t nfb_multi_launch_count(const nfb_multi* multi) {
+  int64_t total = 0;
+  if (multi)
+    for (const nfb_context* c : multi->ctx) total += c->launches.load();
+  return total;
+}
+
+int nfb_host_register(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return fail(NFB_ERR_INVALID_ARGUMENT, "bad argument");
+  NFB_CUDA(cudaHostRegister(ptr, size_t(bytes), cudaHostRegisterPortable));
+  return NFB_OK;
+}
+
+int nfb_host_unregister(void* ptr) {
+  if (ptr) NFB_CUDA(cudaHostUnregister(ptr));
+  return NFB_OK;
+}
+
 int nfb_host_alloc(void** out_ptr, int64_t bytes) {
   if (!out_ptr || bytes < 0) return fail(NFB_ERR_INVALID_ARGUMENT, "bad argument");
   *out_ptr = nullptr;
@@ -1161,7 +1356,7 @@ int nfb_host_free(void* ptr) {
   return NFB_OK;
 }
 
-int64_t nfb_launch_count(const nfb_context* ctx) { return ctx ? ctx->launches : 0; }
+int64_t nfb_launch_count(const nfb_context* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int nfb_debug_tc_stamps(nfb_context* ctx, int enable, long long* out64) {
   if (!ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "ctx is NULL");

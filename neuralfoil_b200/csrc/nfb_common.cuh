@@ -31,13 +31,15 @@ struct EvalParams {
   int out_f64;
   int scalars_only;            // NFB_OUTPUT_SCALARS: store rows 0..5 only (out is 6 x out_ld)
   int k_hidden;                // widest hidden layer rounded up to 16: rows of K beyond it are zero padding
+  // Mean (25) and packed symmetric quadratic form (325, off-diagonals pre-summed S_ij + S_ji) of the scaled-input
+  // distribution (reference main.py:27-32, 47-61).  They travel with every launch in the kernel parameter space --
+  // the constant bank, so the fp64 featurisation still reads them as constant operands -- and therefore belong to the
+  // CONTEXT that launches: two contexts on one device may hold different distributions (a __constant__ symbol, one
+  // copy per device, could not), and nothing is shared between threads or streams.
+  double mean[N_IN];
+  double quad[N_MAHA];
 };
-
-// Mean (25) and packed symmetric quadratic form (325, off-diagonals pre-summed S_ij + S_ji) of the
-// scaled-input distribution (reference main.py:27-32, 47-61).  One copy per device.
-// (Defined here, not extern: the library is a single translation unit, nfb_api.cu.)
-__constant__ double c_mean[N_IN];
-__constant__ double c_quad[N_MAHA];
+static_assert(sizeof(EvalParams) + 64 <= 4096, "EvalParams and its wrappers must fit the 4 KB kernel parameter space");
 
 // ---- Row permutation of the last layer -------------------------------------------------------
 // Packed row p = 4 * g + i of the last layer holds latent output row pack_last_layer_row(p)

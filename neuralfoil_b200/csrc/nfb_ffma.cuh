@@ -196,14 +196,14 @@ __device__ __forceinline__ void featurise_query(const EvalParams& p, long long q
   // (x - mu)^T S^-1 (x - mu) with the packed symmetric form
   double d[N_IN];
 #pragma unroll
-  for (int i = 0; i < N_IN; ++i) d[i] = x[i] - c_mean[i];
+  for (int i = 0; i < N_IN; ++i) d[i] = x[i] - p.mean[i];
   double d2 = 0.0;
   int idx = 0;
 #pragma unroll
   for (int i = 0; i < N_IN; ++i) {
     double t = 0.0;
 #pragma unroll
-    for (int j = i; j < N_IN; ++j) t = fma(c_quad[idx++], d[j], t);
+    for (int j = i; j < N_IN; ++j) t = fma(p.quad[idx++], d[j], t);
     d2 = fma(d[i], t, d2);
   }
   maha = static_cast<float>(d2 / (2.0 * N_IN));  // main.py:244-246

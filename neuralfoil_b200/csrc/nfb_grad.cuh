@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
         double xx[N_IN], gg[N_IN];
 #pragma unroll
         for (int i = 0; i < N_IN; ++i) xx[i] = tw ? xt[i] : x[i];
-        maha_gradient_regs(xx, gg);
+        maha_gradient_regs(p, xx, gg);
         const double mc = double(maha[tw * NQ + c]) / (2.0 * N_IN);
 #pragma unroll
         for (int k = 0; k < N_IN; ++k) {

@@ -45,15 +45,15 @@ struct JacCfg {
       sizeof(float) * (size_t(KMAX) * JAC_COLS + size_t(M_LAST) * JAC_COLS + JAC_COLS + 8) + sizeof(double) * 2 * N_IN;
 };
 
-// d2 = sum_i S_ii d_i^2 + sum_{i<j} Q_ij d_i d_j (c_quad: packed upper triangle, off-diagonals pre-summed):
+// d2 = sum_i S_ii d_i^2 + sum_{i<j} Q_ij d_i d_j (EvalParams::quad: packed upper triangle, off-diagonals pre-summed):
 // g_i = d d2 / d d_i = 2 S_ii d_i + sum_{j != i} Q_ij d_j.  Everything in registers: written as loops that index g[] at run time
 // it goes through local memory -- a 650-step dependent chain per query that nothing hides (it cost the reverse-mode kernel
 // of nfb_grad.cuh a factor 1.6 .. 2.9).
-__device__ __forceinline__ void maha_gradient_regs(const double (&x)[N_IN], double (&g)[N_IN]) {
+__device__ __forceinline__ void maha_gradient_regs(const EvalParams& p, const double (&x)[N_IN], double (&g)[N_IN]) {
   double d[N_IN];
 #pragma unroll
   for (int i = 0; i < N_IN; ++i) {
-    d[i] = x[i] - c_mean[i];
+    d[i] = x[i] - p.mean[i];
     g[i] = 0.0;
   }
   int idx = 0;
@@ -61,7 +61,7 @@ __device__ __forceinline__ void maha_gradient_regs(const double (&x)[N_IN], doub
   for (int i = 0; i < N_IN; ++i) {
 #pragma unroll
     for (int j = i; j < N_IN; ++j) {
-      const double q = c_quad[idx++];
+      const double q = p.quad[idx++];
       if (i == j) {
         g[i] = fma(2.0 * q, d[i], g[i]);
       } else {
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, (H <= 256) ? 2 : 1) nfb_ja
     if (!twin) re_s[0] = re;
     {
       double g[N_IN];
-      maha_gradient_regs(x, g);
+      maha_gradient_regs(p, x, g);
 #pragma unroll
       for (int k = 0; k < N_IN; ++k) grad[tid * N_IN + k] = g[k];
     }
@@ -303,7 +303,10 @@ __global__ void __launch_bounds__(JacCfg<H>::THREADS, (H <= 256) ? 2 : 1) nfb_ja
       float s = 0.0f;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (k < n_out) s = fmaf(cotangent(rows[k]), o[k], s);
+        if (k < n_out) {  // a zero cotangent contributes exactly zero even where the derivative is infinite (theta at ue -> 0):
+          const float ct = cotangent(rows[k]);  // the convention of the reverse-mode kernels (nfb_grad.cuh: bl_group_vjp)
+          if (ct != 0.0f) s = fmaf(ct, o[k], s);
+        }
       part[g * JAC_T + (c - 1)] = s;
       continue;
     }

@@ -171,3 +171,70 @@ class Airfoil:
         self.coordinates = np.asarray(coordinates, dtype=np.float64)
         if self.coordinates.ndim != 2 or self.coordinates.shape[1] != 2:
             raise ValueError("coordinates must have shape (N_points, 2)")
+
+
+def coordinates_from_kulfan_parameters(kulfan_parameters: dict, n_points_per_side: int = 200,
+                                       N1: float = 0.5, N2: float = 1.0) -> np.ndarray:
+    """Selig-ordered coordinates of a CST airfoil: the forward map of `kulfan_parameters_from_coordinates`."""
+    lower = np.asarray(kulfan_parameters["lower_weights"], dtype=np.float64)
+    upper = np.asarray(kulfan_parameters["upper_weights"], dtype=np.float64)
+    w_le = float(kulfan_parameters["leading_edge_weight"])
+    te = float(kulfan_parameters["TE_thickness"])
+    x = cosspace(0, 1, n_points_per_side)
+
+    def side(w, sign):
+        n = len(w)
+        deg = n - 1
+        k = np.array([comb(deg, i) for i in range(n)], dtype=np.float64)
+        i_arr = np.arange(n)
+        bern = k[None, :] * x[:, None] ** i_arr[None, :] * (1 - x[:, None]) ** (deg - i_arr[None, :])
+        return x**N1 * (1 - x) ** N2 * (bern @ w) + w_le * x * (1 - x) ** (n + 0.5) + sign * te * x / 2
+
+    yu, yl = side(upper, +1.0), side(lower, -1.0)
+    return np.stack([np.concatenate([x[::-1], x[1:]]), np.concatenate([yu[::-1], yl[1:]])], axis=1)
+
+
+class KulfanAirfoil:
+    """
+    The little of `aerosandbox.KulfanAirfoil` the reference's `get_aero_from_airfoil` uses (main.py:336,361-364): an
+    airfoil defined by its CST parameters.  `coordinates` are generated on demand.
+    """
+
+    def __init__(self, name: str = "Untitled", lower_weights=None, upper_weights=None, leading_edge_weight: float = 0.0,
+                 TE_thickness: float = 0.0):
+        self.name = name
+        self.lower_weights = np.asarray(lower_weights, dtype=np.float64)
+        self.upper_weights = np.asarray(upper_weights, dtype=np.float64)
+        self.leading_edge_weight = float(leading_edge_weight)
+        self.TE_thickness = float(TE_thickness)
+
+    @property
+    def kulfan_parameters(self) -> dict:
+        return {"lower_weights": self.lower_weights, "upper_weights": self.upper_weights,
+                "leading_edge_weight": self.leading_edge_weight, "TE_thickness": self.TE_thickness}
+
+    @property
+    def coordinates(self) -> np.ndarray:
+        return coordinates_from_kulfan_parameters(self.kulfan_parameters)
+
+
+def kulfan_parameters_of(airfoil):
+    """
+    The CST parameters of a Kulfan-parameterised airfoil object if they can be used as they are -- a `kulfan_parameters`
+    mapping with 8 weights per side -- else None (the caller then fits the object's coordinates).
+    """
+    params = getattr(airfoil, "kulfan_parameters", None)
+    if params is None:
+        return None
+    try:
+        ok = len(params["upper_weights"]) == N_WEIGHTS_PER_SIDE and len(params["lower_weights"]) == N_WEIGHTS_PER_SIDE
+    except (KeyError, TypeError):
+        ok = False
+    if not ok:
+        if not hasattr(airfoil, "coordinates"):
+            raise ValueError(
+                "NeuralFoil's neural networks expect exactly 8 CST weights per side; this airfoil has another resolution "
+                "and no coordinates to refit."
+            )
+        return None
+    return {k: params[k] for k in ("lower_weights", "upper_weights", "leading_edge_weight", "TE_thickness")}

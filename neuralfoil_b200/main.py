@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -134,19 +135,53 @@ def prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower)
 
 class Evaluator:
     """
-    One CUDA context's worth of state: the distribution statistics and every network, repacked and
-    resident on the GPU.  Mirrors the reference's import-time globals (main.py:25-44).
+    The distribution statistics and every network, repacked and resident on one GPU -- or replicated on several GPUs
+    of one box.  Mirrors the reference's import-time globals (main.py:25-44).
+
+    `device`   one CUDA ordinal (default: $NEURALFOIL_B200_DEVICE, else $LOCAL_RANK, else 0).
+    `devices`  "all" or a list of ordinals: the host entry points (`get_aero_from_kulfan_parameters`, `evaluate_host`,
+               `evaluate_host_into`) split batches of at least `multi_threshold` queries into contiguous shards, one per
+               GPU, and every GPU copies its results straight into its column range of the one result block
+               (include/neuralfoil_b200.h: nfb_multi_eval_host).  The values are bit-identical to the
+               single-GPU ones.  Device-resident calls (`evaluate_device`, ...) run on the first device of the list.
+               "auto" = one device now; the others join the first time a batch is large enough to need them.
+
+    Threading: one Evaluator may be shared by any number of Python threads -- the library serialises the calls into a
+    context ("Threading"); use one Evaluator per thread for concurrency.
     """
 
-    def __init__(self, device: int | None = None, weights_dir: Path | str | None = None, extra_models=None):
+    def __init__(self, device: int | None = None, weights_dir: Path | str | None = None, extra_models=None,
+                 devices=None, multi_threshold: int = 1 << 18):
         self._lib = _lib.load()
-        if device is None:
-            device = int(os.environ.get("NEURALFOIL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-        self.device = int(device)
         self.weights_dir = Path(weights_dir) if weights_dir is not None else nn_weights_dir
+        self.multi_threshold = int(multi_threshold)
+        self._multi = None          # nfb_multi handle when this evaluator spans several devices
+        self._auto_multi = None     # devices="auto": the lazily created multi-device twin of this evaluator
+        self._auto = devices == "auto"
+        self._extra_models = dict(extra_models or {})
+        self._lock = threading.Lock()
         handle = C.c_void_p()
-        _lib.check(self._lib.nfb_create(self.device, C.byref(handle)))
-        self._ctx = handle
+        if devices is not None and not self._auto:
+            if device is not None:
+                raise ValueError("give either `device` or `devices`")
+            if isinstance(devices, str):
+                if devices != "all":
+                    raise ValueError(f"Invalid {devices=}. Must be 'all', 'auto' or a list of CUDA ordinals.")
+                _lib.check(self._lib.nfb_multi_create(None, 0, C.byref(handle)))
+            else:
+                ids = [int(d) for d in devices]
+                _lib.check(self._lib.nfb_multi_create((C.c_int * len(ids))(*ids), len(ids), C.byref(handle)))
+            self._multi = handle
+            self.n_devices = int(self._lib.nfb_multi_device_count(self._multi))
+            self._ctx = C.c_void_p(self._lib.nfb_multi_context(self._multi, 0))
+            self.device = self.device_info()["device"]
+        else:
+            if device is None:
+                device = int(os.environ.get("NEURALFOIL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            self.device = int(device)
+            _lib.check(self._lib.nfb_create(self.device, C.byref(handle)))
+            self._ctx = handle
+            self.n_devices = 1
         self._model_ids: dict[str, int] = {}
         self.model_dims: dict[str, list[int]] = {}
 
@@ -155,9 +190,11 @@ class Evaluator:
             inv_cov = np.ascontiguousarray(f["inv_cov_inputs_scaled"], dtype=np.float64)
         if mean.shape != (25,) or inv_cov.shape != (25, 25):
             raise ValueError("scaled_input_distribution.npz does not describe 25 inputs.")
+        set_distribution = self._lib.nfb_multi_set_distribution if self._multi else self._lib.nfb_set_distribution
         _lib.check(
-            self._lib.nfb_set_distribution(
-                self._ctx, mean.ctypes.data_as(C.POINTER(C.c_double)), inv_cov.ctypes.data_as(C.POINTER(C.c_double))
+            set_distribution(
+                self._multi or self._ctx, mean.ctypes.data_as(C.POINTER(C.c_double)),
+                inv_cov.ctypes.data_as(C.POINTER(C.c_double)),
             )
         )
         for path in sorted(self.weights_dir.glob("nn-*.npz")):  # main.py:35-44
@@ -180,17 +217,62 @@ class Evaluator:
         w_ptrs = (C.c_void_p * n)(*[w.ctypes.data for w, _ in layers])
         b_ptrs = (C.c_void_p * n)(*[b.ctypes.data for _, b in layers])
         c_dims = (C.c_int * (n + 1))(*dims)
-        _lib.check(self._lib.nfb_load_model(self._ctx, model_id, n, c_dims, w_ptrs, b_ptrs))
+        load = self._lib.nfb_multi_load_model if self._multi else self._lib.nfb_load_model
+        _lib.check(load(self._multi or self._ctx, model_id, n, c_dims, w_ptrs, b_ptrs))
         self._model_ids[name] = model_id
         self.model_dims[name] = dims
+        if name not in self._extra_models and not (self.weights_dir / f"nn-{name}.npz").exists():
+            self._extra_models[name] = nn_params  # so that a lazily created multi-device twin gets it too
+        if self._auto_multi is not None:
+            self._auto_multi.load_model(name, nn_params)
 
     @staticmethod
     def _variant(variant: str) -> int:
-        """"fp32" = FFMA kernel (reference accuracy); "tensor" = tcgen05 fp16-operand kernel (512-wide models only)."""
+        """
+        "fp32" = FFMA kernel (reference accuracy); "tensor" / "tensor_fp32" = the tcgen05 kernels (one fp16 MMA per
+        product / three-term fp16 split).  A suffix selects a cross-check kernel (tests and A/B only): "fp32:tiled" the
+        CTA-synchronous fp32 kernel, "tensor:one_sm" / "tensor_fp32:one_sm" the one-SM tensor kernels.
+        """
+        name, _, debug = variant.partition(":")
         try:
-            return _lib.VARIANTS[variant]
+            code = _lib.VARIANTS[name]
+            if debug:
+                code |= {"tiled": _lib.DEBUG_FFMA_TILED, "one_sm": _lib.DEBUG_TC_ONE_SM}[debug]
+            return code
         except KeyError:
             raise ValueError(f"Invalid {variant=}. Must be one of {set(_lib.VARIANTS)}.") from None
+
+    def set_tuning(self, small_batch_max: int | None = None, tc2_max_grid: int | None = None,
+                   host_threads: int | None = None) -> None:
+        """Experiment knobs of include/neuralfoil_b200.h (nfb_set_tuning); the defaults are the measured optima."""
+        for key, value in ((_lib.TUNE_SMALL_BATCH_MAX, small_batch_max), (_lib.TUNE_TC2_MAX_GRID, tc2_max_grid),
+                           (_lib.TUNE_HOST_THREADS, host_threads)):
+            if value is not None:
+                _lib.check(self._lib.nfb_set_tuning(self._ctx, key, int(value)))
+
+    def _host_target(self, n: int):
+        """(entry point, handle) for a host-side evaluation of n queries: several devices when there are enough queries."""
+        if n >= self.multi_threshold:
+            if self._multi is not None and self.n_devices > 1:
+                return self._lib.nfb_multi_eval_host, self._multi
+            if self._auto:
+                twin = self._multi_twin()
+                if twin is not None:
+                    return self._lib.nfb_multi_eval_host, twin._multi
+        return self._lib.nfb_eval_host, self._ctx
+
+    def _multi_twin(self):
+        """devices="auto": the all-devices evaluator, created the first time a batch is large enough (None on a one-GPU box)."""
+        with self._lock:
+            if self._auto_multi is None:
+                twin = Evaluator(devices="all", weights_dir=self.weights_dir, extra_models=self._extra_models,
+                                 multi_threshold=self.multi_threshold)
+                if twin.n_devices < 2:
+                    twin.close()
+                    self._auto = False
+                    return None
+                self._auto_multi = twin
+            return self._auto_multi
 
     @staticmethod
     def _rows_and_flag(outputs: str) -> tuple[int, int]:
@@ -259,8 +341,9 @@ class Evaluator:
         Enqueues on torch's current stream; does not synchronise."""
         import torch
 
-        if not isinstance(raw, torch.Tensor) or raw.dim() != 2 or raw.shape[0] != _lib.N_RAW_ROWS or not raw.is_cuda:
-            raise ValueError("raw must be a (23, N) CUDA tensor")
+        if (not isinstance(raw, torch.Tensor) or raw.dim() != 2 or raw.shape[0] != _lib.N_RAW_ROWS or not raw.is_cuda
+                or raw.device.index != self.device):
+            raise ValueError(f"raw must be a (23, N) tensor on cuda:{self.device}")
         if raw.dtype not in (torch.float32, torch.float64) or raw.stride(1) != 1:
             raise ValueError("raw must be float32 or float64 with contiguous rows")
         n = int(raw.shape[1])
@@ -293,8 +376,9 @@ class Evaluator:
         import torch
 
         for name, t, rows in (("raw", raw, _lib.N_RAW_ROWS), ("cotangent", cotangent, _lib.N_OUTPUT_ROWS)):
-            if not isinstance(t, torch.Tensor) or t.dim() != 2 or t.shape[0] != rows or not t.is_cuda or t.stride(1) != 1:
-                raise ValueError(f"{name} must be a ({rows}, N) CUDA tensor with contiguous rows")
+            if (not isinstance(t, torch.Tensor) or t.dim() != 2 or t.shape[0] != rows or not t.is_cuda
+                    or t.device.index != self.device or t.stride(1) != 1):
+                raise ValueError(f"{name} must be a ({rows}, N) tensor on cuda:{self.device} with contiguous rows")
             if t.dtype not in (torch.float32, torch.float64):
                 raise ValueError(f"{name} must be float32 or float64")
         n = int(raw.shape[1])
@@ -331,8 +415,9 @@ class Evaluator:
         import torch
 
         for name, t, rows in (("raw", raw, _lib.N_RAW_ROWS), ("cotangent", cotangent, _lib.N_SCALAR_ROWS)):
-            if not isinstance(t, torch.Tensor) or t.dim() != 2 or t.shape[0] != rows or not t.is_cuda or t.stride(1) != 1:
-                raise ValueError(f"{name} must be a ({rows}, N) CUDA tensor with contiguous rows")
+            if (not isinstance(t, torch.Tensor) or t.dim() != 2 or t.shape[0] != rows or not t.is_cuda
+                    or t.device.index != self.device or t.stride(1) != 1):
+                raise ValueError(f"{name} must be a ({rows}, N) tensor on cuda:{self.device} with contiguous rows")
             if t.dtype not in (torch.float32, torch.float64):
                 raise ValueError(f"{name} must be float32 or float64")
         n = int(raw.shape[1])
@@ -411,9 +496,10 @@ class Evaluator:
             raise ValueError(f"out must be a ({n_rows}, >=N) float32/float64 array with contiguous rows")
         ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].ctypes.data for i in range(_lib.N_RAW_ROWS)])
         strides = (C.c_int64 * _lib.N_RAW_ROWS)(*([1] * _lib.N_RAW_ROWS))
+        entry, handle = self._host_target(n)
         _lib.check(
-            self._lib.nfb_eval_host(
-                self._ctx, self._model_id(model_size), self._variant(variant) | flag, n, ptrs, strides,
+            entry(
+                handle, self._model_id(model_size), self._variant(variant) | flag, n, ptrs, strides,
                 _lib.F64 if raw.dtype == np.float64 else _lib.F32,
                 out.ctypes.data_as(C.c_void_p), out.strides[0] // out.itemsize,
                 _lib.F64 if out.dtype == np.float64 else _lib.F32, chunk,
@@ -444,9 +530,10 @@ class Evaluator:
             ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[r.__array_interface__["data"][0] for r in rows])
             strides = (C.c_int64 * _lib.N_RAW_ROWS)(*[0 if r.size == 1 and n > 1 else 1 for r in rows])
             in_code = _lib.F64 if in_dtype == np.float64 else _lib.F32
+        entry, handle = self._host_target(n)
         _lib.check(
-            self._lib.nfb_eval_host(
-                self._ctx, model_id, self._variant(variant) | flag, n, ptrs, strides, in_code,
+            entry(
+                handle, model_id, self._variant(variant) | flag, n, ptrs, strides, in_code,
                 block.__array_interface__["data"][0], ld,
                 _lib.F64 if block.dtype == np.float64 else _lib.F32, chunk,
             )
@@ -494,6 +581,9 @@ class Evaluator:
         if out is None:
             out = torch.empty((n_rows, ld), dtype=out_dtype, device=f"cuda:{self.device}")
         else:
+            if (not isinstance(out, torch.Tensor) or not out.is_cuda or out.device.index != self.device
+                    or out.dtype not in (torch.float32, torch.float64)):
+                raise ValueError(f"out must be a float32 or float64 tensor on cuda:{self.device}")
             if out.dim() != 2 or out.shape[0] != n_rows or out.shape[1] < n or out.stride(1) != 1:
                 raise ValueError(f"out must be a ({n_rows}, >=N) tensor with contiguous rows")
             ld = int(out.stride(0))
@@ -512,7 +602,9 @@ class Evaluator:
 
     # -- measurement helpers -----------------------------------------------------------------------
     def launch_count(self) -> int:
-        return int(self._lib.nfb_launch_count(self._ctx))
+        """Kernel launches so far, on every device of this evaluator (and of its lazily created multi-device twin)."""
+        own = self._lib.nfb_multi_launch_count(self._multi) if self._multi else self._lib.nfb_launch_count(self._ctx)
+        return int(own) + (self._auto_multi.launch_count() if self._auto_multi is not None else 0)
 
     def device_info(self) -> dict:
         vals = [C.c_int() for _ in range(4)]
@@ -525,7 +617,14 @@ class Evaluator:
         return out.value
 
     def close(self) -> None:
-        if getattr(self, "_ctx", None):
+        if getattr(self, "_auto_multi", None) is not None:
+            self._auto_multi.close()
+            self._auto_multi = None
+        if getattr(self, "_multi", None):
+            self._lib.nfb_multi_destroy(self._multi)  # owns its contexts
+            self._multi = None
+            self._ctx = None
+        elif getattr(self, "_ctx", None):
             self._lib.nfb_destroy(self._ctx)
             self._ctx = None
 
@@ -546,10 +645,16 @@ class Evaluator:
         """
         from . import geometry
 
-        if hasattr(airfoil, "kulfan_parameters") and not hasattr(airfoil, "coordinates"):
-            raise ValueError("pass Kulfan parameters to get_aero_from_kulfan_parameters directly")
-        nrm = geometry.normalize(np.asarray(airfoil.coordinates, dtype=np.float64))
-        kulfan = geometry.kulfan_parameters_from_coordinates(nrm["coordinates"])
+        kulfan = geometry.kulfan_parameters_of(airfoil)
+        if kulfan is not None:
+            # A Kulfan-parameterised airfoil (`geometry.KulfanAirfoil`, `aerosandbox.KulfanAirfoil`: main.py:336) with the
+            # networks' 8 + 8 weights: by construction its leading edge is at (0, 0) and its chord is the unit x axis, so the
+            # reference's normalize() is the identity (rotation 0, scale 1, no translation) and its refit returns the same
+            # parameters up to least-squares noise -- the parameters are used as they are.
+            nrm = {"x_translation": 0.0, "y_translation": 0.0, "scale_factor": 1.0, "rotation_angle": 0.0}
+        else:
+            nrm = geometry.normalize(np.asarray(airfoil.coordinates, dtype=np.float64))
+            kulfan = geometry.kulfan_parameters_from_coordinates(nrm["coordinates"])
         delta_alpha, scale = nrm["rotation_angle"], nrm["scale_factor"]
         x_qc = -nrm["x_translation"] + 0.25 * (1.0 / scale * np.cos(np.radians(delta_alpha))) - 0.25
         y_qc = -nrm["y_translation"] + 0.25 * (1.0 / scale * np.sin(np.radians(-delta_alpha)))
@@ -579,14 +684,27 @@ class Evaluator:
 
 
 _default: Evaluator | None = None
+_default_lock = threading.Lock()
 
 
 def default_evaluator() -> Evaluator:
-    """The process-wide evaluator the module-level functions use (created on first call)."""
+    """
+    The process-wide evaluator the module-level functions use (created on first call; safe to call from any thread).
+    $NEURALFOIL_B200_DEVICES = "all" or "0,1,..." replicates it on several GPUs from the start.  Otherwise it lives on one
+    GPU -- $NEURALFOIL_B200_DEVICE, else $LOCAL_RANK (one process per GPU under torchrun) -- and, when neither is set,
+    brings in the box's other GPUs the first time a call carries at least 262,144 queries (`devices="auto"`).
+    """
     global _default
-    if _default is None:
-        _default = Evaluator()
-    return _default
+    with _default_lock:
+        if _default is None:
+            spec = os.environ.get("NEURALFOIL_B200_DEVICES")
+            if spec:
+                _default = Evaluator(devices="all" if spec == "all" else [int(d) for d in spec.split(",")])
+            elif "NEURALFOIL_B200_DEVICE" in os.environ or "LOCAL_RANK" in os.environ:
+                _default = Evaluator()
+            else:
+                _default = Evaluator(device=0, devices="auto")
+        return _default
 
 
 def get_aero_from_kulfan_parameters(

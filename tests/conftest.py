@@ -14,6 +14,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """Leave the worst parity figures of this session where gpurun brings them back (tests/parity.py: MAXIMA)."""
+    import json
+
+    try:
+        import parity
+    except ImportError:
+        return
+    if parity.MAXIMA:
+        out = REPO / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        (out / "parity_maxima.json").write_text(json.dumps(parity.MAXIMA, indent=1, sort_keys=True))
+
+
 def _extra_models():
     """Seeded synthetic xxxlarge unless a real nn-xxxlarge.npz has been dropped into the weights dir."""
     from neuralfoil_b200 import synthetic

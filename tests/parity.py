@@ -62,6 +62,7 @@ def _tau(out: np.ndarray, Re: np.ndarray) -> np.ndarray:
 # the 32 accumulation steps of a 512-long dot product where FFMA rounds to nearest: measured median relative error
 # 1.6e-6 (trained xxlarge) .. 4.1e-6 (synthetic xxxlarge), 84 .. 92 % of elements within rtol 1e-5.  Stated distribution
 # bound for this variant: median relative error <= 1e-5 (BASELINE.json's figure), >= 75 % of elements within rtol 1e-5.
+TENSOR_FP32_LATENT_ATOL = 2.5e-4
 TENSOR_FP32_MEDIAN_REL = 1e-5
 TENSOR_FP32_FRAC_1E5 = 0.75
 
@@ -112,17 +113,40 @@ def error_report(got: np.ndarray, want: np.ndarray, Re: np.ndarray, latent_atol:
     }
 
 
-def assert_parity(got, want, Re, check_distribution: bool = True, label: str = "", variant: str = "fp32") -> dict:
+# Every comparison made in a test session leaves its worst figures here; tests/conftest.py writes them to
+# gpurun_out/parity_maxima.json at the end of a GPU session (the tolerances above are set from that record:
+# profiles/r2_parity_maxima.json).
+MAXIMA: dict[str, dict] = {}
+
+
+def _record(kind: str, rep: dict, keys) -> None:
+    slot = MAXIMA.setdefault(kind, {"comparisons": 0})
+    slot["comparisons"] += 1
+    for k in keys:
+        v = rep.get(k)
+        if v is None or not np.isfinite(v):
+            continue
+        worst = min if k.startswith("frac_rel") else max
+        slot[k] = v if k not in slot else worst(slot[k], v)
+
+
+def assert_parity(got, want, Re, check_distribution: bool | None = None, label: str = "", variant: str = "fp32") -> dict:
+    """check_distribution: None = on for blocks of at least 1,000 queries (statistics of a handful of queries say little)."""
     re = np.broadcast_to(np.asarray(Re, dtype=np.float64), (np.shape(want)[1],))
+    big = np.shape(want)[1] >= 1000
+    if check_distribution is None:
+        check_distribution = big
     if variant == "tensor":
         rep = error_report(got, want, re, latent_atol=TENSOR_LATENT_ATOL)
+        _record("tensor" + ("" if big else " (small blocks)"), rep, ("worst_ratio", "median_rel", "p999_abs_CL", "p999_abs_CM", "p999_rel_CD"))
         assert rep["worst_ratio"] <= TENSOR_WORST_FACTOR, f"{label}: {rep}"
         assert rep["n_bad"] <= max(TENSOR_BULK_FRACTION * rep["n_elements"], 3 if rep["n_elements"] < 50_000 else 0), f"{label}: {rep}"
         if check_distribution:
             assert rep["median_rel"] <= 2e-3, f"{label}: {rep}"
             assert rep["p999_abs_CL"] <= 5e-3 and rep["p999_abs_CM"] <= 1e-3 and rep["p999_rel_CD"] <= 2e-2, f"{label}: {rep}"
         return rep
-    rep = error_report(got, want, re)
+    rep = error_report(got, want, re, latent_atol=TENSOR_FP32_LATENT_ATOL if variant == "tensor_fp32" else LATENT_ATOL)
+    _record(variant + ("" if big else " (small blocks)"), rep, ("worst_ratio", "median_rel", "frac_rel_le_1e-5"))
     assert rep["n_bad"] == 0, f"{label}: {rep}"
     if variant == "tensor_fp32":
         if check_distribution:
@@ -181,6 +205,7 @@ def assert_jacobian_parity(got_j, want_j, got_v, want_v, raw, label: str = "") -
     rel = err / np.maximum(np.abs(dw) + np.abs(want_v)[:, None, :], 1e-300)
     rep = {"worst_ratio": float(ratio.max()), "median_rel": float(np.median(rel[compare])), "compared": float(compare.mean()),
            "frac_outside": float((ratio > 1.0).sum() / compare.sum())}
+    _record("jacobian", rep, ("worst_ratio", "median_rel", "frac_outside"))
     assert ratio.max() <= JAC_WORST_FACTOR, f"{label}: derivative of output row {k[0]} w.r.t. input {k[1]} (query {k[2]}): got {got[k]:.6g}, want {want_j[k]:.6g}, error/tolerance {ratio.max():.2f}"
     assert rep["frac_outside"] <= JAC_BULK_FRACTION, f"{label}: {rep['frac_outside']:.2e} of the derivatives outside the bound"
     assert rep["median_rel"] <= 1e-6, f"{label}: median relative error of the derivatives {rep['median_rel']:.2e}"

@@ -57,7 +57,10 @@ def test_library_is_sm100a_only(library):
 
 
 def test_version_and_error_strings(library):
+    import neuralfoil_b200
+
     assert b"sm_100a" in library.nfb_version()
+    assert f"neuralfoil_b200 {neuralfoil_b200.__version__} ".encode() in library.nfb_version()  # one version, two places
     assert isinstance(library.nfb_last_error(), bytes)
 
 
@@ -82,3 +85,10 @@ def test_argument_errors_need_no_device(library):
     assert library.nfb_create(0, None) == _lib.ERR_INVALID_ARGUMENT
     assert library.nfb_eval_host(None, 0, 0, 1, None, None, 0, None, 1, 0, 0) == _lib.ERR_INVALID_ARGUMENT
     assert library.nfb_launch_count(None) == 0
+    assert library.nfb_multi_eval_host(None, 0, 0, 1, None, None, 0, None, 1, 0, 0) == _lib.ERR_INVALID_ARGUMENT
+    assert library.nfb_multi_device_count(None) == 0 and library.nfb_multi_launch_count(None) == 0
+    assert library.nfb_set_tuning(None, 0, 0) == _lib.ERR_INVALID_ARGUMENT
+    handle = C.c_void_p()
+    assert library.nfb_multi_create(None, 0, C.byref(handle)) in (_lib.ERR_NO_DEVICE, _lib.OK)  # OK only on a GPU box
+    if handle.value:
+        library.nfb_multi_destroy(handle)

@@ -93,3 +93,28 @@ def test_entry_points_agree(oracle, tmp_path):
         np.testing.assert_allclose(a[key], b[key], rtol=1e-6, err_msg=key)
     with pytest.raises(ValueError):
         geometry.Airfoil("e387")  # database lookups are not part of this package
+
+
+def test_kulfan_airfoil_objects_skip_the_fit():
+    """reference main.py:336: `airfoil` may be a KulfanAirfoil; its 8 + 8 parameters are used as they are."""
+    coords = geometry.normalize(geometry.Airfoil("naca4412").coordinates)["coordinates"]
+    params = geometry.kulfan_parameters_from_coordinates(coords)
+    kaf = geometry.KulfanAirfoil("fit", **params)
+    got = geometry.kulfan_parameters_of(kaf)
+    assert got is not None and all(np.array_equal(got[k], params[k]) for k in params)
+    assert geometry.kulfan_parameters_of(geometry.Airfoil("naca0012")) is None
+    # the generated coordinates are the forward map of the fit: refitting them returns the parameters
+    back = geometry.kulfan_parameters_from_coordinates(kaf.coordinates)
+    for k in params:
+        np.testing.assert_allclose(back[k], params[k], atol=1e-9)
+    # and they are already normalised: leading edge at the origin, unit chord along x
+    nrm = geometry.normalize(kaf.coordinates)
+    assert abs(nrm["rotation_angle"]) < 1e-9 and abs(nrm["scale_factor"] - 1) < 1e-12 and nrm["x_translation"] == 0
+    coarse = geometry.KulfanAirfoil("coarse", lower_weights=-np.ones(6) * 0.1, upper_weights=np.ones(6) * 0.1)
+    assert geometry.kulfan_parameters_of(coarse) is None  # another resolution: refitted from its coordinates
+
+    class ParamsOnly:
+        kulfan_parameters = {"lower_weights": np.zeros(5), "upper_weights": np.zeros(5), "leading_edge_weight": 0.0, "TE_thickness": 0.0}
+
+    with pytest.raises(ValueError, match="8 CST weights per side"):
+        geometry.kulfan_parameters_of(ParamsOnly())

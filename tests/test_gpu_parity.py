@@ -78,7 +78,7 @@ def test_matches_reference_fixture_all_outputs(evaluator, golden_dir, size):
     raw = g["raw"]
     got = evaluator.evaluate_host(raw, size, out_dtype=np.float64)
     assert got.shape == (198, raw.shape[1]) and got.dtype == np.float64
-    parity.assert_parity(got, g[f"out_{size}"], raw[19], check_distribution=False, label=size)
+    parity.assert_parity(got, g[f"out_{size}"], raw[19], label=size)
 
 
 def test_matches_reference_fixture_config1(evaluator, golden_dir):
@@ -91,7 +91,7 @@ def test_matches_reference_fixture_config1(evaluator, golden_dir):
             np.testing.assert_allclose(full[i], g["scalars"][i], rtol=5e-4)
         else:
             np.testing.assert_allclose(full[i], g["scalars"][i], rtol=1e-5, atol=tol)
-    parity.assert_parity(full[:, ::20], g["full_every_20"], np.full(50, float(g["Re"])), check_distribution=False)
+    parity.assert_parity(full[:, ::20], g["full_every_20"], np.full(50, float(g["Re"])))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -121,7 +121,7 @@ def test_ragged_batch_sizes(evaluator, oracle, size, n):
     raw = synthetic.sample_training_distribution(n, seed=100 + n)
     got = evaluator.evaluate_host(raw, size, out_dtype=np.float64)
     assert got.shape == (198, n)
-    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], check_distribution=False, label=f"{size} n={n}")
+    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], label=f"{size} n={n}")
 
 
 def test_polar_grid_broadcast_rows(evaluator, oracle):
@@ -132,7 +132,7 @@ def test_polar_grid_broadcast_rows(evaluator, oracle):
         {k: (v[:, 0] if v.ndim == 2 else float(v[0])) for k, v in kulfan.items()},
         alpha=raw[18], Re=raw[19], n_crit=raw[20], model_size="large",
     )
-    parity.assert_parity(stack(aero), oracle.evaluate_raw(raw, "large"), raw[19], check_distribution=False)
+    parity.assert_parity(stack(aero), oracle.evaluate_raw(raw, "large"), raw[19])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -162,8 +162,8 @@ def test_mirror_identity_reference_case(evaluator, golden_dir):
     a = evaluator.get_aero_from_kulfan_parameters(KULFAN, alpha=alpha, xtr_upper=0.7, xtr_lower=0.4, **kw)
     m = evaluator.get_aero_from_kulfan_parameters(mirror, alpha=-alpha, xtr_upper=0.4, xtr_lower=0.7, **kw)
     re = np.full(alpha.size, 5e5)
-    parity.assert_parity(stack(a), g["out"], re, check_distribution=False)
-    parity.assert_parity(stack(m), g["out_mirror"], re, check_distribution=False)
+    parity.assert_parity(stack(a), g["out"], re)
+    parity.assert_parity(stack(m), g["out_mirror"], re)
     tol = dict(rtol=0, atol=1e-12)  # the reference's own tolerance
     np.testing.assert_allclose(m["CL"], -a["CL"], **tol)
     np.testing.assert_allclose(m["CM"], -a["CM"], **tol)
@@ -227,7 +227,7 @@ def test_always_returns_an_answer(evaluator, oracle, alpha, Re):
         assert np.isfinite(aero[k]).all(), k
     assert 0 <= aero["analysis_confidence"][0] <= 1 and aero["CD"][0] > 0
     want = oracle.get_aero_from_kulfan_parameters(KULFAN, alpha=alpha, Re=Re, model_size="large")
-    parity.assert_parity(stack(aero), np.stack(list(want.values())), np.array([Re]), check_distribution=False)
+    parity.assert_parity(stack(aero), np.stack(list(want.values())), np.array([Re]))
 
 
 def test_error_paths(evaluator):
@@ -254,7 +254,7 @@ def test_kulfan_weights_as_8_by_n(evaluator, oracle):
     raw = synthetic.sample_training_distribution(77, seed=3)
     kulfan, flow = synthetic.kulfan_dict_from_raw(raw)
     aero = evaluator.get_aero_from_kulfan_parameters(kulfan, model_size="small", **flow)
-    parity.assert_parity(stack(aero), oracle.evaluate_raw(raw, "small"), raw[19], check_distribution=False)
+    parity.assert_parity(stack(aero), oracle.evaluate_raw(raw, "small"), raw[19])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -357,7 +357,7 @@ def test_tensor_variant_ragged_batch_sizes(evaluator, oracle, size, n):
     raw = synthetic.sample_training_distribution(n, seed=300 + n)
     got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor")
     assert got.shape == (198, n)
-    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], check_distribution=False, variant="tensor")
+    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], variant="tensor")
 
 
 def test_tensor_variant_golden_and_far_ood(evaluator, golden_dir):
@@ -367,7 +367,7 @@ def test_tensor_variant_golden_and_far_ood(evaluator, golden_dir):
     for size in ("xxlarge", "xxxlarge"):
         got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor")
         assert np.isfinite(got[:6]).all(), size
-        parity.assert_parity(got, g[f"out_{size}"], raw[19], check_distribution=False, variant="tensor", label=size)
+        parity.assert_parity(got, g[f"out_{size}"], raw[19], variant="tensor", label=size)
 
 
 def test_tensor_variant_invariants_are_exact(evaluator):
@@ -463,7 +463,7 @@ def test_tensor_fp32_variant_ragged_batch_sizes(evaluator, oracle, size, n):
     raw = synthetic.sample_training_distribution(n, seed=500 + n)
     got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor_fp32")
     assert got.shape == (198, n)
-    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], check_distribution=False, variant="tensor_fp32")
+    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], variant="tensor_fp32")
 
 
 def test_tensor_fp32_variant_golden_and_invariants(evaluator, golden_dir):
@@ -479,7 +479,7 @@ def test_tensor_fp32_variant_golden_and_invariants(evaluator, golden_dir):
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(2)).cuda()
     for size in ("xxlarge", "xxxlarge"):
         got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant="tensor_fp32")
-        parity.assert_parity(got, g[f"out_{size}"], raw[19], check_distribution=False, variant="tensor_fp32", label=size)
+        parity.assert_parity(got, g[f"out_{size}"], raw[19], variant="tensor_fp32", label=size)
         aero = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size=size, variant="tensor_fp32")
         assert aero["CL"][0] == 0.0 and aero["CM"][0] == 0.0 and aero["Top_Xtr"][0] == aero["Bot_Xtr"][0]
         out = evaluator.evaluate_device(d_big, size, variant="tensor_fp32")
@@ -492,37 +492,15 @@ def test_tensor_fp32_variant_golden_and_invariants(evaluator, golden_dir):
 
 # ---------------------------------------------------------------------------------------------
 # The tensor variants run on CTA pairs (nfb_tc2.cuh); the one-SM kernels (nfb_tc.cuh) are a second, independent
-# implementation of the same pipeline, selectable with NFB_TC_ONE_SM=1 (read once per process)
+# implementation of the same pipeline, selected by the NFB_DEBUG_TC_ONE_SM flag of the C ABI (variant "...:one_sm")
 # ---------------------------------------------------------------------------------------------
-_ONE_SM_CHECK = r"""
-import sys, numpy as np
-sys.path.insert(0, {repo!r}); sys.path.insert(0, {tests!r})
-import parity
-from neuralfoil_b200 import Evaluator, synthetic
-from oracle.neuralfoil_oracle import Oracle
-extra = {{"xxxlarge": synthetic.synthetic_xxxlarge_params()}}
-ev, orc = Evaluator(device=0, extra_models=extra), Oracle(extra_models=extra)
-for size, n in (("xxlarge", 4001), ("xxxlarge", 1003), ("xxxlarge", 65)):
-    raw = synthetic.sample_training_distribution(n, seed=77 + n)
-    want = orc.evaluate_raw(raw, size)
-    for variant in ("tensor", "tensor_fp32"):
-        got = ev.evaluate_host(raw, size, out_dtype=np.float64, variant=variant)
-        parity.assert_parity(got, want, raw[19], check_distribution=False, variant=variant, label=f"{{variant}} {{size}} n={{n}}")
-print("ONE_SM_OK")
-"""
-
-
-def test_one_sm_tensor_kernels_still_match_oracle():
-    import os
-    import subprocess
-    import sys
-    from pathlib import Path
-
-    repo = Path(__file__).resolve().parents[1]
-    env = dict(os.environ, NFB_TC_ONE_SM="1")
-    code = _ONE_SM_CHECK.format(repo=str(repo), tests=str(repo / "tests"))
-    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0 and "ONE_SM_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+def test_one_sm_tensor_kernels_still_match_oracle(evaluator, oracle):
+    for size, n in (("xxlarge", 4001), ("xxxlarge", 1003), ("xxxlarge", 65)):
+        raw = synthetic.sample_training_distribution(n, seed=77 + n)
+        want = oracle.evaluate_raw(raw, size)
+        for variant in ("tensor", "tensor_fp32"):
+            got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant=variant + ":one_sm")
+            parity.assert_parity(got, want, raw[19], check_distribution=n >= 1000, variant=variant, label=f"{variant}:one_sm {size} n={n}")
 
 
 @pytest.mark.parametrize("variant", ["tensor", "tensor_fp32"])
@@ -538,7 +516,7 @@ def test_tensor_variants_fp32_output_unaligned_and_fp64_input(evaluator, oracle,
         out = torch.full((198, n + 1), float("nan"), dtype=torch.float32, device="cuda")[:, :n]   # ld = n + 1: odd
         res = evaluator.evaluate_device(d_raw, size, out=out, variant=variant)
         torch.cuda.synchronize()
-        parity.assert_parity(res.cpu().numpy().astype(np.float64), want, raw[19], check_distribution=False, variant=variant, label=size)
+        parity.assert_parity(res.cpu().numpy().astype(np.float64), want, raw[19], variant=variant, label=size)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -680,48 +658,28 @@ def test_vjp_matches_oracle_and_jacobian(evaluator, oracle, size):
 
 # ---------------------------------------------------------------------------------------------
 # The fp32 path runs the column-group kernels (nfb_ffma_groups.cuh); the CTA-synchronous tiled kernels (nfb_ffma.cuh)
-# are the earlier implementation of the same arithmetic, selectable with NFB_FFMA_TILED=1 (read once per process).
-# Both must give the same bits: same bias + fma chain per output, same SiLU, same decode.
+# are the earlier implementation of the same arithmetic, selected by the NFB_DEBUG_FFMA_TILED flag of the C ABI
+# (variant "fp32:tiled").  Both must give the same bits: same bias + fma chain per output, same SiLU, same decode.
 # ---------------------------------------------------------------------------------------------
-_TILED_DUMP = r"""
-import sys, numpy as np, torch
-sys.path.insert(0, {repo!r})
-from neuralfoil_b200 import Evaluator, synthetic
-ev = Evaluator(device=0, extra_models={{"xxxlarge": synthetic.synthetic_xxxlarge_params()}})
-res = {{}}
-for size, n in {cases!r}:
-    raw = torch.from_numpy(synthetic.sample_training_distribution(n, seed=500 + n, dtype=np.float32)).cuda()
-    res[f"{{size}}_{{n}}"] = ev.evaluate_device(raw, size).cpu().numpy()
-    res[f"{{size}}_{{n}}_scalars"] = ev.evaluate_device(raw, size, outputs="scalars").cpu().numpy()
-np.savez({out!r}, **res)
-print("DUMP_OK")
-"""
-
 _GROUP_CASES = [("xxsmall", 20_011), ("xsmall", 9_999), ("small", 20_000), ("medium", 33_333), ("large", 20_001),
                 ("xlarge", 50_021), ("xxlarge", 20_003), ("xxxlarge", 9_001)]
 
 
-@pytest.mark.gpu
-def test_column_group_kernels_match_tiled_kernels_bit_for_bit(tmp_path):
-    import os
-    import subprocess
-    import sys
-    from pathlib import Path
+@pytest.mark.parametrize("size,n", _GROUP_CASES)
+def test_column_group_kernels_match_tiled_kernels_bit_for_bit(evaluator, size, n):
+    import torch
 
-    repo = Path(__file__).resolve().parents[1]
-    dumps = {}
-    for name, extra_env in (("groups", {}), ("tiled", {"NFB_FFMA_TILED": "1"})):
-        out = tmp_path / f"{name}.npz"
-        code = _TILED_DUMP.format(repo=str(repo), cases=_GROUP_CASES, out=str(out))
-        res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra_env), capture_output=True,
-                             text=True, timeout=600)
-        assert res.returncode == 0 and "DUMP_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
-        dumps[name] = np.load(out)
-    for key in dumps["groups"].files:
-        a, b = dumps["groups"][key], dumps["tiled"][key]
-        assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True), key
-        if key.endswith("_scalars"):
-            assert a.shape[0] == 6 and np.array_equal(a, dumps["groups"][key[: -len("_scalars")]][:6], equal_nan=True), key
+    raw = torch.from_numpy(synthetic.sample_training_distribution(n, seed=500 + n, dtype=np.float32)).cuda()
+    launches0 = evaluator.launch_count()
+    groups = evaluator.evaluate_device(raw, size).cpu().numpy()
+    tiled = evaluator.evaluate_device(raw, size, variant="fp32:tiled").cpu().numpy()
+    assert evaluator.launch_count() == launches0 + 2
+    assert np.array_equal(groups, tiled, equal_nan=True)
+    for variant in ("fp32", "fp32:tiled"):
+        scalars = evaluator.evaluate_device(raw, size, variant=variant, outputs="scalars").cpu().numpy()
+        assert scalars.shape[0] == 6 and np.array_equal(scalars, groups[:6], equal_nan=True), variant
+    small = evaluator.evaluate_device(raw[:, :37].contiguous(), size, variant="fp32:tiled").cpu().numpy()  # the flag also bypasses the small-batch kernel
+    assert np.array_equal(small, groups[:, :37], equal_nan=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -759,7 +717,7 @@ def test_user_supplied_architectures_match_oracle():
         for name in extra:
             want = orc.evaluate_raw(raw, name)
             got = ev.evaluate_host(raw, name, out_dtype=np.float64)
-            parity.assert_parity(got, want, raw[19], check_distribution=False, label=name)
+            parity.assert_parity(got, want, raw[19], label=name)
             small = ev.evaluate_host(np.ascontiguousarray(raw[:, :37]), name, out_dtype=np.float64)  # the 4-queries-per-CTA kernel
             np.testing.assert_array_equal(small, got[:, :37])
             sc = ev.evaluate_device(torch.from_numpy(raw).cuda(), name, outputs="scalars", out_dtype=torch.float64)
