@@ -9,16 +9,18 @@ whatever the summation order.  The criterion is therefore stated as
 
     |got - want| <= RTOL * |want| + atol(row)            with RTOL = 1e-5
 
-where atol(row) is the effect of a latent-space error of LATENT_ATOL = 2.5e-4 (4x the worst fp32
-yardstick error) pushed through that row's decode (main.py:292-316):
+where atol(row) is the effect of a latent-space error of LATENT_ATOL = 1.25e-4 pushed through that row's decode
+(main.py:292-316).  LATENT_ATOL is 3 x the worst latent error any fp32 comparison of the GPU suite has shown (round 2,
+B200: worst error / tolerance 0.171 at the old 2.5e-4, i.e. 4.3e-5; profiles/r2_parity_maxima_session_a.json), so a
+kernel that loses a factor 3 of accuracy anywhere fails:
 
-    analysis_confidence  sigmoid, slope <= 1/4      -> atol 6.25e-5  (x4 for the logit: 2.5e-4)
-    CL = z/2                                         -> atol 1.25e-4
+    analysis_confidence  sigmoid, slope <= 1/4      -> atol LATENT_ATOL  (x4 for the logit)
+    CL = z/2                                         -> atol LATENT_ATOL / 2
     CD = exp(2 (z - 2))                              -> relative 2 * LATENT_ATOL
-    CM = z/20                                        -> atol 1.25e-5
-    Top/Bot_Xtr = clip(z)                            -> atol 2.5e-4
+    CM = z/20                                        -> atol LATENT_ATOL / 20
+    Top/Bot_Xtr = clip(z)                            -> atol LATENT_ATOL
     H = 2.6 exp(z)                                   -> relative LATENT_ATOL
-    ue/vinf = z                                      -> atol 2.5e-4
+    ue/vinf = z                                      -> atol LATENT_ATOL
     theta = (10^z - 0.1) / (|ue| Re)                 -> compared as tau = theta |ue| Re = 10^z - 0.1,
                                                         atol ln(10) * LATENT_ATOL * (tau + 0.1)
                                                         (the reference itself is singular at ue -> 0)
@@ -32,7 +34,7 @@ from __future__ import annotations
 import numpy as np
 
 RTOL = 1e-5
-LATENT_ATOL = 2.5e-4
+LATENT_ATOL = 1.25e-4
 N = 32
 
 ROW_THETA = np.r_[6 : 6 + N, 6 + 3 * N : 6 + 4 * N]
@@ -142,7 +144,7 @@ def assert_parity(got, want, Re, check_distribution: bool | None = None, label: 
         assert rep["worst_ratio"] <= TENSOR_WORST_FACTOR, f"{label}: {rep}"
         assert rep["n_bad"] <= max(TENSOR_BULK_FRACTION * rep["n_elements"], 3 if rep["n_elements"] < 50_000 else 0), f"{label}: {rep}"
         if check_distribution:
-            assert rep["median_rel"] <= 2e-3, f"{label}: {rep}"
+            assert rep["median_rel"] <= 1.5e-3, f"{label}: {rep}"  # measured 6.0e-4 .. 6.4e-4 (profiles/r2_parity_maxima_session_a.json)
             assert rep["p999_abs_CL"] <= 5e-3 and rep["p999_abs_CM"] <= 1e-3 and rep["p999_rel_CD"] <= 2e-2, f"{label}: {rep}"
         return rep
     rep = error_report(got, want, re, latent_atol=TENSOR_FP32_LATENT_ATOL if variant == "tensor_fp32" else LATENT_ATOL)
@@ -171,16 +173,16 @@ def assert_parity(got, want, Re, check_distribution: bool | None = None, label: 
 # size): non-theta rows worst 3e-4, theta rows worst 0.13 at |ue| = 3e-5 (bound there: 0.67), median 1e-8 .. 6e-8.
 # Top_Xtr / Bot_Xtr are clipped to [0, 1]: their derivative jumps at the clip, so elements whose value lies within
 # 1e-4 of 0 or 1 (and is not exactly clipped in both evaluations) are not compared.
-# Bulk and worst case, as for the tensor variants: at least 99.9 % of the compared elements meet the bound above
-# (measured: all but 2e-5 of them); none misses it by more than JAC_WORST_FACTOR.  The elements that exceed it belong to
+# Bulk and worst case, as for the tensor variants: all but JAC_BULK_FRACTION of the compared elements meet the bound above
+# (measured: all but 5.5e-7 of them); none misses it by more than JAC_WORST_FACTOR (measured 1.10).  The elements that exceed it belong to
 # far-from-training queries (analysis_confidence 0.02) of the trained xxlarge, where forward mode in fp32 is off by 0.6 %
 # even in a NumPy float32 emulation and by 3 % on the GPU (sequential fma chains): a latent derivative error of 2e-3.
 # ---------------------------------------------------------------------------------------------------
 JAC_INPUT_SCALE = np.array([0.1] * 16 + [0.1, 0.002, 1.0, np.nan, 1.0, 0.1, 0.1])  # Re (row 19): relative, filled per query
 JAC_RTOL = 2e-3
 JAC_UE_FLOOR = 1e-2
-JAC_BULK_FRACTION = 1e-3
-JAC_WORST_FACTOR = 25.0
+JAC_BULK_FRACTION = 1e-5  # measured 5.5e-7 (round 2, profiles/r2_parity_maxima_session_a.json)
+JAC_WORST_FACTOR = 3.5   # measured 1.10
 
 
 def assert_jacobian_parity(got_j, want_j, got_v, want_v, raw, label: str = "") -> dict:
@@ -208,6 +210,6 @@ def assert_jacobian_parity(got_j, want_j, got_v, want_v, raw, label: str = "") -
     _record("jacobian", rep, ("worst_ratio", "median_rel", "frac_outside"))
     assert ratio.max() <= JAC_WORST_FACTOR, f"{label}: derivative of output row {k[0]} w.r.t. input {k[1]} (query {k[2]}): got {got[k]:.6g}, want {want_j[k]:.6g}, error/tolerance {ratio.max():.2f}"
     assert rep["frac_outside"] <= JAC_BULK_FRACTION, f"{label}: {rep['frac_outside']:.2e} of the derivatives outside the bound"
-    assert rep["median_rel"] <= 1e-6, f"{label}: median relative error of the derivatives {rep['median_rel']:.2e}"
+    assert rep["median_rel"] <= 2e-7, f"{label}: median relative error of the derivatives {rep['median_rel']:.2e}"  # measured <= 6.0e-8
     assert rep["compared"] > 0.99
     return rep
