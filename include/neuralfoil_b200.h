@@ -183,6 +183,24 @@ int nfb_eval_vjp_reverse_device(nfb_context* ctx, int model_id, int64_t n, const
                                 const int64_t* in_strides, int in_dtype, const void* cot, int64_t cot_ld,
                                 void* values, int64_t values_ld, void* grad, int64_t grad_ld, int out_dtype, void* stream);
 
+/* One training step's forward, loss and backward: what the reference's loop computes between `net(x)` and
+ * `loss.backward()` (training/train.py:56-114 Net.forward, :194-236 loss_function, :251-255), for the network in slot
+ * `model_id`, in fp32 on the GPU.  All data pointers are DEVICE pointers.
+ *   x, x_ld             (batch, 25) float32 scaled inputs, row b at x + b * x_ld            [train.py:251]
+ *   y_data, y_ld        (batch, 198) float32 targets, NaN = no data for that output         [train.py:252, :197]
+ *   loss_weights        198 float32 (train.py:180-190)          huber_delta   0.05 in the reference (train.py:213)
+ *   loss_components     198 float64 OUT: the weighted mean loss of every output; their sum is `loss` (train.py:222-230)
+ *   grad_weights[l]     OUT, float32 (dims[l+1], dims[l]) row-major = d loss / d net.{2l}.weight
+ *   grad_biases[l]      OUT, float32 (dims[l+1],)                    = d loss / d net.{2l}.bias
+ *                       (host arrays of n_layers device pointers, the layout nfb_load_model takes the parameters in)
+ * Enqueues three kernels on `stream`; a context-owned workspace grows with the batch (49 KB per sample for xxxlarge, 10 KB
+ * for xlarge).  The gradients are bit-reproducible from run to run; loss_components is summed with floating-point atomics
+ * in double precision (reproducible to ~1e-16 relative).  The optimiser step stays with the caller, who re-uploads the
+ * updated parameters with nfb_load_model. */
+int nfb_train_step_device(nfb_context* ctx, int model_id, int64_t batch, const float* x, int64_t x_ld,
+                          const float* y_data, int64_t y_ld, const float* loss_weights, float huber_delta,
+                          double* loss_components, float* const* grad_weights, float* const* grad_biases, void* stream);
+
 /* ---- several GPUs of one box behind one call (BASELINE configs[2] and [4]) ---------------------------------
  * Queries are independent (main.py:198-201: every row of the stacked input is its own case) and the weights are a few MB,
  * so the path shards by contiguous index range with NO collective: device i of G evaluates queries

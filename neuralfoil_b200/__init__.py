@@ -13,6 +13,7 @@ from .main import (  # noqa: F401
     Evaluator,
     bl_x_points,
     default_evaluator,
+    default_loss_weights,
     get_aero_from_airfoil,
     get_aero_from_coordinates,
     get_aero_from_dat_file,

@@ -15,6 +15,7 @@ if os.environ.get("NFB_LIB_PATH"):  # A/B experiments only: another build of the
     LIB_PATH = Path(os.environ["NFB_LIB_PATH"])
 
 N_RAW_ROWS = 23
+N_LATENT_INPUTS = 25
 N_OUTPUT_ROWS = 198
 F32, F64 = 0, 1
 VARIANT_FP32_FFMA = 0
@@ -81,6 +82,11 @@ _SIGNATURES = {
         C.c_int,
         [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
          C.c_void_p, C.c_int64, C.c_void_p, C.c_int],
+    ),
+    "nfb_train_step_device": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
+         C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p],
     ),
     "nfb_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "nfb_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),

@@ -23,8 +23,10 @@
 #include "nfb_small.cuh"
 #include "nfb_tc.cuh"
 #include "nfb_tc2.cuh"
+#include "nfb_tcn.cuh"
 #include "nfb_jac.cuh"
 #include "nfb_grad.cuh"
+#include "nfb_train.cuh"
 
 namespace {
 
@@ -62,6 +64,10 @@ struct Model {
   __half* tc2_w3 = nullptr;
   float* tc_bias = nullptr;
   float* tc_inv_scale = nullptr;
+  // narrow models (64- / 128-wide): weight streams of nfb_tcn.cuh (one-term, three-term), biases [L][256]
+  __half* tcn_w = nullptr;
+  __half* tcn_w3 = nullptr;
+  float* tcn_bias = nullptr;
 };
 
 // Kernel tuning per padded width: <H, KC, STAGES>.
@@ -176,6 +182,9 @@ struct nfb_context {
   HostSlot slots[2];
   void* grad_scratch = nullptr;  // nfb_grad.cuh: SiLU slopes and parked cotangents, one block per CTA
   size_t grad_scratch_bytes = 0;
+  void* train_ws = nullptr;      // nfb_train_step_device: saved activations / cotangents and the split partial sums
+  size_t train_ws_bytes = 0;
+  int* packed_row_of = nullptr;  // [198] inverse of nfb::pack_last_layer_row (device)
   cudaEvent_t grad_event = nullptr;      // recorded behind the last launch that uses grad_scratch ...
   cudaStream_t grad_stream = nullptr;    // ... on this stream: a launch on another stream waits for it first
   bool grad_event_recorded = false;
@@ -376,6 +385,58 @@ std::vector<__half> pack_model_tc2(int L, const int* dims, const float* const* W
   return out;
 }
 
+// Weight streams of the narrow tensor-core kernels (nfb_tcn.cuh): the ring slots of one tile in the order the kernel consumes
+// them -- layer, position of the K sweep -- each slot two pieces of (N_l rows x 32 k), K-major no-swizzle core matrices:
+// SPLIT = 1: k-slices 2 pos and 2 pos + 1 (layer 0: [W_hi | W_hi | W_lo | 0] over the same 32 inputs); SPLIT = 3: the W_hi and
+// the W_lo piece of k-slice pos.  Slot stride Cfg::SLOT_BYTES; the second piece follows the first at piece_bytes(l).
+template <class Cfg>
+std::vector<__half> pack_model_tcn(int L, const int* dims, const float* const* W, std::vector<float>* inv_scale_out) {
+  using nfb::tc::SLICE_K;
+  size_t slots = 0;
+  for (int l = 0; l < L; ++l) slots += Cfg::slots_in_layer(l);
+  std::vector<__half> out(slots * (Cfg::SLOT_BYTES / 2), __float2half_rn(0.0f));
+  if (inv_scale_out) inv_scale_out->assign(L, 1.0f);
+  size_t slot = 0;
+  for (int l = 0; l < L; ++l) {
+    const int in = dims[l], outd = dims[l + 1];
+    const bool last = (l == L - 1);
+    float wmax = 0.0f;
+    for (size_t i = 0; i < size_t(in) * outd; ++i) wmax = std::max(wmax, std::fabs(W[l][i]));
+    int e = 0;  // scale = 2^e, as large as keeps |w| * scale < 16384, at most 2^12 (as pack_model_tc)
+    if (wmax > 0.0f && std::isfinite(wmax)) e = std::min(12, std::max(-12, int(std::floor(std::log2(16384.0f / wmax)))));
+    const float scale = std::ldexp(1.0f, e);
+    if (inv_scale_out) (*inv_scale_out)[l] = std::ldexp(1.0f, -e);
+    const int n_rows = Cfg::n_of(l, L);
+    const size_t piece_halfs = Cfg::piece_bytes(l, L) / 2;
+    for (int pos = 0; pos < Cfg::slots_in_layer(l); ++pos, ++slot) {
+      __half* const dst_slot = out.data() + slot * (Cfg::SLOT_BYTES / 2);
+      for (int piece = 0; piece < 2; ++piece) {
+        const int ks = (Cfg::SPLIT == 3) ? pos : 2 * pos + piece;
+        bool want_lo = (Cfg::SPLIT == 3) ? (piece == 1) : false;
+        bool zero = false;
+        if (Cfg::SPLIT == 1 && l == 0) {  // [W_hi | W_hi | W_lo | 0]
+          want_lo = (ks == 2);
+          zero = (ks == 3);
+        }
+        if (zero) continue;
+        __half* const dst = dst_slot + piece * piece_halfs;
+        for (int r = 0; r < n_rows; ++r) {
+          const int src = last ? nfb::pack_last_layer_row(r) : (r < outd ? r : -1);
+          if (src < 0 || src >= outd) continue;
+          for (int kk = 0; kk < SLICE_K; ++kk) {
+            const int k = (Cfg::SPLIT == 1 && l == 0) ? kk : ks * SLICE_K + kk;
+            if (k >= in) continue;
+            const float ws = W[l][size_t(src) * in + k] * scale;
+            const __half hi = __float2half_rn(ws);
+            dst[(r / 8) * 256 + (kk / 8) * 64 + (r % 8) * 8 + (kk % 8)] = want_lo ? __float2half_rn(ws - __half2float(hi)) : hi;
+          }
+        }
+      }
+    }
+  }
+  return out;
+}
+
 // Raise a kernel's dynamic shared memory limit once per context (the attribute is per device and per function).
 template <class K>
 int configure(nfb_context* ctx, K kernel, size_t smem_bytes) {
@@ -477,6 +538,18 @@ int launch_tc2(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t strea
   return NFB_OK;
 }
 
+// the narrow tensor-core kernels (nfb_tcn.cuh): one CTA per SM
+template <class Cfg>
+int launch_tcn(nfb_context* ctx, const nfb::tc::TcParams& tp, cudaStream_t stream) {
+  NFB_CONFIGURE(nfb::tcn::nfb_tcn_kernel<Cfg>, Cfg::SMEM_BYTES);
+  const long long tiles = (tp.ev.n + Cfg::NQT - 1) / Cfg::NQT;
+  const int grid = int(std::min<long long>(tiles, ctx->sm_count));
+  nfb::tcn::nfb_tcn_kernel<Cfg><<<grid, nfb::tcn::TCN_THREADS, Cfg::SMEM_BYTES, stream>>>(tp);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return NFB_OK;
+}
+
 template <int H>
 int launch_small(nfb_context* ctx, const nfb::EvalParams& p, cudaStream_t stream) {
   using Cfg = nfb::SmallCfg<H>;
@@ -508,9 +581,9 @@ int check_eval_args(nfb_context* ctx, int model_id, int variant, int64_t n, cons
   variant &= ~NFB_VARIANT_FLAGS;
   if (variant != NFB_VARIANT_FP32_FFMA && variant != NFB_VARIANT_TENSOR_FP16 && variant != NFB_VARIANT_TENSOR_FP16X3)
     return fail(NFB_ERR_INVALID_ARGUMENT, "unknown variant %d", variant);
-  if (variant != NFB_VARIANT_FP32_FFMA && !ctx->models[model_id].tc_w)
+  if (variant != NFB_VARIANT_FP32_FFMA && !ctx->models[model_id].tc_w && !ctx->models[model_id].tcn_w)
     return fail(NFB_ERR_UNSUPPORTED_MODEL,
-                "the tensor-core variant exists for 256- and 512-wide models with at most %d layers only; model slot %d is not one",
+                "the tensor-core variants exist for models with at most %d layers only; model slot %d has more",
                 nfb::tc::MAX_TC_LAYERS, model_id);
   if (n < 0) return fail(NFB_ERR_INVALID_ARGUMENT, "n = %lld is negative", (long long)n);
   if ((in_dtype != NFB_F32 && in_dtype != NFB_F64) || (out_dtype != NFB_F32 && out_dtype != NFB_F64))
@@ -559,6 +632,15 @@ int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, con
     const bool x3 = (variant == NFB_VARIANT_TENSOR_FP16X3);
     nfb::tc::TcParams tp;
     tp.ev = p;
+    if (m.tcn_w) {  // 64- / 128-wide models: nfb_tcn.cuh (a layer is one MMA wide; there is no second implementation to cross-check)
+      tp.wblob = x3 ? m.tcn_w3 : m.tcn_w;
+      tp.bias = m.tcn_bias;
+      tp.inv_scale = m.tc_inv_scale;
+      tp.dbg = ctx->tc_debug;
+      if (m.h_pad == 128)
+        return x3 ? launch_tcn<nfb::tcn::TcnCfg<128, 3>>(ctx, tp, stream) : launch_tcn<nfb::tcn::TcnCfg<128, 1>>(ctx, tp, stream);
+      return x3 ? launch_tcn<nfb::tcn::TcnCfg<64, 3>>(ctx, tp, stream) : launch_tcn<nfb::tcn::TcnCfg<64, 1>>(ctx, tp, stream);
+    }
     tp.wblob = one_sm ? (x3 ? m.tc3_w : m.tc_w) : (x3 ? m.tc2_w3 : m.tc2_w);
     tp.bias = m.tc_bias;
     tp.inv_scale = m.tc_inv_scale;
@@ -720,6 +802,9 @@ void nfb_destroy(nfb_context* ctx) {
     if (m.tc2_w3) cudaFree(m.tc2_w3);
     if (m.tc_bias) cudaFree(m.tc_bias);
     if (m.tc_inv_scale) cudaFree(m.tc_inv_scale);
+    if (m.tcn_w) cudaFree(m.tcn_w);
+    if (m.tcn_w3) cudaFree(m.tcn_w3);
+    if (m.tcn_bias) cudaFree(m.tcn_bias);
   }
   for (auto& s : ctx->slots) {
     if (s.stream) {
@@ -736,6 +821,8 @@ void nfb_destroy(nfb_context* ctx) {
   if (ctx->jac_dev) cudaFree(ctx->jac_dev);
   if (ctx->grad_scratch) cudaFree(ctx->grad_scratch);
   if (ctx->grad_event) cudaEventDestroy(ctx->grad_event);
+  if (ctx->train_ws) cudaFree(ctx->train_ws);
+  if (ctx->packed_row_of) cudaFree(ctx->packed_row_of);
   if (ctx->jac_host) cudaFreeHost(ctx->jac_host);
   delete ctx;
 }
@@ -801,6 +888,9 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
     if (m.tc2_w3) NFB_CUDA(cudaFree(m.tc2_w3));
     if (m.tc_bias) NFB_CUDA(cudaFree(m.tc_bias));
     if (m.tc_inv_scale) NFB_CUDA(cudaFree(m.tc_inv_scale));
+    if (m.tcn_w) NFB_CUDA(cudaFree(m.tcn_w));
+    if (m.tcn_w3) NFB_CUDA(cudaFree(m.tcn_w3));
+    if (m.tcn_bias) NFB_CUDA(cudaFree(m.tcn_bias));
     m = Model();
   }
   NFB_CUDA(cudaMalloc(&m.blob, blob.size() * sizeof(float)));
@@ -837,6 +927,30 @@ int nfb_load_model(nfb_context* ctx, int model_id, int n_layers, const int* dims
     NFB_CUDA(cudaMemcpy(m.tc_w, tcp.w.data(), tcp.w.size() * sizeof(__half), cudaMemcpyHostToDevice));
     NFB_CUDA(cudaMemcpy(m.tc_bias, tcp.bias.data(), tcp.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     NFB_CUDA(cudaMemcpy(m.tc_inv_scale, tcp.inv_scale.data(), tcp.inv_scale.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  if ((h_pad == 128 || h_pad == 64) && n_layers <= nfb::tc::MAX_TC_LAYERS) {
+    std::vector<float> inv_scale;
+    const std::vector<__half> w1 = h_pad == 128 ? pack_model_tcn<nfb::tcn::TcnCfg<128, 1>>(n_layers, dims, weights, &inv_scale)
+                                                : pack_model_tcn<nfb::tcn::TcnCfg<64, 1>>(n_layers, dims, weights, &inv_scale);
+    const std::vector<__half> w3 = h_pad == 128 ? pack_model_tcn<nfb::tcn::TcnCfg<128, 3>>(n_layers, dims, weights, nullptr)
+                                                : pack_model_tcn<nfb::tcn::TcnCfg<64, 3>>(n_layers, dims, weights, nullptr);
+    std::vector<float> bias(size_t(n_layers) * nfb::tcn::TCN_BIAS_LD, 0.0f);
+    for (int l = 0; l < n_layers; ++l) {
+      const bool last = (l == n_layers - 1);
+      const int rows = last ? nfb::tcn::TCN_LAST_N : h_pad;
+      for (int r = 0; r < rows; ++r) {
+        const int src = last ? nfb::pack_last_layer_row(r) : (r < dims[l + 1] ? r : -1);
+        if (src >= 0 && src < dims[l + 1]) bias[size_t(l) * nfb::tcn::TCN_BIAS_LD + r] = biases[l][src];
+      }
+    }
+    NFB_CUDA(cudaMalloc(&m.tcn_w, w1.size() * sizeof(__half)));
+    NFB_CUDA(cudaMemcpy(m.tcn_w, w1.data(), w1.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    NFB_CUDA(cudaMalloc(&m.tcn_w3, w3.size() * sizeof(__half)));
+    NFB_CUDA(cudaMemcpy(m.tcn_w3, w3.data(), w3.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    NFB_CUDA(cudaMalloc(&m.tcn_bias, bias.size() * sizeof(float)));
+    NFB_CUDA(cudaMemcpy(m.tcn_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    NFB_CUDA(cudaMalloc(&m.tc_inv_scale, inv_scale.size() * sizeof(float)));
+    NFB_CUDA(cudaMemcpy(m.tc_inv_scale, inv_scale.data(), inv_scale.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   m.loaded = true;
   m.n_layers = n_layers;
@@ -1085,6 +1199,164 @@ int nfb_eval_vjp_reverse_device(nfb_context* ctx, int model_id, int64_t n, const
                                 int64_t grad_ld, int out_dtype, void* stream) {
   return grad_device_impl(ctx, true, model_id, n, in_rows, in_strides, in_dtype, cot, cot_ld, values, values_ld, grad, grad_ld,
                           out_dtype, stream);
+}
+
+}  // extern "C"
+
+namespace {
+// One training step for one padded width: forward + loss + backward (nfb_train_fwdbwd_kernel), the weight gradients of every
+// layer (nfb_train_wgrad_kernel) and the fixed-order reduction of its column splits (nfb_train_reduce_kernel).
+template <class Cfg, class WCfg>
+int launch_train(nfb_context* ctx, const Model& m, int64_t batch, const float* x, int64_t x_ld, const float* y, int64_t y_ld,
+                 const float* loss_weights, float delta, double* loss_out, float* const* grad_w, float* const* grad_b,
+                 cudaStream_t stream) {
+  constexpr int H = Cfg::H, NC = Cfg::NC, NQ = Cfg::NQ;
+  using TC = nfb::TrainCfg<Cfg>;
+  const int L = m.n_layers;
+  NFB_CONFIGURE(nfb::nfb_train_fwdbwd_kernel<Cfg>, TC::SMEM_BYTES);
+  NFB_CONFIGURE(nfb::nfb_train_wgrad_kernel<WCfg>, WCfg::SMEM_BYTES);
+  const long long tiles = (batch + NQ - 1) / NQ;
+  const long long cols = tiles * NC;
+  const int grid = int(std::min<long long>(tiles, ctx->sm_count));
+
+  // ---- jobs of the weight-gradient kernel, one per layer ----
+  nfb::WgradParams wp;
+  nfb::ReduceParams rp;
+  long long part = 0, first_out = 0;
+  int ctas = 0;
+  for (int l = 0; l < L; ++l) {
+    const bool last = (l == L - 1);
+    const int m_pad = last ? nfb::TRAIN_LAST_ROWS : H;
+    const int n_valid = (l == 0) ? nfb::K0_PAD : H;
+    const int n_pad = (n_valid + WCfg::BN - 1) / WCfg::BN * WCfg::BN;
+    nfb::WgradJob& j = wp.job[l];
+    j.ldz = m_pad;
+    j.lda = n_valid;
+    j.m_blocks = m_pad / WCfg::BM;
+    j.n_blocks = n_pad / WCfg::BN;
+    j.n_valid = n_valid;
+    j.part_off = part;
+    nfb::ReduceJob& r = rp.job[l];
+    r.grad_w = grad_w[l];
+    r.grad_b = grad_b[l];
+    r.out_dim = m.dims[l + 1];
+    r.in_dim = m.dims[l];
+    r.n_pad = n_pad;
+    r.m_pad = m_pad;
+    r.last = last ? 1 : 0;
+    r.part_off = part;
+    r.first = first_out;
+    first_out += (long long)r.out_dim * (r.in_dim + 1);
+    part += (long long)m_pad * n_pad + m_pad;
+    ctas += j.m_blocks * j.n_blocks;
+  }
+  const long long steps_total = cols / WCfg::BK;
+  int k_splits = int(std::max<long long>(1, std::min<long long>({(2LL * ctx->sm_count + ctas - 1) / ctas, steps_total / 4, 64LL})));
+  {
+    int first = 0;
+    for (int l = 0; l < L; ++l) {
+      wp.job[l].first_cta = first;
+      first += wp.job[l].m_blocks * wp.job[l].n_blocks * k_splits;
+    }
+    ctas = first;
+  }
+
+  // ---- workspace: [scratch of the fused kernel | saved A | saved DZ | partial sums] ----
+  auto align = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t scratch_b = align(size_t(grid) * nfb::grad_scratch_floats<H, NC>(L, true) * sizeof(float));
+  const size_t a_b = align(nfb::train_saved_a_floats<H>(L, cols) * sizeof(float));
+  const size_t dz_b = align(nfb::train_saved_dz_floats<H>(L, cols) * sizeof(float));
+  const size_t part_b = align(size_t(k_splits) * size_t(part) * sizeof(float));
+  const size_t need = scratch_b + a_b + dz_b + part_b;
+  if (need > ctx->train_ws_bytes) {
+    // (cudaFree waits for the device: nothing still uses the old block.  Not capturable: warm up with one eager step.)
+    int rc = ensure(&ctx->train_ws, &ctx->train_ws_bytes, need, false);
+    if (rc != NFB_OK) return rc;
+  }
+  if (!ctx->packed_row_of) {
+    int inv[nfb::N_OUT];
+    for (int o = 0; o < nfb::N_OUT; ++o) inv[o] = -1;
+    for (int pr = 0; pr < nfb::TRAIN_LAST_ROWS; ++pr) {
+      const int o = nfb::pack_last_layer_row(pr);
+      if (o >= 0 && o < nfb::N_OUT) inv[o] = pr;
+    }
+    NFB_CUDA(cudaMalloc(&ctx->packed_row_of, sizeof(inv)));
+    NFB_CUDA(cudaMemcpy(ctx->packed_row_of, inv, sizeof(inv), cudaMemcpyHostToDevice));
+  }
+  char* const ws = static_cast<char*>(ctx->train_ws);
+  nfb::TrainParams tp;
+  static const void* const no_rows[nfb::N_RAW] = {nullptr};
+  static const int64_t no_strides[nfb::N_RAW] = {0};
+  fill_eval_params(ctx, m, m.grad_blob, batch, no_rows, no_strides, NFB_F32, nullptr, 0, NFB_F32, tp.ev);
+  tp.x = x;
+  tp.y = y;
+  tp.x_ld = x_ld;
+  tp.y_ld = y_ld;
+  tp.loss_w = loss_weights;
+  tp.inv_batch = 1.0f / float(batch);
+  tp.delta = delta;
+  tp.loss_out = loss_out;
+  tp.scratch = reinterpret_cast<float*>(ws);
+  tp.saved_a = reinterpret_cast<float*>(ws + scratch_b);
+  tp.saved_dz = reinterpret_cast<float*>(ws + scratch_b + a_b);
+  tp.cols = cols;
+  for (int l = 0; l < L; ++l) {
+    wp.job[l].dz = tp.saved_dz + size_t(l) * H * cols;  // (the last layer's block follows the L - 1 hidden ones)
+    wp.job[l].a = tp.saved_a + nfb::train_saved_a_offset<H>(l, cols);
+  }
+  wp.n_jobs = L;
+  wp.k_splits = k_splits;
+  wp.cols = cols;
+  wp.partial = reinterpret_cast<float*>(ws + scratch_b + a_b + dz_b);
+  wp.part_stride = part;
+  rp.n_jobs = L;
+  rp.k_splits = k_splits;
+  rp.partial = wp.partial;
+  rp.part_stride = part;
+  rp.total = first_out;
+  rp.packed_row_of = ctx->packed_row_of;
+
+  NFB_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(double) * nfb::N_OUT, stream));
+  nfb::nfb_train_fwdbwd_kernel<Cfg><<<grid, Cfg::THREADS, TC::SMEM_BYTES, stream>>>(tp);
+  NFB_CUDA(cudaGetLastError());
+  nfb::nfb_train_wgrad_kernel<WCfg><<<ctas, WCfg::THREADS, WCfg::SMEM_BYTES, stream>>>(wp);
+  NFB_CUDA(cudaGetLastError());
+  nfb::nfb_train_reduce_kernel<<<unsigned((first_out + 255) / 256), 256, 0, stream>>>(rp);
+  NFB_CUDA(cudaGetLastError());
+  ctx->launches += 3;
+  return NFB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int nfb_train_step_device(nfb_context* ctx, int model_id, int64_t batch, const float* x, int64_t x_ld, const float* y_data,
+                          int64_t y_ld, const float* loss_weights, float huber_delta, double* loss_components,
+                          float* const* grad_weights, float* const* grad_biases, void* stream) {
+  if (!ctx) return fail(NFB_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (model_id < 0 || model_id >= NFB_MAX_MODELS)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "model_id %d out of range [0, %d)", model_id, NFB_MAX_MODELS);
+  if (!ctx->models[model_id].loaded) return fail(NFB_ERR_NOT_LOADED, "model slot %d is empty", model_id);
+  if (!ctx->have_distribution) return fail(NFB_ERR_NOT_LOADED, "nfb_set_distribution has not been called");
+  if (batch < 1 || batch > (int64_t(1) << 28)) return fail(NFB_ERR_INVALID_ARGUMENT, "batch = %lld; supported: 1 .. 2^28", (long long)batch);
+  if (!x || !y_data || !loss_weights || !loss_components || !grad_weights || !grad_biases)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (x_ld < NFB_N_LATENT_INPUTS || y_ld < NFB_N_OUTPUT_ROWS)
+    return fail(NFB_ERR_INVALID_ARGUMENT, "row strides %lld / %lld are smaller than the rows (25 / 198)", (long long)x_ld, (long long)y_ld);
+  if (!(huber_delta > 0.0f)) return fail(NFB_ERR_INVALID_ARGUMENT, "huber_delta must be positive");
+  const Model& m = ctx->models[model_id];
+  for (int l = 0; l < m.n_layers; ++l)
+    if (!grad_weights[l] || !grad_biases[l]) return fail(NFB_ERR_INVALID_ARGUMENT, "gradient pointer of layer %d is NULL", l);
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (m.h_pad) {
+    case 64: return launch_train<Grp64, nfb::WgradCfg<64, 64>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
+    case 128: return launch_train<Grad128, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
+    case 256: return launch_train<Grad256, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
+    case 512: return launch_train<Grad512, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
+  }
+  return fail(NFB_ERR_UNSUPPORTED_MODEL, "no kernel for padded width %d", m.h_pad);
 }
 
 int nfb_eval_jacobian_host(nfb_context* ctx, int model_id, int64_t n, const void* const* in_rows,

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_train_fwdbwd_kernel(const
         for (int i = 0; i < 6; ++i) {
           float v = ls[i];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(QG == 32 ? 0xffffffffu : 0x0000ffffu, v, o < QG ? o : 0);
+          for (int o = QG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(QG == 32 ? 0xffffffffu : 0x0000ffffu, v, o);
           if (lane == 0 && v != 0.0f) atomicAdd(tp.loss_out + i, double(v));
         }
         const float dq[6] = {0.5f * gz[0], 0.5f * gz[1], 0.5f * gz[2], 0.5f * gz[3], 0.5f * gz[4], 0.5f * gz[5]};

@@ -52,6 +52,16 @@ JACOBIAN_INPUTS = tuple(
 )
 
 
+def default_loss_weights() -> np.ndarray:
+    """The reference's loss weights (training/train.py:180-190): 198 float64, normalised to sum to 1000."""
+    w = np.ones(198)
+    w[0] *= 0.005  # analysis confidence
+    w[2] *= 3      # ln(CD)
+    w[3:6] *= 0.25  # CM, Top_Xtr, Bot_Xtr
+    w[6:] *= 5e-3  # boundary-layer outputs
+    return w / w.sum() * 1000
+
+
 def _length(x) -> int:
     """aerosandbox.numpy.length as used at main.py:161,189-193: len() of sized things, 1 for scalars."""
     try:
@@ -599,6 +609,50 @@ class Evaluator:
             )
         )
         return out[:, :n]
+
+    # -- training step ----------------------------------------------------------------
+    def train_step_device(self, x, y_data, model_size: str, loss_weights=None, huber_delta: float = 0.05):
+        """
+        Forward, loss and backward of one iteration of the reference's training loop (training/train.py:56-114, 194-236,
+        251-255) for the network loaded under `model_size`, on this evaluator's GPU:
+        x (batch, 25) scaled inputs and y_data (batch, 198) targets (NaN = no data), float32 CUDA tensors with contiguous
+        rows -> (loss_components (198,) float64, [(dW_l, db_l), ...] float32 in the reference's `net.{2l}.weight/bias`
+        shapes).  `loss_components.sum()` is the loss the reference back-propagates.  `loss_weights` defaults to
+        `default_loss_weights()`.  Enqueues on torch's current stream; the optimiser step (and `load_model` of the updated
+        parameters) stays with the caller.
+        """
+        import torch
+
+        model_id = self._model_id(model_size)
+        dev = f"cuda:{self.device}"
+        for name, t, cols in (("x", x, _lib.N_LATENT_INPUTS), ("y_data", y_data, _lib.N_OUTPUT_ROWS)):
+            if (not isinstance(t, torch.Tensor) or t.dim() != 2 or t.shape[1] != cols or not t.is_cuda
+                    or t.device.index != self.device or t.dtype != torch.float32 or t.stride(1) != 1):
+                raise ValueError(f"{name} must be a (batch, {cols}) float32 tensor on {dev} with contiguous rows")
+        batch = int(x.shape[0])
+        if batch < 1 or y_data.shape[0] != batch:
+            raise ValueError("x and y_data must have the same, non-zero number of rows")
+        if loss_weights is None:
+            loss_weights = default_loss_weights()
+        w = torch.as_tensor(np.asarray(loss_weights, dtype=np.float32) if not isinstance(loss_weights, torch.Tensor) else loss_weights,
+                            dtype=torch.float32, device=dev).contiguous()
+        if w.shape != (_lib.N_OUTPUT_ROWS,):
+            raise ValueError("loss_weights must have 198 entries")
+        dims = self.model_dims[model_size]
+        grads = [(torch.empty((dims[l + 1], dims[l]), dtype=torch.float32, device=dev),
+                  torch.empty((dims[l + 1],), dtype=torch.float32, device=dev)) for l in range(len(dims) - 1)]
+        loss = torch.empty((_lib.N_OUTPUT_ROWS,), dtype=torch.float64, device=dev)
+        n = len(grads)
+        gw = (C.c_void_p * n)(*[g.data_ptr() for g, _ in grads])
+        gb = (C.c_void_p * n)(*[b.data_ptr() for _, b in grads])
+        _lib.check(
+            self._lib.nfb_train_step_device(
+                self._ctx, model_id, batch, C.c_void_p(x.data_ptr()), int(x.stride(0)), C.c_void_p(y_data.data_ptr()),
+                int(y_data.stride(0)), C.c_void_p(w.data_ptr()), float(huber_delta), C.c_void_p(loss.data_ptr()), gw, gb,
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream),
+            )
+        )
+        return loss, grads
 
     # -- measurement helpers -----------------------------------------------------------------------
     def launch_count(self) -> int:

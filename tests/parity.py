@@ -68,6 +68,13 @@ TENSOR_FP32_LATENT_ATOL = 2.5e-4
 TENSOR_FP32_MEDIAN_REL = 1e-5
 TENSOR_FP32_FRAC_1E5 = 0.75
 
+# The 48-wide models (xxsmall, xsmall) on the one-term variant (nfb_tcn.cuh): with 48 instead of >= 64 .. 512 terms per dot
+# product the rounding of the operands averages out less, and these networks' weights are the largest: measured on B200
+# (20,011 queries, trained weights) p99.9 |dCL| 8.4e-3, |dCM| 1.3e-3, CD 2.1 %, median relative error 1.2e-3 -- about twice
+# the wider models' figures (for scale: xxsmall's own mean error against XFoil is CL 0.040, README.md:120).  Stated bound
+# for them: twice the bounds above; same bulk and worst-case criteria.
+TENSOR_NARROW48_FACTOR = 2.0
+
 TENSOR_LATENT_ATOL = 3e-2
 TENSOR_WORST_FACTOR = 5.0   # worst case = TENSOR_WORST_FACTOR * TENSOR_LATENT_ATOL = 0.15 in latent space
 TENSOR_BULK_FRACTION = 1e-4
@@ -132,7 +139,8 @@ def _record(kind: str, rep: dict, keys) -> None:
         slot[k] = v if k not in slot else worst(slot[k], v)
 
 
-def assert_parity(got, want, Re, check_distribution: bool | None = None, label: str = "", variant: str = "fp32") -> dict:
+def assert_parity(got, want, Re, check_distribution: bool | None = None, label: str = "", variant: str = "fp32",
+                  narrow48: bool = False) -> dict:
     """check_distribution: None = on for blocks of at least 1,000 queries (statistics of a handful of queries say little)."""
     re = np.broadcast_to(np.asarray(Re, dtype=np.float64), (np.shape(want)[1],))
     big = np.shape(want)[1] >= 1000
@@ -140,12 +148,13 @@ def assert_parity(got, want, Re, check_distribution: bool | None = None, label: 
         check_distribution = big
     if variant == "tensor":
         rep = error_report(got, want, re, latent_atol=TENSOR_LATENT_ATOL)
-        _record("tensor" + ("" if big else " (small blocks)"), rep, ("worst_ratio", "median_rel", "p999_abs_CL", "p999_abs_CM", "p999_rel_CD"))
+        _record("tensor" + (" 48-wide" if narrow48 else "") + ("" if big else " (small blocks)"), rep, ("worst_ratio", "median_rel", "p999_abs_CL", "p999_abs_CM", "p999_rel_CD"))
         assert rep["worst_ratio"] <= TENSOR_WORST_FACTOR, f"{label}: {rep}"
         assert rep["n_bad"] <= max(TENSOR_BULK_FRACTION * rep["n_elements"], 3 if rep["n_elements"] < 50_000 else 0), f"{label}: {rep}"
         if check_distribution:
-            assert rep["median_rel"] <= 1.5e-3, f"{label}: {rep}"  # measured 6.0e-4 .. 6.4e-4 (profiles/r2_parity_maxima_session_a.json)
-            assert rep["p999_abs_CL"] <= 5e-3 and rep["p999_abs_CM"] <= 1e-3 and rep["p999_rel_CD"] <= 2e-2, f"{label}: {rep}"
+            k = TENSOR_NARROW48_FACTOR if narrow48 else 1.0
+            assert rep["median_rel"] <= k * 1.5e-3, f"{label}: {rep}"  # measured 6.0e-4 .. 6.4e-4 (profiles/r2_parity_maxima_session_a.json)
+            assert rep["p999_abs_CL"] <= k * 5e-3 and rep["p999_abs_CM"] <= k * 1e-3 and rep["p999_rel_CD"] <= k * 2e-2, f"{label}: {rep}"
         return rep
     rep = error_report(got, want, re, latent_atol=TENSOR_FP32_LATENT_ATOL if variant == "tensor_fp32" else LATENT_ATOL)
     _record(variant + ("" if big else " (small blocks)"), rep, ("worst_ratio", "median_rel", "frac_rel_le_1e-5"))

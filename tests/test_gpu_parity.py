@@ -392,12 +392,81 @@ def test_tensor_variant_invariants_are_exact(evaluator):
         np.testing.assert_array_equal(out_m.cpu().numpy(), unmirror_outputs(out.cpu().numpy()))
 
 
-def test_tensor_variant_refuses_other_models(evaluator):
+def test_tensor_variant_refuses_what_it_cannot_run(evaluator):
+    from neuralfoil_b200 import Evaluator
+
     raw = synthetic.sample_training_distribution(8, seed=0)
-    with pytest.raises(ValueError, match="tensor-core variant"):
-        evaluator.evaluate_host(raw, "xlarge", variant="tensor")
     with pytest.raises(ValueError, match="variant"):
         evaluator.evaluate_host(raw, "xxxlarge", variant="bf16")
+    deep = Evaluator(device=0, extra_models={"odd_deep": _random_network([25] + [33] * 15 + [198], 5)})  # 16 affine layers
+    try:
+        with pytest.raises(ValueError, match="tensor-core variants"):
+            deep.evaluate_host(raw, "odd_deep", variant="tensor")
+        assert deep.evaluate_host(raw, "odd_deep").shape == (198, 8)  # the fp32 path takes it
+    finally:
+        deep.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Tensor-core variants of the NARROW models (nfb_tcn.cuh): 128-wide (large, xlarge = the reference's default model) and
+# 64-wide (xxsmall .. medium), trained weights: same tolerances, same exact invariants as the wide models' kernels
+# ---------------------------------------------------------------------------------------------
+NARROW = ["xxsmall", "xsmall", "small", "medium", "large", "xlarge"]
+
+
+@pytest.mark.parametrize("variant", ["tensor", "tensor_fp32"])
+@pytest.mark.parametrize("size", NARROW)
+def test_narrow_tensor_variants_match_oracle(evaluator, oracle, size, variant):
+    raw = synthetic.sample_training_distribution(20011, seed=11)
+    want = oracle.evaluate_raw(raw, size)
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant=variant)
+    parity.assert_parity(got, want, raw[19], label=f"{variant} {size}", variant=variant, narrow48=size in ("xxsmall", "xsmall"))
+    ref = evaluator.evaluate_host(raw, size, out_dtype=np.float64)
+    assert not np.array_equal(got, ref)  # really another kernel ...
+    assert np.nanmax(np.abs(got[1] - ref[1])) <= 7.5e-2  # ... of the same network
+
+
+@pytest.mark.parametrize("variant", ["tensor", "tensor_fp32"])
+@pytest.mark.parametrize("n", [1, 3, 63, 64, 65, 127, 129, 1000, 9473])
+@pytest.mark.parametrize("size", ["medium", "xlarge"])
+def test_narrow_tensor_variants_ragged_batch_sizes(evaluator, oracle, size, n, variant):
+    raw = synthetic.sample_training_distribution(n, seed=300 + n)
+    got = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant=variant)
+    assert got.shape == (198, n)
+    parity.assert_parity(got, oracle.evaluate_raw(raw, size), raw[19], variant=variant, label=f"{variant} {size} n={n}")
+    scal = evaluator.evaluate_host(raw, size, out_dtype=np.float64, variant=variant, outputs="scalars")
+    assert np.array_equal(scal, got[:6], equal_nan=True)
+
+
+@pytest.mark.parametrize("variant", ["tensor", "tensor_fp32"])
+def test_narrow_tensor_variants_golden_far_ood_and_invariants(evaluator, golden_dir, variant):
+    import torch
+
+    g = np.load(golden_dir / "golden_all_sizes.npz")
+    raw48 = g["raw"]
+    w = np.array([0.15, 0.20, 0.15, 0.20, 0.15, 0.20, 0.15, 0.15])
+    sym = dict(upper_weights=w, lower_weights=-w, leading_edge_weight=0.0, TE_thickness=0.002)
+    n = 100_000
+    raw = synthetic.sample_training_distribution(n, seed=4).astype(np.float32)
+    d_raw = torch.from_numpy(raw).cuda()
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).cuda()
+    for size in ("medium", "large", "xlarge"):
+        got = evaluator.evaluate_host(raw48, size, out_dtype=np.float64, variant=variant)  # incl. alpha = +-90, +-180, Re = 1e2, 1e10
+        assert np.isfinite(got[:6]).all(), size
+        parity.assert_parity(got, g[f"out_{size}"], raw48[19], variant=variant, label=f"{variant} {size} fixture")
+        aero = evaluator.get_aero_from_kulfan_parameters(sym, alpha=0.0, Re=1e6, model_size=size, variant=variant)
+        assert aero["CL"][0] == 0.0 and aero["CM"][0] == 0.0 and aero["Top_Xtr"][0] == aero["Bot_Xtr"][0]
+        out = evaluator.evaluate_device(d_raw, size, variant=variant)
+        out_m = evaluator.evaluate_device(torch.from_numpy(mirrored(raw)).cuda(), size, variant=variant)
+        out_p = evaluator.evaluate_device(d_raw[:, perm].contiguous(), size, variant=variant)
+        torch.cuda.synchronize()
+        assert torch.equal(out_p, out[:, perm]), size
+        np.testing.assert_array_equal(out_m.cpu().numpy(), unmirror_outputs(out.cpu().numpy()))
+    bad = raw[:, :5000].copy()
+    bad[18, 7] = np.nan
+    out_bad = evaluator.evaluate_host(bad, "xlarge", variant=variant)
+    out_ok = evaluator.evaluate_host(raw[:, :5000], "xlarge", variant=variant)
+    assert np.isnan(out_bad[1, 7]) and np.array_equal(np.delete(out_bad, 7, axis=1), np.delete(out_ok, 7, axis=1))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,130 @@
+"""
+The training step on the GPU (nfb_train_step_device) against the float64 oracle
+(oracle/training_oracle.py, itself pinned by torch autograd of the reference's Net: tests/test_training_oracle.py):
+the 198 weighted loss components and d loss / d W_l, d loss / d b_l of every layer, for a 64-, a 128-, a 256- and a 512-wide
+network, batches that are not multiples of any tile, NaN targets in every column, the reference's batch size (256) and a
+large one; run-to-run bit reproducibility of the gradients; and torch CUDA autograd of the same Net in float32 as the
+"plain PyTorch fp32 reference" yardstick.
+"""
+
+import numpy as np
+import pytest
+
+from neuralfoil_b200 import synthetic
+from neuralfoil_b200.main import default_loss_weights, layers_from_params, nn_weights_dir
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+# Gradient tolerance: |got - want| <= GRAD_RTOL * (|want| + max |want| of that array).  fp32 accumulation over
+# batch x 2 columns of products whose signs vary; set to 3 x the worst figure measured on B200 (profiles/r2_parity_maxima*.json).
+GRAD_RTOL = 3e-4
+LOSS_RTOL = 2e-5
+
+
+def _params(size):
+    if size == "xxxlarge":
+        return synthetic.synthetic_xxxlarge_params()
+    with np.load(nn_weights_dir / f"nn-{size}.npz") as f:
+        return {k: f[k] for k in f.files}
+
+
+def _case(oracle, size, batch, seed, nan_fraction=0.15):
+    """Inputs over the training distribution (featurised by the oracle), targets = the network's own prediction + noise."""
+    from oracle import training_oracle as T
+
+    rng = np.random.default_rng(seed)
+    raw = synthetic.sample_training_distribution(batch, seed=seed)
+    from oracle.neuralfoil_oracle import featurise
+
+    x = np.ascontiguousarray(featurise(raw).T, dtype=np.float32)  # (batch, 25), the reference's `inputs_scaled`
+    layers = [(w.astype(np.float64), b.astype(np.float64)) for w, b in layers_from_params(_params(size))]
+    dist = oracle.dist
+    fused, _, _, _ = T.forward(layers, dist["mean"], dist["inv_cov"], x.astype(np.float64))
+    y = fused + rng.standard_normal(fused.shape) * 0.04
+    y[:, 0] = (rng.random(batch) < 0.8).astype(float)
+    y[:, 4:6] = np.clip(y[:, 4:6] + rng.standard_normal((batch, 2)) * 0.3, -0.2, 1.2)
+    y[rng.random(y.shape) < nan_fraction] = np.nan
+    return layers, dist, x, y.astype(np.float32)
+
+
+def _check(evaluator, oracle, size, batch, seed, label):
+    import torch
+    from oracle import training_oracle as T
+
+    layers, dist, x, y = _case(oracle, size, batch, seed)
+    want_c, want_g = T.train_step(layers, dist["mean"], dist["inv_cov"], x.astype(np.float64), y.astype(np.float64))
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    loss, grads = evaluator.train_step_device(xd, yd, size)
+    torch.cuda.synchronize()
+    got_c = loss.cpu().numpy()
+    assert np.isfinite(got_c).all()
+    np.testing.assert_allclose(got_c, want_c, rtol=LOSS_RTOL, atol=LOSS_RTOL * np.abs(want_c).max(), err_msg=label)
+    assert abs(got_c.sum() - want_c.sum()) <= LOSS_RTOL * abs(want_c.sum())
+    worst = 0.0
+    for l, ((gw, gb), (ww, wb)) in enumerate(zip(grads, want_g)):
+        for name, g, w in (("W", gw, ww), ("b", gb, wb)):
+            g = g.cpu().numpy().astype(np.float64)
+            assert g.shape == w.shape and np.isfinite(g).all(), (label, l, name)
+            ratio = np.abs(g - w) / (np.abs(w) + np.abs(w).max())
+            worst = max(worst, float(ratio.max()))
+            assert ratio.max() <= GRAD_RTOL, f"{label}: d{name}_{l} off by {ratio.max():.2e} of its scale"
+    parity._record("training gradients", {"worst_ratio": worst / GRAD_RTOL, "median_rel": float(np.abs(got_c - want_c).max() / np.abs(want_c).max())},
+                   ("worst_ratio", "median_rel"))
+    return loss, grads, (xd, yd)
+
+
+@pytest.mark.parametrize("size,batch", [("xxsmall", 256), ("xsmall", 1000), ("large", 777), ("xlarge", 256), ("xlarge", 4099),
+                                        ("xxlarge", 515), ("xxxlarge", 256), ("xxxlarge", 1001)])
+def test_training_step_matches_oracle(evaluator, oracle, size, batch):
+    _check(evaluator, oracle, size, batch, seed=batch + len(size), label=f"{size} batch {batch}")
+
+
+def test_training_step_is_bit_reproducible_and_stream_ordered(evaluator, oracle):
+    import torch
+
+    loss0, grads0, (xd, yd) = _check(evaluator, oracle, "xlarge", 20_000, seed=5, label="xlarge 20000")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        loss1, grads1 = evaluator.train_step_device(xd, yd, "xlarge")
+    torch.cuda.synchronize()
+    for (a, b), (c, d) in zip(grads0, grads1):
+        assert torch.equal(a, c) and torch.equal(b, d)  # fixed-order reduction of the column splits
+    assert torch.allclose(loss0, loss1, rtol=1e-12, atol=0)  # double-precision atomics: order-dependent in the last bits only
+
+
+def test_training_step_against_torch_fp32_autograd(evaluator, oracle):
+    """The plain PyTorch fp32 reference of the same op: the reference's Net in float32 on the GPU, torch autograd."""
+    import torch
+    from test_training_oracle import torch_reference  # the CPU float64 restatement, re-used for its structure
+
+    size, batch = "large", 2048
+    layers, dist, x, y = _case(oracle, size, batch, seed=21)
+    want_c, want_g = torch_reference(layers, dist, x.astype(np.float64), y.astype(np.float64), default_loss_weights(), 0.05)
+    loss, grads = evaluator.train_step_device(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), size)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(loss.cpu().numpy().sum(), want_c.sum(), rtol=LOSS_RTOL)
+    for (gw, gb), (tw, tb) in zip(grads, want_g):
+        assert np.abs(gw.cpu().numpy() - tw).max() <= GRAD_RTOL * 2 * np.abs(tw).max()
+        assert np.abs(gb.cpu().numpy() - tb).max() <= GRAD_RTOL * 2 * np.abs(tb).max()
+
+
+def test_training_step_argument_errors(evaluator):
+    import torch
+
+    x = torch.zeros((8, 25), device="cuda")
+    y = torch.zeros((8, 198), device="cuda")
+    with pytest.raises(ValueError):
+        evaluator.train_step_device(x.cpu(), y, "small")
+    with pytest.raises(ValueError):
+        evaluator.train_step_device(x, y[:4], "small")
+    with pytest.raises(ValueError):
+        evaluator.train_step_device(x.double(), y, "small")
+    with pytest.raises(ValueError):
+        evaluator.train_step_device(x, y, "small", loss_weights=np.ones(5))
+    with pytest.raises(ValueError):
+        evaluator.train_step_device(x, y, "small", huber_delta=0.0)
+    with pytest.raises(ValueError):
+        evaluator.train_step_device(x, y, "nonexistent")
