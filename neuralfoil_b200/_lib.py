@@ -25,7 +25,7 @@ OUTPUT_SCALARS = 0x100  # NFB_OUTPUT_SCALARS: OR-ed into the variant, only the s
 DEBUG_FFMA_TILED = 0x1000  # cross-check kernels (tests / A-B only), OR-ed into the variant
 DEBUG_TC_ONE_SM = 0x2000
 DEBUG_FLAGS = {"ffma_tiled": DEBUG_FFMA_TILED, "tc_one_sm": DEBUG_TC_ONE_SM}
-TUNE_SMALL_BATCH_MAX, TUNE_TC2_MAX_GRID, TUNE_HOST_THREADS = 0, 1, 2
+TUNE_SMALL_BATCH_MAX, TUNE_TC2_MAX_GRID, TUNE_HOST_THREADS, TUNE_MAPPED_MAX = 0, 1, 2, 3
 N_SCALAR_ROWS = 6
 VARIANTS = {"fp32": VARIANT_FP32_FFMA, "tensor": VARIANT_TENSOR_FP16, "tensor_fp32": VARIANT_TENSOR_FP16X3}
 

@@ -176,6 +176,7 @@ struct nfb_context {
   double quad[nfb::N_MAHA] = {0};
   std::unordered_set<const void*> configured;  // kernels whose dynamic shared memory limit has been raised on this device
   int64_t tune_small_batch_max = -1;  // nfb_set_tuning; -1 = the measured defaults
+  int64_t tune_mapped_max = -1;
   int tune_tc2_max_grid = 0;
   int host_thread_cap = 0;            // 0 = all; nfb_multi_* divides the host cores among its devices
   Model models[NFB_MAX_MODELS];
@@ -983,6 +984,10 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   // Small batches (a design optimiser's per-iteration call): pack everything into one pinned block so
   // that there is exactly one H2D copy, one launch and one D2H copy.
   const bool small = n <= 16384;
+  // The smallest batches (an optimiser's single query): the kernel reads its inputs from and writes its results to the pinned
+  // staging block directly (zero-copy over PCIe: pinned host memory is device-addressable under UVA) -- one launch and one
+  // synchronisation, no copy commands at all.
+  const bool mapped = small && n <= (ctx->tune_mapped_max >= 0 ? ctx->tune_mapped_max : 1024);
   // Large batches in pageable memory (NumPy arrays): staged through pinned buffers by all host cores, see host_threads().
   const bool stage_out = !small && is_pageable(out);
   bool stage_in = false;
@@ -1017,8 +1022,10 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
     HostSlot& s = ctx->slots[ci & 1];
     const int64_t cn = std::min<int64_t>(chunk, n - c0);
     NFB_CUDA(cudaStreamSynchronize(s.stream));  // the slot's previous chunk has fully landed
-    if ((rc = ensure(&s.d_in, &s.in_bytes, in_need, false)) != NFB_OK) return rc;
-    if ((rc = ensure(&s.d_out, &s.out_bytes, dev_out_need, false)) != NFB_OK) return rc;
+    if (!mapped) {
+      if ((rc = ensure(&s.d_in, &s.in_bytes, in_need, false)) != NFB_OK) return rc;
+      if ((rc = ensure(&s.d_out, &s.out_bytes, dev_out_need, false)) != NFB_OK) return rc;
+    }
 
     const void* d_rows[nfb::N_RAW];
     int64_t d_strides[nfb::N_RAW];
@@ -1038,9 +1045,9 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
           for (int64_t i = 0; i < cn; ++i) memcpy(dst + i * isz, src + size_t(c0 + i) * in_strides[r] * isz, isz);
           d_strides[r] = 1;
         }
-        d_rows[r] = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
+        d_rows[r] = (mapped ? hs : static_cast<char*>(s.d_in)) + size_t(r) * chunk * isz;
       }
-      NFB_CUDA(cudaMemcpyAsync(s.d_in, hs, in_need, cudaMemcpyHostToDevice, s.stream));
+      if (!mapped) NFB_CUDA(cudaMemcpyAsync(s.d_in, hs, in_need, cudaMemcpyHostToDevice, s.stream));
     } else if (stage_in) {
       if ((rc = ensure(&s.h_in, &s.h_in_bytes, in_need, true)) != NFB_OK) return rc;
       char* hs = static_cast<char*>(s.h_in);
@@ -1080,12 +1087,13 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
         d_rows[r] = dst;
       }
     }
-    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype, s.d_out, chunk, dev_out_dtype, s.stream);
+    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype,
+                          mapped ? static_cast<void*>(static_cast<char*>(s.h_stage) + in_need) : s.d_out, chunk, dev_out_dtype, s.stream);
     if (rc != NFB_OK) return rc;
     char* out_c = static_cast<char*>(out) + size_t(c0) * osz;
     if (small) {
       char* hs_out = static_cast<char*>(s.h_stage) + in_need;
-      NFB_CUDA(cudaMemcpyAsync(hs_out, s.d_out, dev_out_need, cudaMemcpyDeviceToHost, s.stream));
+      if (!mapped) NFB_CUDA(cudaMemcpyAsync(hs_out, s.d_out, dev_out_need, cudaMemcpyDeviceToHost, s.stream));
       NFB_CUDA(cudaStreamSynchronize(s.stream));
       if (small_widen) {
         unstage_output(reinterpret_cast<const float*>(hs_out), chunk, out_c, out_ld, true, out_rows, cn, thread_cap);
@@ -1431,6 +1439,7 @@ int nfb_set_tuning(nfb_context* ctx, int key, int64_t value) {
     case NFB_TUNE_SMALL_BATCH_MAX: ctx->tune_small_batch_max = value; return NFB_OK;
     case NFB_TUNE_TC2_MAX_GRID: ctx->tune_tc2_max_grid = int(value); return NFB_OK;
     case NFB_TUNE_HOST_THREADS: ctx->host_thread_cap = int(std::max<int64_t>(0, value)); return NFB_OK;
+    case NFB_TUNE_MAPPED_MAX: ctx->tune_mapped_max = value; return NFB_OK;
   }
   return fail(NFB_ERR_INVALID_ARGUMENT, "unknown tuning key %d", key);
 }

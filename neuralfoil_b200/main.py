@@ -253,10 +253,10 @@ class Evaluator:
             raise ValueError(f"Invalid {variant=}. Must be one of {set(_lib.VARIANTS)}.") from None
 
     def set_tuning(self, small_batch_max: int | None = None, tc2_max_grid: int | None = None,
-                   host_threads: int | None = None) -> None:
+                   host_threads: int | None = None, mapped_max: int | None = None) -> None:
         """Experiment knobs of include/neuralfoil_b200.h (nfb_set_tuning); the defaults are the measured optima."""
         for key, value in ((_lib.TUNE_SMALL_BATCH_MAX, small_batch_max), (_lib.TUNE_TC2_MAX_GRID, tc2_max_grid),
-                           (_lib.TUNE_HOST_THREADS, host_threads)):
+                           (_lib.TUNE_HOST_THREADS, host_threads), (_lib.TUNE_MAPPED_MAX, mapped_max)):
             if value is not None:
                 _lib.check(self._lib.nfb_set_tuning(self._ctx, key, int(value)))
 

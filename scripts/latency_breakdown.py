@@ -34,3 +34,16 @@ for size in ("xxsmall", "xlarge"):
         for _ in range(50): ev.evaluate_device(r, size, out=out)
         e1.record(); torch.cuda.synchronize()
         print(size, "kernel time per launch at n=1 (us, back-to-back launches)", e0.elapsed_time(e1) / 50 * 1e3)
+# zero-copy (mapped pinned staging block) against explicit copies, library call alone
+for size in ("xxsmall", "xlarge"):
+    mid = ev._model_id(size)
+    rows, n = nfm.prepare_raw_rows(K, 3.0, 1e6, 9.0, 1.0, 1.0)
+    for nq in (1, 64, 1024):
+        raw = np.ascontiguousarray(synthetic.sample_training_distribution(nq, seed=2))
+        block = np.empty((198, (nq + 3) & ~3)); ptrs = (C.c_void_p * 23)(*[raw[i].ctypes.data for i in range(23)]); strides = (C.c_int64 * 23)(*([1] * 23))
+        f = lambda: ev._lib.nfb_eval_host(ev._ctx, mid, 0, nq, ptrs, strides, 1, block.ctypes.data_as(C.c_void_p), block.shape[1], 1, 0)
+        ev.set_tuning(mapped_max=0)
+        t_copy = med(f)
+        ev.set_tuning(mapped_max=-1)
+        t_map = med(f)
+        print(size, f"nfb_eval_host n={nq}: explicit copies {t_copy:.1f} us, zero-copy {t_map:.1f} us")
