@@ -554,6 +554,57 @@ def main():
         except Exception as e:  # noqa: BLE001  (an extra must never cost the headline line)
             scalar_grad_extra = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- the training step (forward + loss + backward to every layer's weight gradients), device-resident ----
+    training_extra = None
+    if variant == "fp32" and not args.no_extras and not threads_mode:
+        try:
+            nb = 65536
+            xt = torch.randn((nb, 25), device="cuda") * 0.3
+            yt = torch.randn((nb, 198), device="cuda") * 0.1
+            yt[:, 0] = (torch.rand(nb, device="cuda") < 0.8).float()
+            for _ in range(2):
+                ev.train_step_device(xt, yt, size)
+            barrier()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(3):
+                ev.train_step_device(xt, yt, size)
+            t1e.record()
+            barrier()
+            t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / 3
+            tf = 3 * FLOP_PER_QUERY[size] * nb / (t_ms * 1e-3) / 1e12
+            training_extra = {"value": world * nb / (t_ms * 1e-3), "unit": "samples/s", "batch": nb, "ms_per_step": t_ms,
+                              "achieved_tflops": tf, "flop_model": "3 x the forward pass (forward, d a = W^T d z, d W = d z a^T), both twins",
+                              "kernels": "nfb_train_fwdbwd_kernel + nfb_train_wgrad_kernel + nfb_train_reduce_kernel (fp32 FFMA2)",
+                              "reference": "training/train.py:56-114, 194-236 (forward, loss, backward; the optimiser step stays with the caller)"}
+            del xt, yt
+        except Exception as e:  # noqa: BLE001
+            training_extra = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- the reference's DEFAULT model (xlarge, main.py:71) on the three kernels, device-resident, briefly ----
+    default_model_extra = None
+    if size != "xlarge" and not args.no_extras and not threads_mode:
+        try:
+            nd = min(n_local, 4_000_000)
+            rd = raw_dev[rank][:, :nd].contiguous()
+            od = torch.empty((198, (nd + 3) & ~3), dtype=torch.float32, device="cuda")
+            default_model_extra = {"model_size": "xlarge", "queries_per_launch": nd, "unit": UNIT}
+            for v in ("fp32", "tensor", "tensor_fp32"):
+                for _ in range(2):
+                    ev.evaluate_device(rd, "xlarge", out=od, variant=v)
+                barrier()
+                t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0e.record()
+                for _ in range(5):
+                    ev.evaluate_device(rd, "xlarge", out=od, variant=v)
+                t1e.record()
+                barrier()
+                t_ms = max_over_ranks(t0e.elapsed_time(t1e)) / 5
+                default_model_extra[v] = world * nd / (t_ms * 1e-3)
+            del rd, od
+        except Exception as e:  # noqa: BLE001
+            default_model_extra = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         peaks_path = REPO / "MEASURED_PEAKS.json"
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -617,6 +668,9 @@ def main():
                              "achieved": mult * achieved_tflops, "frac": mult * achieved_tflops / bf16_peak,
                              "tensor_macs_per_algorithmic_mac": mult})
             roofline.pop("frac_of_nominal_74.4", None)
+        if training_extra and "achieved_tflops" in training_extra:
+            training_extra["roofline"] = {"bound": "fp32", "achieved": training_extra["achieved_tflops"], "peak": fp32_peak, "unit": "TFLOP/s",
+                                          "frac": training_extra["achieved_tflops"] / fp32_peak if fp32_peak else None}
         cpu_baseline = None
         if not args.no_cpu_baseline and n_dev == 1:
             sample = args.cpu_sample or auto_cpu_sample(size)
@@ -634,7 +688,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "tensor_variant": tensor_extra,
             "tensor_fp32_variant": tensor_fp32_extra, "weak_scaling": weak_extra, "jacobian": jacobian_extra,
-            "scalar_gradient": scalar_grad_extra, "checksum_first_1000": checksum,
+            "scalar_gradient": scalar_grad_extra, "training_step": training_extra, "default_model_xlarge": default_model_extra,
+            "checksum_first_1000": checksum,
             "process_model": "one process, one host thread per device" if threads_mode else "one process per GPU (torchrun)" if world > 1 else "one process, one GPU",
         }
         print(json.dumps(line), flush=True)

@@ -102,7 +102,7 @@ void nfb_destroy(nfb_context* ctx);
  *   NFB_TUNE_TC2_MAX_GRID     at most `value` CTAs (rounded down to whole pairs) for the CTA-pair tensor kernels (0 = all SMs)
  *   NFB_TUNE_HOST_THREADS     at most `value` host threads stage pageable caller memory in nfb_eval_host (0 = all cores, max 32)
  *   NFB_TUNE_MAPPED_MAX       nfb_eval_host: batches of at most `value` queries run zero-copy -- the kernel reads and writes the
- *                             pinned staging block directly, one launch and one synchronisation (-1 = default 1024, 0 = never) */
+ *                             pinned staging block directly, one launch and one synchronisation (-1 = default 128, 0 = never) */
 enum nfb_tuning { NFB_TUNE_SMALL_BATCH_MAX = 0, NFB_TUNE_TC2_MAX_GRID = 1, NFB_TUNE_HOST_THREADS = 2, NFB_TUNE_MAPPED_MAX = 3 };
 int nfb_set_tuning(nfb_context* ctx, int key, int64_t value);
 

@@ -20,9 +20,9 @@
 //     column 256 (the tensor core truncates at every accumulation, nfb_tc.cuh).
 //   * Precisions as in nfb_tc.cuh: SPLIT = 1 "tensor" (fp16 operands, first layer fp32-exact by K-concatenation
 //     [x_hi | x_lo | x_hi | -] . [W_hi | W_hi | W_lo | 0]); SPLIT = 3 "tensor_fp32" (a_hi w_hi + a_lo w_hi + a_hi w_lo).
-//   * Roles (384 threads): warp 0 weight producer; warp 1 MMA issue; warps 2..9 epilogue (tcgen05.ld -> scale, bias, SiLU
+//   * Roles (448 threads): warp 0 weight producer; warp 1 MMA issue; warps 2..9 epilogue (tcgen05.ld -> scale, bias, SiLU
 //     -> fp16 -> smem; the two warps of a TMEM lane quarter split the features) and, after the last layer, the decode
-//     straight from the accumulators (nfb_tc2.cuh's); warps 10..11 featurise the NEXT tile (fp64) into a first-layer input
+//     straight from the accumulators (nfb_tc2.cuh's); warps 10..13 featurise the NEXT tile (fp64, one row per thread) into a first-layer input
 //     buffer of its own while the current tile's layers run.
 //   * Schedule: a tile's layers run one after the other -- MMA sweep, then epilogue, then the next sweep -- with the next
 //     tile's layer 0 starting as soon as the last accumulators are read, i.e. under the decode.  (Not yet: two tiles in
@@ -40,8 +40,8 @@ using nfb::tc2::decode_group_store1;
 using nfb::tc2::decode_groups4_store;
 using nfb::tc2::silu_ex2;
 
-constexpr int TCN_THREADS = 384;
-constexpr int TCN_EPI_WARPS = 8, TCN_FW_WARP0 = 10, TCN_FW_WARPS = 2;
+constexpr int TCN_THREADS = 448;
+constexpr int TCN_EPI_WARPS = 8, TCN_FW_WARP0 = 10, TCN_FW_WARPS = 4;
 constexpr int TCN_LAST_N = 208;        // packed rows of the last layer (200 used), a multiple of 16
 constexpr int TCN_BIAS_LD = 256;       // floats per layer in the bias block
 
@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) nfb_tcn_kernel(const TcParams 
       issue_layer(0);
       commit(bar_d);
       commit(bar_infree);
+      if (tp.dbg && blockIdx.x == 0 && t == 1 && lane == 0) tp.dbg[33] = clock64();
       for (int l = 1; l < L; ++l) {
         mbar_wait(bar_a, ph_a);
         ph_a ^= 1;
@@ -233,16 +234,19 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) nfb_tcn_kernel(const TcParams 
     }
   } else if (warp >= TCN_FW_WARP0) {
     // ============================ featurise-ahead warps ============================
-    // Thread ft owns batch rows ft and ft + 64: row 2 i is query i of the tile, row 2 i + 1 its flipped twin.
+    // Thread ft owns batch row ft: row 2 i is query i of the tile, row 2 i + 1 its flipped twin.  One row per thread: a row's
+    // featurisation is ~10,000 latency-bound cycles (fp64 sin / cos / log and the 325-term quadratic form), and with two rows
+    // per thread it was what paced every narrow model (measured: profiles/r2_tcn_phase_stamps_first_version.txt).
     const int ft = tid - 32 * TCN_FW_WARP0;
     uint32_t ph_free = 0;
     for (uint32_t t = 0; t < my_tiles; ++t) {
       const long long tile_q0 = (blockIdx.x + (long long)t * gridDim.x) * NQT;
       float* const maha = maha2 + (t & 1) * ROWS;
       float* const re_s = re2 + (t & 1) * NQT;
+      if (tp.dbg && blockIdx.x == 0 && t == 2 && ft == 0) tp.dbg[46] = clock64();
 #pragma unroll 1
       for (int j = 0; j < ROWS / (32 * TCN_FW_WARPS); ++j) {
-        const int n = ft + 64 * j;
+        const int n = ft + 32 * TCN_FW_WARPS * j;
         const bool twin = n & 1;
         const long long qi = tile_q0 + (n >> 1);
         uint32_t hi[16], lo[16];
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) nfb_tcn_kernel(const TcParams 
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_in);
+      if (tp.dbg && blockIdx.x == 0 && t == 2 && ft == 0) tp.dbg[47] = clock64();
     }
   } else {
     // ============================ epilogue warps ============================

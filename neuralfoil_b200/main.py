@@ -170,6 +170,7 @@ class Evaluator:
         self._auto = devices == "auto"
         self._extra_models = dict(extra_models or {})
         self._lock = threading.Lock()
+        self._tls = threading.local()
         handle = C.c_void_p()
         if devices is not None and not self._auto:
             if device is not None:
@@ -304,6 +305,9 @@ class Evaluator:
         variant: str = "fp32", outputs: str = "all",
     ) -> dict[str, np.ndarray]:
         model_id = self._model_id(model_size)  # main.py:154-157
+        block = self._evaluate_single_case(model_id, kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower, variant, outputs)
+        if block is not None:  # one case given as scalars: an optimiser's per-iteration call (BASELINE configs[3])
+            return dict(zip(_OUTPUT_KEYS, block[:, :1]))
         rows, n_cases = prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower)
         block = self._evaluate_host_rows(model_id, rows, n_cases, np.float64, variant=variant, outputs=outputs)
         # Row views of one (198, ld) block: each value is a contiguous (N,) float64 array, as in the
@@ -516,6 +520,42 @@ class Evaluator:
             )
         )
         return out[:, :n]
+
+    def _evaluate_single_case(self, model_id, kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower, variant, outputs):
+        """
+        Fast path of the drop-in call for ONE case whose flow inputs are scalars and whose Kulfan weights are plain length-8
+        vectors: the 23 numbers go straight into a per-thread (23, 1) block whose pointer table is built once.  Returns the
+        (198, 4) result block, or None when the arguments are anything else (the general path then validates them and raises
+        the reference's errors).  Same library call, same bits.
+        """
+        try:
+            upper, lower = kulfan_parameters["upper_weights"], kulfan_parameters["lower_weights"]
+            le, te = kulfan_parameters["leading_edge_weight"], kulfan_parameters["TE_thickness"]
+            if len(upper) != 8 or len(lower) != 8:
+                return None
+            if (np.ndim(alpha) or np.ndim(Re) or np.ndim(n_crit) or np.ndim(xtr_upper) or np.ndim(xtr_lower) or np.ndim(le)
+                    or np.ndim(te) or np.ndim(upper) != 1 or np.ndim(lower) != 1):
+                return None
+            tls = self._tls
+            buf = getattr(tls, "buf", None)
+            if buf is None:
+                buf = tls.buf = np.empty((_lib.N_RAW_ROWS, 1), dtype=np.float64)
+                base = buf.__array_interface__["data"][0]
+                tls.ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*range(base, base + _lib.N_RAW_ROWS * 8, 8))
+            buf[0:8, 0] = upper
+            buf[8:16, 0] = lower
+            buf[16:23, 0] = (le, te, alpha, Re, n_crit, xtr_upper, xtr_lower)
+        except (TypeError, ValueError, KeyError, IndexError):
+            return None
+        n_rows, flag = self._rows_and_flag(outputs)
+        block = np.empty((n_rows, 4), dtype=np.float64)
+        _lib.check(
+            self._lib.nfb_eval_host(
+                self._ctx, model_id, self._variant(variant) | flag, 1, tls.ptrs, _ONES_23, _lib.F64,
+                block.__array_interface__["data"][0], 4, _lib.F64, 0,
+            )
+        )
+        return block
 
     def _evaluate_host_rows(self, model_id: int, rows, n: int, out_dtype, chunk: int = 0, variant: str = "fp32",
                             outputs: str = "all"):

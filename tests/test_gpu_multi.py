@@ -227,12 +227,12 @@ def test_out_argument_is_validated(evaluator):
 
 @pytest.mark.parametrize("n", [1, 5, 64, 1000, 1024])
 def test_zero_copy_small_batches_equal_copied_ones(evaluator, n):
-    """nfb_eval_host runs batches <= 1024 zero-copy (the kernel reads / writes the pinned staging block): same bits."""
+    """nfb_eval_host runs the smallest batches zero-copy (the kernel reads / writes the pinned staging block): same bits."""
     raw = synthetic.sample_training_distribution(n, seed=900 + n)
     try:
         evaluator.set_tuning(mapped_max=0)
         copied = [evaluator.evaluate_host(raw, size, out_dtype=dt) for size in ("xxsmall", "xlarge") for dt in (np.float32, np.float64)]
-        evaluator.set_tuning(mapped_max=-1)
+        evaluator.set_tuning(mapped_max=4096)
         mapped = [evaluator.evaluate_host(raw, size, out_dtype=dt) for size in ("xxsmall", "xlarge") for dt in (np.float32, np.float64)]
     finally:
         evaluator.set_tuning(mapped_max=-1)

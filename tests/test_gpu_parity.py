@@ -720,10 +720,7 @@ def test_vjp_matches_oracle_and_jacobian(evaluator, oracle, size):
     scale[19] = raw[19]
     np.testing.assert_allclose(grad * scale, mine * scale, rtol=2e-4, atol=2e-5)   # same derivatives, summed in fp32 vs fp64
     want_v, want_j = oracle.jacobian_raw(raw, size)
-    want = np.einsum("rtq,rq->tq", want_j, cot)
-    err = np.abs(grad - want) * scale
-    ref = np.abs(want) * scale + np.einsum("rq,rq->q", np.abs(cot), np.abs(want_v))[None, :] * 1e-1
-    assert (err <= 5e-3 * ref + 1e-6).mean() > 0.999 and np.median(err / np.maximum(ref, 1e-30)) < 1e-5
+    parity.assert_vjp_parity(grad, want_j, want_v, cot, raw, label=f"forward-mode kernel: {size}")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -813,10 +810,7 @@ def test_scalar_gradient_matches_oracle_and_forward_mode(evaluator, oracle, size
     scale = parity.JAC_INPUT_SCALE.copy()[:, None] * np.ones((1, n))
     scale[19] = raw[19]
     want_v, want_j = oracle.jacobian_raw(raw, size)
-    want = np.einsum("rtq,rq->tq", want_j[:6], cot)
-    err = np.abs(grad - want) * scale
-    ref = np.abs(want) * scale + np.einsum("rq,rq->q", np.abs(cot), np.abs(want_v[:6]))[None, :] * 1e-1
-    assert (err <= 5e-3 * ref + 1e-6).mean() > 0.999 and np.median(err / np.maximum(ref, 1e-30)) < 1e-5
+    parity.assert_vjp_parity(grad, want_j[:6], want_v[:6], cot, raw, label=f"scalar-gradient kernel: {size}")
     cot198 = np.zeros((198, n))
     cot198[:6] = cot
     _, forward_mode = evaluator.evaluate_vjp_host(raw, cot198, size)
@@ -867,18 +861,20 @@ def test_reverse_vjp_all_outputs_matches_forward_mode_and_oracle(evaluator, orac
     assert values.shape == (198, n) and grad.shape == (23, n)
     np.testing.assert_array_equal(values, evaluator.evaluate_host(raw, size, out_dtype=np.float64))
     _, forward_mode = evaluator.evaluate_vjp_host(raw, cot, size, reverse=False)
-    scale = parity.JAC_INPUT_SCALE.copy()[:, None] * np.ones((1, n))
-    scale[19] = raw[19]
     want_v, want_j = oracle.jacobian_raw(raw, size)
-    want = np.einsum("rtq,rq->tq", want_j, cot)
-    ref = np.abs(want) * scale + np.einsum("rq,rq->q", np.abs(cot), np.abs(want_v))[None, :] * 1e-1
-    err = np.abs(grad - want) * scale
-    err_fwd = np.abs(forward_mode - want) * scale
-    ok, ok_fwd = (err <= 5e-3 * ref + 1e-6), (err_fwd <= 5e-3 * ref + 1e-6)
-    assert ok.mean() >= ok_fwd.mean() - 1e-3 and ok.mean() > 0.98, (ok.mean(), ok_fwd.mean())
-    assert np.median(err / np.maximum(ref, 1e-30)) < 1e-5
-    between = np.abs(grad - forward_mode) * scale  # two fp32 evaluations of the same derivative
-    assert (between <= 5e-3 * ref + 1e-6).mean() > 0.999 and np.median(between / np.maximum(ref, 1e-30)) < 1e-5
+    # theta's derivative diverges where the edge velocity crosses zero: the elementwise bound is stated on the queries whose
+    # 64 stations all have |ue| >= VJP_UE_WELL (tests/parity.py) ...
+    well = np.abs(want_v[parity.ROW_UE]).min(axis=0) >= parity.VJP_UE_WELL
+    assert well.mean() > 0.5
+    rep = parity.assert_vjp_parity(grad, want_j, want_v, cot, raw, label=f"reverse kernel, all outputs: {size}", well=well)
+    # ... and on ALL queries the reverse pass may not do worse than the forward-mode kernel, the other fp32 evaluation of the
+    # same derivative, and the two must agree with each other
+    rep_fwd = parity.vjp_report(forward_mode, want_j, want_v, cot, raw)
+    assert rep["ok"].mean() >= rep_fwd["ok"].mean() - 1e-3, (rep["ok"].mean(), rep_fwd["ok"].mean())
+    between = np.abs(grad - forward_mode) * rep["scale"]
+    assert (between <= parity.VJP_RTOL * rep["ref"] + 1e-6).mean() > 0.999 and np.median(between / np.maximum(rep["ref"], 1e-30)) < 1e-5
+    parity._record("vjp reverse kernel, all queries", {"frac_outside": float(1 - rep["ok"].mean()), "frac_outside_fwd": float(1 - rep_fwd["ok"].mean())},
+                   ("frac_outside", "frac_outside_fwd"))
 
 
 def test_reverse_vjp_device_api_ragged_and_position_independent(evaluator):
