@@ -329,20 +329,22 @@ def main():
     ld_total = (n_total + 3) & ~3
 
     # ---- ONE batch in page-locked shared host memory: rank 0 samples it, every rank maps it ----
-    names = [None, None]
+    names = [None, None, None]
     if rank == 0:
         raw_block = sharding.SharedHostBlock(23, ld_total, np.float32, create=True)
         out_block = sharding.SharedHostBlock(198, ld_total, np.float32, create=True)
+        bl16_block = sharding.SharedHostBlock(192, ld_total, np.uint16, create=True)  # bfloat16 boundary-layer rows (mixed outputs)
         step = 1 << 21
         for s in range(0, n_total, step):  # the same sampler as ever, chunked so that 80 M queries need no 15 GB temporary
             e = min(n_total, s + step)
             raw_block.array[:, s:e] = synthetic.sample_training_distribution(e - s, seed=1000 + s // step, dtype=np.float32)
-        names = [raw_block.name, out_block.name]
+        names = [raw_block.name, out_block.name, bl16_block.name]
     if world > 1:
         dist.broadcast_object_list(names, src=0)
         if rank != 0:
             raw_block = sharding.SharedHostBlock(23, ld_total, np.float32, name=names[0])
             out_block = sharding.SharedHostBlock(198, ld_total, np.float32, name=names[1])
+            bl16_block = sharding.SharedHostBlock(192, ld_total, np.uint16, name=names[2])
         dist.barrier()
 
     # the shards this process drives: one (its own rank's) under torchrun, all of them in threads mode
@@ -426,11 +428,15 @@ def main():
     multi_ev = Evaluator(devices=list(range(n_dev)), extra_models=models, multi_threshold=0) if threads_mode else None
 
     def e2e_timed(v, outputs="all"):
-        rows = 198 if outputs == "all" else 6
+        rows = 198 if outputs == "all" else 6  # ("scalars" and "mixed": the six float32 rows)
         view_out = out_block.array[:rows]
 
         def one_pass():
-            if threads_mode:  # the single-process product call: shards, threads and landing inside nfb_multi_eval_host
+            if outputs == "mixed":  # six float32 scalars + 192 bfloat16 boundary-layer rows: 408 B per query device->host
+                s, e = ranges[rank]
+                if e > s:
+                    ev.evaluate_host_mixed_into(raw_block.array[:, s:e], size, view_out[:, s:e], bl16_block.array[:, s:e], variant=v)
+            elif threads_mode:  # the single-process product call: shards, threads and landing inside nfb_multi_eval_host
                 multi_ev.evaluate_host_into(raw_block.array[:, :n_total], size, view_out, variant=v, outputs=outputs)
             else:
                 s, e = ranges[rank]
@@ -470,6 +476,11 @@ def main():
             te = e2e_timed(other)
             extra["e2e"] = {"value": n_total / te, "unit": UNIT, "ms_per_step": te * 1e3,
                             "note": "same host path and gather as the headline's e2e; PCIe device->host moves 792 B/query"}
+            if not threads_mode:
+                tm = e2e_timed(other, outputs="mixed")
+                extra["e2e_bf16_boundary_layer"] = {"value": n_total / tm, "unit": UNIT, "ms_per_step": tm * 1e3, "d2h_bytes_per_query": 408,
+                                                    "note": "nfb_eval_host_mixed: six float32 scalars + 192 bfloat16 boundary-layer rows "
+                                                            "(the float32 results rounded to nearest), same shared pinned blocks and gather"}
         return extra
 
     def measure_scalars(v: str) -> dict:  # outputs="scalars": only the six scalar rows travel back over PCIe
@@ -702,9 +713,9 @@ def main():
     raw_dev.clear(); out_dev.clear()
     if world > 1:
         dist.barrier()
-    raw_block.close(); out_block.close()
+    raw_block.close(); out_block.close(); bl16_block.close()
     if rank == 0:
-        raw_block.unlink(); out_block.unlink()
+        raw_block.unlink(); out_block.unlink(); bl16_block.unlink()
     if world > 1:
         dist.destroy_process_group()
 

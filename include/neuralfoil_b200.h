@@ -102,7 +102,7 @@ void nfb_destroy(nfb_context* ctx);
  *   NFB_TUNE_TC2_MAX_GRID     at most `value` CTAs (rounded down to whole pairs) for the CTA-pair tensor kernels (0 = all SMs)
  *   NFB_TUNE_HOST_THREADS     at most `value` host threads stage pageable caller memory in nfb_eval_host (0 = all cores, max 32)
  *   NFB_TUNE_MAPPED_MAX       nfb_eval_host: batches of at most `value` queries run zero-copy -- the kernel reads and writes the
- *                             pinned staging block directly, one launch and one synchronisation (-1 = default 128, 0 = never) */
+ *                             pinned staging block directly, one launch and one synchronisation (-1 = default 8, 0 = never) */
 enum nfb_tuning { NFB_TUNE_SMALL_BATCH_MAX = 0, NFB_TUNE_TC2_MAX_GRID = 1, NFB_TUNE_HOST_THREADS = 2, NFB_TUNE_MAPPED_MAX = 3 };
 int nfb_set_tuning(nfb_context* ctx, int key, int64_t value);
 
@@ -142,6 +142,21 @@ int nfb_eval_device(nfb_context* ctx, int model_id, int variant, int64_t n,
 int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n,
                   const void* const* in_rows, const int64_t* in_strides, int in_dtype,
                   void* out, int64_t out_ld, int out_dtype, int64_t chunk);
+
+/* Mixed-precision outputs: as nfb_eval_device / nfb_eval_host, but the 192 boundary-layer rows (theta, H, ue/Vinf of both
+ * surfaces: output rows 6..197) are written as bfloat16 -- the fp32 results rounded to nearest, relative error <= 2^-9 -- and
+ * the six scalars stay float32: 408 instead of 792 bytes per query cross PCIe, which is what bounds the host entry point for
+ * every model but the largest on the fp32 kernel.  Any variant (not NFB_OUTPUT_SCALARS).
+ *   out_scalars   6 x out_ld float32 (rows 0..5, bit-identical to nfb_eval_*)
+ *   out_bl        192 x out_ld bfloat16 (row r - 6 = output row r); bit-identical to the bfloat16 rounding of nfb_eval_*'s rows
+ * nfb_eval_host_mixed copies straight between the caller's memory and the device, chunk by chunk on two streams: give it
+ * pinned memory (nfb_host_alloc / nfb_host_register); pageable memory works at cudaMemcpy's pageable rate. */
+int nfb_eval_device_mixed(nfb_context* ctx, int model_id, int variant, int64_t n,
+                          const void* const* in_rows, const int64_t* in_strides, int in_dtype,
+                          float* out_scalars, void* out_bl, int64_t out_ld, void* stream);
+int nfb_eval_host_mixed(nfb_context* ctx, int model_id, int variant, int64_t n,
+                        const void* const* in_rows, const int64_t* in_strides, int in_dtype,
+                        float* out_scalars, void* out_bl, int64_t out_ld, int64_t chunk);
 
 /* Outputs AND their derivatives with respect to the 23 raw inputs (forward mode, fp32 arithmetic, every model size).
  * what a design optimiser needs from the path; the reference's users obtain it by tracing main.py

@@ -11,6 +11,7 @@ from .main import (  # noqa: F401
     JACOBIAN_INPUTS,
     MODEL_SIZES,
     Evaluator,
+    bf16_bits_to_float32,
     bl_x_points,
     default_evaluator,
     default_loss_weights,

@@ -58,6 +58,16 @@ _SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
          C.c_void_p, C.c_int64, C.c_int, C.c_int64],
     ),
+    "nfb_eval_device_mixed": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+    ),
+    "nfb_eval_host_mixed": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+         C.c_void_p, C.c_void_p, C.c_int64, C.c_int64],
+    ),
     "nfb_eval_jacobian_device": (
         C.c_int,
         [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,

@@ -615,16 +615,18 @@ void fill_eval_params(const nfb_context* ctx, const Model& m, const float* blob,
   p.in_f64 = (in_dtype == NFB_F64);
   p.out_f64 = (out_dtype == NFB_F64);
   p.scalars_only = 0;
+  p.out_bl = nullptr;
   memcpy(p.mean, ctx->mean, sizeof(p.mean));
   memcpy(p.quad, ctx->quad, sizeof(p.quad));
 }
 
 int eval_device_impl(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
                      const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, void* out_bl = nullptr) {
   const Model& m = ctx->models[model_id];
   nfb::EvalParams p;
   fill_eval_params(ctx, m, m.blob, n, in_rows, in_strides, in_dtype, out, out_ld, out_dtype, p);
+  p.out_bl = out_bl;
   p.scalars_only = (variant & NFB_OUTPUT_SCALARS) ? 1 : 0;
   const bool one_sm = (variant & NFB_DEBUG_TC_ONE_SM) != 0;      // cross-check: the one-SM kernels of nfb_tc.cuh
   const bool tiled_only = (variant & NFB_DEBUG_FFMA_TILED) != 0;  // cross-check: the CTA-synchronous kernel, every batch size
@@ -987,7 +989,7 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   // The smallest batches (an optimiser's single query): the kernel reads its inputs from and writes its results to the pinned
   // staging block directly (zero-copy over PCIe: pinned host memory is device-addressable under UVA) -- one launch and one
   // synchronisation, no copy commands at all.
-  const bool mapped = small && n <= (ctx->tune_mapped_max >= 0 ? ctx->tune_mapped_max : 128);  // measured: n = 1: 31 vs 36 us, 64: 42 vs 44, 1024: 248 vs 179
+  const bool mapped = small && n <= (ctx->tune_mapped_max >= 0 ? ctx->tune_mapped_max : 8);  // measured (us, zero-copy vs copies): n = 1: 32 vs 37, 64: 51 vs 45, 1024: 188 vs 189
   // Large batches in pageable memory (NumPy arrays): staged through pinned buffers by all host cores, see host_threads().
   const bool stage_out = !small && is_pageable(out);
   bool stage_in = false;
@@ -1207,6 +1209,79 @@ int nfb_eval_vjp_reverse_device(nfb_context* ctx, int model_id, int64_t n, const
                                 int64_t grad_ld, int out_dtype, void* stream) {
   return grad_device_impl(ctx, true, model_id, n, in_rows, in_strides, in_dtype, cot, cot_ld, values, values_ld, grad, grad_ld,
                           out_dtype, stream);
+}
+
+}  // extern "C"
+
+namespace {
+int check_mixed_args(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows, const int64_t* in_strides,
+                     int in_dtype, float* out_scalars, void* out_bl, int64_t out_ld) {
+  int rc = check_eval_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out_scalars, out_ld, NFB_F32);
+  if (rc != NFB_OK) return rc;
+  if (variant & NFB_OUTPUT_SCALARS) return fail(NFB_ERR_INVALID_ARGUMENT, "NFB_OUTPUT_SCALARS has no boundary-layer rows to write as bfloat16");
+  if (n > 0 && !out_bl) return fail(NFB_ERR_INVALID_ARGUMENT, "out_bl is NULL");
+  return NFB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int nfb_eval_device_mixed(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
+                          const int64_t* in_strides, int in_dtype, float* out_scalars, void* out_bl, int64_t out_ld, void* stream) {
+  int rc = check_mixed_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out_scalars, out_bl, out_ld);
+  if (rc != NFB_OK || n == 0) return rc;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  return eval_device_impl(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out_scalars, out_ld, NFB_F32,
+                          static_cast<cudaStream_t>(stream), out_bl);
+}
+
+int nfb_eval_host_mixed(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
+                        const int64_t* in_strides, int in_dtype, float* out_scalars, void* out_bl, int64_t out_ld, int64_t chunk) {
+  int rc = check_mixed_args(ctx, model_id, variant, n, in_rows, in_strides, in_dtype, out_scalars, out_bl, out_ld);
+  if (rc != NFB_OK || n == 0) return rc;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+  NFB_CUDA(cudaSetDevice(ctx->device));
+  const size_t isz = in_dtype == NFB_F64 ? 8 : 4;
+  if (chunk <= 0) chunk = 1 << 19;
+  chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
+  constexpr int BL_ROWS = nfb::N_OUT - 6;
+  const size_t in_need = size_t(nfb::N_RAW) * chunk * isz;
+  const size_t scal_bytes = size_t(6) * chunk * 4, out_need = scal_bytes + size_t(BL_ROWS) * chunk * 2;
+  for (int64_t c0 = 0, ci = 0; c0 < n; c0 += chunk, ++ci) {
+    HostSlot& s = ctx->slots[ci & 1];
+    const int64_t cn = std::min<int64_t>(chunk, n - c0);
+    NFB_CUDA(cudaStreamSynchronize(s.stream));  // the slot's previous chunk has fully landed
+    if ((rc = ensure(&s.d_in, &s.in_bytes, in_need, false)) != NFB_OK) return rc;
+    if ((rc = ensure(&s.d_out, &s.out_bytes, out_need, false)) != NFB_OK) return rc;
+    const void* d_rows[nfb::N_RAW];
+    int64_t d_strides[nfb::N_RAW];
+    for (int r = 0; r < nfb::N_RAW; ++r) {
+      char* dst = static_cast<char*>(s.d_in) + size_t(r) * chunk * isz;
+      const char* src = static_cast<const char*>(in_rows[r]);
+      if (in_strides[r] == 0) {
+        NFB_CUDA(cudaMemcpyAsync(dst, src, isz, cudaMemcpyHostToDevice, s.stream));
+        d_strides[r] = 0;
+      } else if (in_strides[r] == 1) {
+        NFB_CUDA(cudaMemcpyAsync(dst, src + size_t(c0) * isz, size_t(cn) * isz, cudaMemcpyHostToDevice, s.stream));
+        d_strides[r] = 1;
+      } else {
+        NFB_CUDA(cudaMemcpy2DAsync(dst, isz, src + size_t(c0) * in_strides[r] * isz, size_t(in_strides[r]) * isz, isz, size_t(cn),
+                                   cudaMemcpyHostToDevice, s.stream));
+        d_strides[r] = 1;
+      }
+      d_rows[r] = dst;
+    }
+    float* const d_scal = static_cast<float*>(s.d_out);
+    char* const d_bl = static_cast<char*>(s.d_out) + scal_bytes;
+    rc = eval_device_impl(ctx, model_id, variant, cn, d_rows, d_strides, in_dtype, d_scal, chunk, NFB_F32, s.stream, d_bl);
+    if (rc != NFB_OK) return rc;
+    NFB_CUDA(cudaMemcpy2DAsync(out_scalars + c0, size_t(out_ld) * 4, d_scal, size_t(chunk) * 4, size_t(cn) * 4, 6, cudaMemcpyDeviceToHost, s.stream));
+    NFB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(out_bl) + size_t(c0) * 2, size_t(out_ld) * 2, d_bl, size_t(chunk) * 2, size_t(cn) * 2, BL_ROWS,
+                               cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto& s : ctx->slots) NFB_CUDA(cudaStreamSynchronize(s.stream));
+  return NFB_OK;
 }
 
 }  // extern "C"

@@ -38,6 +38,9 @@ struct EvalParams {
   // copy per device, could not), and nothing is shared between threads or streams.
   double mean[N_IN];
   double quad[N_MAHA];
+  // Mixed-precision outputs (nfb_eval_*_mixed): when not NULL, the 192 boundary-layer rows (output rows 6..197) are written
+  // as bfloat16 (round to nearest) into this 192 x out_ld block instead of `out`, which then holds the six scalar rows only.
+  void* out_bl;
 };
 static_assert(sizeof(EvalParams) + 64 <= 4096, "EvalParams and its wrappers must fit the 4 KB kernel parameter space");
 
@@ -98,6 +101,12 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+// two fp32 -> packed bf16x2 (lo = first argument), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");

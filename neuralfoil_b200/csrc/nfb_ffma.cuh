@@ -230,6 +230,17 @@ __device__ __forceinline__ void featurise_column(const EvalParams& p, long long 
 __device__ __forceinline__ void store_row4(const EvalParams& p, int row, long long q0, int nvalid,
                                            bool vec_ok, const float (&v)[4]) {
   if (nvalid <= 0) return;
+  if (p.out_bl != nullptr && row >= 6) {  // mixed-precision outputs: boundary-layer rows as bfloat16
+    unsigned short* o = static_cast<unsigned short*>(p.out_bl) + (row - 6) * p.out_ld + q0;
+    if (nvalid == 4 && (p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out_bl) & 7) == 0) {
+      __stcs(reinterpret_cast<uint2*>(o), make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) o[j] = static_cast<unsigned short>(pack_bf16x2(v[j], 0.0f) & 0xFFFFu);
+    }
+    return;
+  }
   if (p.out_f64) {
     double* o = static_cast<double*>(p.out) + row * p.out_ld + q0;
     if (vec_ok && nvalid == 4) {

@@ -184,12 +184,18 @@ __device__ __forceinline__ void decode_group_store1(const EvalParams& p, int g, 
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (k < n_out) {
-      if (p.out_f64) __stcs(static_cast<double*>(p.out) + row[k] * p.out_ld + q, double(o[k]));
+      if (p.out_bl != nullptr && row[k] >= 6)
+        __stcs(static_cast<unsigned short*>(p.out_bl) + (row[k] - 6) * p.out_ld + q, static_cast<unsigned short>(pack_bf16x2(o[k], 0.0f) & 0xFFFFu));
+      else if (p.out_f64) __stcs(static_cast<double*>(p.out) + row[k] * p.out_ld + q, double(o[k]));
       else __stcs(static_cast<float*>(p.out) + row[k] * p.out_ld + q, o[k]);
     }
 }
 
 __device__ __forceinline__ void store1(const EvalParams& p, int row, long long q, float v) {
+  if (p.out_bl != nullptr && row >= 6) {  // mixed-precision outputs: boundary-layer rows as bfloat16
+    __stcs(static_cast<unsigned short*>(p.out_bl) + (row - 6) * p.out_ld + q, static_cast<unsigned short>(pack_bf16x2(v, 0.0f) & 0xFFFFu));
+    return;
+  }
   if (p.out_f64) __stcs(static_cast<double*>(p.out) + row * p.out_ld + q, double(v));
   else __stcs(static_cast<float*>(p.out) + row * p.out_ld + q, v);
 }

@@ -62,6 +62,11 @@ def default_loss_weights() -> np.ndarray:
     return w / w.sum() * 1000
 
 
+def bf16_bits_to_float32(bits: np.ndarray) -> np.ndarray:
+    """uint16 bfloat16 bit patterns (the `out_bl` block of `evaluate_host_mixed_into`) -> float32, exactly."""
+    return (np.asarray(bits, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
 def _length(x) -> int:
     """aerosandbox.numpy.length as used at main.py:161,189-193: len() of sized things, 1 for scalars."""
     try:
@@ -649,6 +654,60 @@ class Evaluator:
             )
         )
         return out[:, :n]
+
+    # -- mixed-precision outputs: six float32 scalars + 192 bfloat16 boundary-layer rows (408 instead of 792 B per query) --------
+    def evaluate_device_mixed(self, raw, model_size: str = "xlarge", variant: str = "fp32"):
+        """
+        raw: (23, N) torch CUDA tensor, float32 or float64, contiguous rows -> (scalars (6, N) float32, bl (192, N) bfloat16):
+        the six scalars bit-identical to `evaluate_device`, the boundary-layer rows (output rows 6..197) its float32 values
+        rounded to nearest bfloat16.  Enqueues on torch's current stream.
+        """
+        import torch
+
+        if (not isinstance(raw, torch.Tensor) or raw.dim() != 2 or raw.shape[0] != _lib.N_RAW_ROWS or not raw.is_cuda
+                or raw.device.index != self.device or raw.dtype not in (torch.float32, torch.float64) or raw.stride(1) != 1):
+            raise ValueError(f"raw must be a (23, N) float32 / float64 tensor on cuda:{self.device} with contiguous rows")
+        n = int(raw.shape[1])
+        ld = (n + 3) & ~3
+        dev = f"cuda:{self.device}"
+        scalars = torch.empty((_lib.N_SCALAR_ROWS, ld), dtype=torch.float32, device=dev)
+        bl = torch.empty((_lib.N_OUTPUT_ROWS - _lib.N_SCALAR_ROWS, ld), dtype=torch.bfloat16, device=dev)
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].data_ptr() for i in range(_lib.N_RAW_ROWS)])
+        _lib.check(
+            self._lib.nfb_eval_device_mixed(
+                self._ctx, self._model_id(model_size), self._variant(variant), n, ptrs, _ONES_23,
+                _lib.F64 if raw.dtype == torch.float64 else _lib.F32, C.c_void_p(scalars.data_ptr()), C.c_void_p(bl.data_ptr()), ld,
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream),
+            )
+        )
+        return scalars[:, :n], bl[:, :n]
+
+    def evaluate_host_mixed_into(self, raw: np.ndarray, model_size: str, out_scalars: np.ndarray, out_bl: np.ndarray,
+                                 chunk: int = 0, variant: str = "fp32"):
+        """
+        Host version: raw (23, N) float32/float64 -> out_scalars (6, >=N) float32 and out_bl (192, >=N) uint16 holding bfloat16
+        bit patterns (`bf16_bits_to_float32` widens them), both with the same row stride and contiguous rows, ideally pinned.
+        Returns their (., N) views.
+        """
+        if raw.ndim != 2 or raw.shape[0] != _lib.N_RAW_ROWS or raw.dtype not in (np.float32, np.float64) or raw.strides[1] != raw.itemsize:
+            raise ValueError("raw must be a (23, N) float32/float64 array with contiguous rows")
+        n = raw.shape[1]
+        n_bl = _lib.N_OUTPUT_ROWS - _lib.N_SCALAR_ROWS
+        if (out_scalars.dtype != np.float32 or out_scalars.ndim != 2 or out_scalars.shape[0] != _lib.N_SCALAR_ROWS or out_scalars.shape[1] < n
+                or out_scalars.strides[1] != 4):
+            raise ValueError("out_scalars must be a (6, >=N) float32 array with contiguous rows")
+        if (out_bl.dtype != np.uint16 or out_bl.ndim != 2 or out_bl.shape[0] != n_bl or out_bl.shape[1] < n or out_bl.strides[1] != 2
+                or out_bl.strides[0] // 2 != out_scalars.strides[0] // 4):
+            raise ValueError("out_bl must be a (192, >=N) uint16 array with contiguous rows and the row stride (in elements) of out_scalars")
+        ptrs = (C.c_void_p * _lib.N_RAW_ROWS)(*[raw[i].ctypes.data for i in range(_lib.N_RAW_ROWS)])
+        _lib.check(
+            self._lib.nfb_eval_host_mixed(
+                self._ctx, self._model_id(model_size), self._variant(variant), n, ptrs, _ONES_23,
+                _lib.F64 if raw.dtype == np.float64 else _lib.F32, out_scalars.ctypes.data_as(C.c_void_p),
+                out_bl.ctypes.data_as(C.c_void_p), out_scalars.strides[0] // 4, chunk,
+            )
+        )
+        return out_scalars[:, :n], out_bl[:, :n]
 
     # -- training step (SURVEY 8(f-4)) ----------------------------------------------------------------
     def train_step_device(self, x, y_data, model_size: str, loss_weights=None, huber_delta: float = 0.05):

@@ -238,3 +238,33 @@ def test_zero_copy_small_batches_equal_copied_ones(evaluator, n):
         evaluator.set_tuning(mapped_max=-1)
     for a, b in zip(copied, mapped):
         assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("size,variant", [("xxsmall", "fp32"), ("xlarge", "fp32"), ("xlarge", "tensor"), ("xxlarge", "tensor_fp32"),
+                                          ("xxxlarge", "tensor"), ("xxxlarge", "fp32")])
+def test_mixed_precision_outputs_are_the_bf16_rounding_of_the_fp32_ones(evaluator, size, variant):
+    """nfb_eval_*_mixed: scalars bit-identical, boundary-layer rows = the float32 results rounded to nearest bfloat16."""
+    import torch
+
+    from neuralfoil_b200 import bf16_bits_to_float32
+
+    for n in (37, 3000, 70_001):  # small-batch kernel, one chunk, ragged
+        raw = synthetic.sample_training_distribution(n, seed=n, dtype=np.float32)
+        d_raw = torch.from_numpy(raw).cuda()
+        full = evaluator.evaluate_device(d_raw, size, variant=variant)
+        scal, bl = evaluator.evaluate_device_mixed(d_raw, size, variant=variant)
+        torch.cuda.synchronize()
+        assert scal.dtype == torch.float32 and bl.dtype == torch.bfloat16 and bl.shape == (192, n)
+        assert torch.equal(scal, full[:6])
+        assert torch.equal(bl.view(torch.int16), full[6:].to(torch.bfloat16).view(torch.int16))  # torch rounds to nearest even too
+        ld = (n + 3) & ~3
+        h_scal, h_bl = np.zeros((6, ld), dtype=np.float32), np.zeros((192, ld), dtype=np.uint16)
+        a, b = evaluator.evaluate_host_mixed_into(raw, size, h_scal, h_bl, variant=variant, chunk=16384)
+        assert np.array_equal(a, scal.cpu().numpy(), equal_nan=True)
+        want = full[6:].cpu().numpy()
+        got = bf16_bits_to_float32(b)
+        assert np.array_equal(got, bl.float().cpu().numpy(), equal_nan=True)
+        finite = np.isfinite(want) & (np.abs(want) > 1e-30)
+        assert np.max(np.abs(got[finite] - want[finite]) / np.abs(want[finite])) <= 2.0 ** -8
+    with pytest.raises(ValueError):
+        evaluator.evaluate_host_mixed_into(raw, size, h_scal, h_bl.astype(np.float32), variant=variant)

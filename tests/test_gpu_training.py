@@ -18,7 +18,7 @@ import parity
 pytestmark = pytest.mark.gpu
 
 # Gradient tolerance: |got - want| <= GRAD_RTOL * (|want| + max |want| of that array).  fp32 accumulation over
-# batch x 2 columns of products whose signs vary; set to 3 x the worst figure measured on B200 (profiles/r2_parity_maxima*.json).
+# batch x 2 columns of products whose signs vary; set to 3 x the worst figure measured on B200 (profiles/r2_parity_maxima.json).
 GRAD_RTOL = 3e-4   # measured worst 1.3e-4 (xxxlarge, batch 1001)
 LOSS_RTOL = 5e-5   # measured worst 1.8e-5: a Huber term is quadratic in a residual of ~0.04 that carries the fp32 latent error
 
