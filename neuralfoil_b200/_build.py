@@ -27,6 +27,7 @@ NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
     "-lineinfo",
+    "--no-compress",  # the SASS pass (_sass.py) edits the code bytes in place
     "--shared",
     "-Xcompiler",
     "-fPIC",
@@ -72,6 +73,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if proc.returncode != 0:
         tmp.unlink(missing_ok=True)
         raise RuntimeError(f"nvcc failed with exit code {proc.returncode}")
+    if os.environ.get("NFB_NO_SASS_PASS", "") != "1":  # A/B only: the library as ptxas left it
+        # operand-reuse flags of the FFMA2 blocks (see _sass.py): same instructions, same order, bit-identical results
+        from . import _sass
+
+        stats = _sass.patch_file(str(tmp), verbose=verbose)
+        if verbose:
+            print(f"sass pass: {stats}", flush=True)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

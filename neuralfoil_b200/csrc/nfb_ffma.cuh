@@ -20,6 +20,10 @@
 #define NFB_GROUP_BARS 0
 #endif
 
+#ifndef NFB_SLICE_ORDER
+#define NFB_SLICE_ORDER 0
+#endif
+
 namespace nfb {
 
 template <int H_, int KC_, int STAGES_, int TN_>
@@ -128,6 +132,45 @@ __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const fl
           acc[i][jj] = __ffma2_rn(make_float2(wv[cur][i], wv[cur][i]), av[cur][jj], acc[i][jj]);
     }
   } else {
+#if NFB_SLICE_ORDER == 3
+    // Transposed pairing: the packed operand is a pair of ROWS (two adjacent weights, exactly as LDS.128 delivers them)
+    // of one column; it stays in the operand-reuse cache while the TN column scalars stream past.  The accumulators are
+    // the same scalars, only paired differently in the register file: acc[2 ip][jj].x sits beside acc[2 ip + 1][jj].x.
+    static_assert(TM % 2 == 0, "rows are paired");
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float wv[TM];
+      float2 av[TN / 2];
+      load_fragments<TM, TN, MP, NC>(w + kk * MP, a + kk * NC, wv, av);
+#pragma unroll
+      for (int ip = 0; ip < TM / 2; ++ip) {
+        const float2 wp = make_float2(wv[2 * ip], wv[2 * ip + 1]);
+#pragma unroll
+        for (int jj = 0; jj < TN / 2; ++jj) {
+          float2 t = __ffma2_rn(wp, make_float2(av[jj].x, av[jj].x), make_float2(acc[2 * ip][jj].x, acc[2 * ip + 1][jj].x));
+          acc[2 * ip][jj].x = t.x; acc[2 * ip + 1][jj].x = t.y;
+          t = __ffma2_rn(wp, make_float2(av[jj].y, av[jj].y), make_float2(acc[2 * ip][jj].y, acc[2 * ip + 1][jj].y));
+          acc[2 * ip][jj].y = t.x; acc[2 * ip + 1][jj].y = t.y;
+        }
+      }
+    }
+#elif NFB_SLICE_ORDER == 2  // fragments double-buffered by hand, as for the 8 x 8 tile
+    float wv[2][TM];
+    float2 av[2][TN / 2];
+    load_fragments<TM, TN, MP, NC>(w, a, wv[0], av[0]);
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const int cur = kk & 1;
+      if (kk + 1 < KC) load_fragments<TM, TN, MP, NC>(w + (kk + 1) * MP, a + (kk + 1) * NC, wv[cur ^ 1], av[cur ^ 1]);
+#pragma unroll
+      for (int jj = 0; jj < TN / 2; ++jj)
+#pragma unroll
+        for (int ii = 0; ii < TM; ++ii) {
+          const int i = (jj & 1) ? TM - 1 - ii : ii;
+          acc[i][jj] = __ffma2_rn(make_float2(wv[cur][i], wv[cur][i]), av[cur][jj], acc[i][jj]);
+        }
+    }
+#else
 #pragma unroll
     for (int kk = 0; kk < KC; ++kk) {
       float wv[TM];
@@ -136,9 +179,16 @@ __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const fl
 #pragma unroll
       for (int jj = 0; jj < TN / 2; ++jj)
 #pragma unroll
-        for (int i = 0; i < TM; ++i)
+        for (int ii = 0; ii < TM; ++ii) {
+#if NFB_SLICE_ORDER == 1  // snake: the row index turns round at every column pair, so the weight operand carries over
+          const int i = (jj & 1) ? TM - 1 - ii : ii;
+#else
+          const int i = ii;
+#endif
           acc[i][jj] = __ffma2_rn(make_float2(wv[i], wv[i]), av[jj], acc[i][jj]);
+        }
     }
+#endif
   }
 }
 

@@ -29,9 +29,15 @@
 // nfb_ffma_kernel, nfb_small_kernel and the value columns of nfb_jac_kernel (tests/test_gpu_parity.py).
 #pragma once
 #include "nfb_ffma.cuh"
+#include "nfb_ring.cuh"
 
 #ifndef NFB_GRP_DECODE_ONCE
 #define NFB_GRP_DECODE_ONCE 0
+#endif
+// Timing experiments only (scripts/groups_probe.cu; results are wrong with any bit set): 1 no featurisation, 2 no SiLU
+// arithmetic, 4 no decode, 8 no group barriers, 64 no last layer.
+#ifndef NFB_EXP
+#define NFB_EXP 0
 #endif
 
 namespace nfb {
@@ -125,54 +131,26 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
       for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(SB::half_off(L)) + c * KC * (H / 2), KC * (H / 2) * 4);
     if (NSCAL) table[j++] = make_uint2(uint32_t(SB::scal_off(L)), uint32_t(p.k_hidden) * 8 * 4);
   }
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, WARPS);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
   const int lm = lane / LN, ln = lane % LN;
   const int wm = warp % WM, wn = warp / WM;   // wn: this warp's column group
   const int h_row = (wm * LM + lm) * 4;       // rows h_row..+3 and H/2 + h_row..+3 of a layer (or of a sweep)
   const int h_col = wn * QG + ln * QT;        // columns h_col..+QT-1 and NC/2 + h_col..
   const int gtid = tid - wn * Cfg::GROUP_THREADS;
+#if NFB_EXP & 8
+  auto group_bar = [&]() {};
+#else
   auto group_bar = [&]() { named_bar_sync(1 + wn, Cfg::GROUP_THREADS); };
+#endif
 
   const bool vec_ok =
       p.out_f64 ? ((p.out_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
                 : ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
 
-  // Weight stream: slice j of the CTA's run lands in ring slot j % STAGES and is issued by lane 0 of warp j % WARPS when
-  // that warp starts slice j - LEAD.  The issuer waits until every warp has released slice j - STAGES, so a warp runs at
-  // most STAGES - LEAD slices ahead of the slowest one without blocking, and finds its weights as long as it is less
-  // than LEAD slices ahead of the issuers: LEAD = STAGES / 2 bounds the drift of the groups by half a ring either way.
+  // Weight stream: see nfb_ring.cuh.  LEAD = STAGES / 2 bounds the drift of the groups by half a ring either way.
   // (Measured and rejected: feeding the ring opportunistically -- whichever warp finds the next slot free claims the
   //  slice with a shared-memory atomic -- puts a shared-memory round trip on every warp's path at every slice: -3 %.)
-  constexpr uint32_t LEAD = Cfg::LEAD;
-  uint32_t it = 0;  // slices this warp has consumed
-  auto issue = [&](uint32_t j) {
-    const uint2 e = table[j % slices_per_tile];
-    const uint32_t s = j % STAGES, ph = (j / STAGES) & 1;
-    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-    mbar_arrive_expect_tx(bar_full + 8 * s, e.y);
-    bulk_copy_g2s(smem_u32(ring + s * SLOT), p.blob + e.x, e.y, bar_full + 8 * s);
-  };
-  if (tid == 0)
-    for (uint32_t j = 0; j < LEAD && j < total_slices; ++j) issue(j);
-  auto wait_slice = [&](uint32_t& s_out) {
-    const uint32_t j = it + LEAD;
-    if (lane == 0 && (j & (WARPS - 1)) == uint32_t(warp) && j < total_slices) issue(j);
-    s_out = it % STAGES;
-    mbar_wait(bar_full + 8 * s_out, (it / STAGES) & 1);
-  };
-  auto release_slice = [&](uint32_t s) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-    ++it;
-  };
+  WeightRing<STAGES, Cfg::LEAD, WARPS, SLOT> wr;
+  wr.init(ring, table, p.blob, bar_full, bar_empty, slices_per_tile, total_slices);
 
   const float* const sweep_bias = p.blob + SB::bias_off(L);
 
@@ -184,7 +162,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
       const bool twin = t >= QG;
       const int c = wn * QG + (t % QG);
       const long long q = tile_q0 + c;
+#if NFB_EXP & 1
+      const int col = twin ? NQ + c : c;
+      maha[col] = 0.f;
+      if (!twin) re_s[c] = 1e6f;
+      for (int k = 0; k < K0_PAD; ++k) act[k * NC + col] = 1e-3f * float(k + (q & 7));
+#else
       featurise_column<NC>(p, q, q < p.n, twin, twin ? NQ + c : c, act, maha, re_s);
+#endif
     }
     group_bar();
 
@@ -203,10 +188,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
       }
       const int nk = (l == 0) ? K0_PAD / KC : nkh;
       for (int c = 0; c < nk; ++c) {
-        uint32_t s;
-        wait_slice(s);
-        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-        release_slice(s);
+        const float* ws = wr.wait();
+        ffma_slice<8, TN, H, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+        wr.release();
       }
       group_bar();  // the group has finished reading this layer's input
 #pragma unroll
@@ -215,10 +199,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
 #pragma unroll
         for (int v = 0; v < TN / 8; ++v) {
           float4 lo, hi;
+#if NFB_EXP & 2
+#define silu(x) (x)
+#endif
           lo.x = silu(acc[i][2 * v].x); lo.y = silu(acc[i][2 * v].y);
           lo.z = silu(acc[i][2 * v + 1].x); lo.w = silu(acc[i][2 * v + 1].y);
           hi.x = silu(acc[i][TN / 4 + 2 * v].x); hi.y = silu(acc[i][TN / 4 + 2 * v].y);
           hi.z = silu(acc[i][TN / 4 + 2 * v + 1].x); hi.w = silu(acc[i][TN / 4 + 2 * v + 1].y);
+#if NFB_EXP & 2
+#undef silu
+#endif
           *reinterpret_cast<float4*>(act + row * NC + h_col + 4 * v) = lo;
           *reinterpret_cast<float4*>(act + row * NC + NC / 2 + h_col + 4 * v) = hi;
         }
@@ -242,9 +232,19 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
         const long long q0 = tile_q0 + c4;
         const long long left = p.n - q0;
         const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
+#if NFB_EXP & 4
+        float sum = 0.f;
+        for (int i = 0; i < 4; ++i)
+          for (int j = 0; j < 8; ++j) sum += yf[i][j];
+        if (sum == 123.456f) static_cast<float*>(p.out)[q0] = sum + float(g + nvalid);
+#else
         decode_and_store(p, g, q0, nvalid, vec_ok, yf, maha + c4, maha + NQ + c4, re_s + c4);
+#endif
       }
     };
+#if NFB_EXP & 64
+    continue;
+#endif
     for (int sw = 0; sw < n_full; ++sw) {
       float2 acc[8][TN / 2];
 #pragma unroll
@@ -257,10 +257,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
         }
       }
       for (int c = 0; c < nkh; ++c) {
-        uint32_t s;
-        wait_slice(s);
-        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-        release_slice(s);
+        const float* ws = wr.wait();
+        ffma_slice<8, TN, H, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+        wr.release();
       }
       const int g = sw * (H / 4) + wm * LM + lm;  // packed row groups g and g + H / 8
 #if NFB_GRP_DECODE_ONCE
@@ -291,24 +290,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
           for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(b, b);
         }
         for (int c = 0; c < nkh; ++c) {
-          uint32_t s;
-          wait_slice(s);
-          ffma_slice<4, TN, H / 2, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-          release_slice(s);
+          const float* ws = wr.wait();
+          ffma_slice<4, TN, H / 2, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+          wr.release();
         }
         decode_rows(acc, SB::HALF_ROW0 / 4 + wm * LM + lm);
       }
     }
     if constexpr (NSCAL > 0) {
       // scalar pass: lane = query of the group; accumulators for the query (yq) and its twin (yt), latent rows 0..5
-      uint32_t s;
-      wait_slice(s);
+      const float* ws = wr.wait();
       if (wm == 0) {
         const int c = wn * QG + lane;
         float yq[6], yt[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) yq[i] = yt[i] = __ldg(sweep_bias + SB::SCAL_ROW0 + i);
-        const float* w = ring + s * SLOT;
+        const float* w = ws;
         const float* aq = act + c;
         const int kh = p.k_hidden;
 #pragma unroll 4
@@ -346,7 +343,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_ffma_groups_kernel(const 
           }
         }
       }
-      release_slice(s);
+      __syncwarp();  // the scalar pass diverges on q < p.n
+      wr.release();
     }
   }
 }
