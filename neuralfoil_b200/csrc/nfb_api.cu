@@ -999,8 +999,11 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
         stage_in = is_pageable(in_rows[r]);
         break;
       }
-  // default chunk: 512 Ki queries; 128 Ki when the host copies are the library's own, so that they overlap the GPU sooner
-  if (chunk <= 0) chunk = stage_out ? (1 << 17) : (1 << 19);
+  // default chunk: 128 Ki queries when the host copies are the library's own, so that they overlap the GPU sooner; otherwise a
+  // sixteenth of the batch within [64 Ki, 512 Ki]: the last chunk's device->host copy is the one nothing hides, and when eight
+  // GPUs share the host's 92 GB/s (profiles/r2_pcie_pitched_8gpu.jsonl) a 512 Ki chunk of full outputs is a 36 ms tail on a
+  // 115 ms shard (8 GPUs x 1.25 M queries, xxxlarge fp32: 148 ms per pass with 512 Ki chunks, 123 ms with 128 Ki)
+  if (chunk <= 0) chunk = stage_out ? (1 << 17) : std::min<int64_t>(1 << 19, std::max<int64_t>(1 << 16, (n / 16 + 3) & ~int64_t(3)));
   chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
   const int out_rows = (variant & NFB_OUTPUT_SCALARS) ? 6 : nfb::N_OUT;
   const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(out_rows) * chunk * osz;
