@@ -148,6 +148,72 @@ def prepare_raw_rows(kulfan_parameters, alpha, Re, n_crit, xtr_upper, xtr_lower)
     return arrays, n_cases
 
 
+
+class _PooledBlock:
+    """Owns the memory of one large result block and hands it back to the pool when the last NumPy view of it dies.
+    NumPy keeps the object exposing `__array_interface__` alive as the base of every array built on it."""
+
+    __slots__ = ("_mem", "_pool", "__array_interface__")
+
+    def __init__(self, mem: np.ndarray, shape, dtype, pool):
+        self._mem, self._pool = mem, pool
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": np.dtype(dtype).str,
+                                    "data": (mem.__array_interface__["data"][0], False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._pool._give_back(self._mem)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class _ResultPool:
+    """
+    Recycles the host memory of large result blocks (the 198 x N float64 block behind the returned dict).
+
+    A fresh 1.6 GB NumPy array costs the kernel a zero-filled page fault for every page the first time it is written --
+    for a 1 M-point call that was a third of the drop-in call's time (profiles/r2_polar_grid_result_pool.jsonl).  Blocks of
+    at least `MIN_BYTES` are therefore carved out of byte buffers that return here when the caller drops the last array
+    that points into them, and the next call of the same size finds its pages already mapped.  A caller that rebinds
+    `aero = get_aero_from_kulfan_parameters(...)` in a loop alternates between two buffers.  At most `cap_bytes` are kept
+    (`$NEURALFOIL_B200_RESULT_POOL_MB`, default 4096; 0 switches the pool off); the oldest buffers go first.
+    """
+
+    MIN_BYTES = 8 << 20
+
+    def __init__(self, cap_bytes: int):
+        self.cap_bytes = int(cap_bytes)
+        self._lock = threading.Lock()
+        self._free: list[np.ndarray] = []  # oldest first
+
+    def empty(self, shape, dtype) -> np.ndarray:
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if self.cap_bytes <= 0 or nbytes < self.MIN_BYTES:
+            return np.empty(shape, dtype=dtype)
+        mem = None
+        with self._lock:
+            for i in range(len(self._free) - 1, -1, -1):
+                if self._free[i].nbytes == nbytes:
+                    mem = self._free.pop(i)
+                    break
+        if mem is None:
+            mem = np.empty(nbytes, dtype=np.uint8)
+        return np.asarray(_PooledBlock(mem, shape, dtype, self))
+
+    def _give_back(self, mem: np.ndarray) -> None:
+        with self._lock:
+            self._free.append(mem)
+            while self._free and sum(m.nbytes for m in self._free) > self.cap_bytes:
+                self._free.pop(0)
+
+    def clear(self) -> None:
+        with self._lock:
+            self._free.clear()
+
+
+_result_pool = _ResultPool(int(float(os.environ.get("NEURALFOIL_B200_RESULT_POOL_MB", "4096")) * (1 << 20)))
+
+
 class Evaluator:
     """
     The distribution statistics and every network, repacked and resident on one GPU -- or replicated on several GPUs
@@ -566,7 +632,7 @@ class Evaluator:
                             outputs: str = "all"):
         ld = (n + 3) & ~3
         n_rows, flag = self._rows_and_flag(outputs)
-        block = np.empty((n_rows, ld), dtype=out_dtype)
+        block = _result_pool.empty((n_rows, ld), out_dtype)
         if n <= 4096:
             # Small batches (an optimiser's per-iteration call): gather the rows into one (23, n) float64 block so
             # that the pointer table is plain integer arithmetic -- numpy's `.ctypes` accessors cost ~1 us apiece.

@@ -126,3 +126,37 @@ def test_evaluator_rejects_conflicting_device_arguments(library):
     with pytest.raises(ValueError, match="Invalid variant"):
         nfb_main.Evaluator._variant("fp32:fast")
     assert nfb_main.Evaluator._variant("fp32:tiled") == 0x1000 and nfb_main.Evaluator._variant("tensor_fp32:one_sm") == 0x2002
+
+
+def test_result_pool_recycles_only_released_blocks():
+    """Large result blocks come from a pool (main._ResultPool): memory returns to it when the LAST view dies, never before."""
+    import gc
+
+    from neuralfoil_b200.main import _ResultPool
+
+    pool = _ResultPool(64 << 20)
+    a = pool.empty((198, 20000), np.float64)  # 31.7 MB >= MIN_BYTES
+    assert a.shape == (198, 20000) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"]
+    a[:] = 3.0
+    ptr = a.__array_interface__["data"][0]
+    views = [a[i, :19999] for i in range(198)]  # what the returned dict holds
+    del a
+    gc.collect()
+    assert len(pool._free) == 0, "a block still referenced by a row view must not be recycled"
+    b = pool.empty((198, 20000), np.float64)
+    assert b.__array_interface__["data"][0] != ptr
+    assert float(views[7][5]) == 3.0
+    del views
+    gc.collect()
+    assert len(pool._free) == 1
+    c = pool.empty((198, 20000), np.float64)
+    assert c.__array_interface__["data"][0] == ptr and len(pool._free) == 0  # same size: reused
+    d = pool.empty((198, 10000), np.float64)
+    assert d.__array_interface__["data"][0] != ptr  # other size: fresh
+    del b, c, d
+    gc.collect()
+    assert sum(m.nbytes for m in pool._free) <= pool.cap_bytes  # 31.7 + 31.7 + 15.8 MB > 64 MB: the oldest went
+    small = pool.empty((198, 100), np.float64)
+    assert small.base is None  # below MIN_BYTES: a plain NumPy array
+    off = _ResultPool(0)
+    assert off.empty((198, 20000), np.float64).base is None
