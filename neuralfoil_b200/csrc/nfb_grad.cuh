@@ -187,13 +187,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
     for (int l = L - 2; l >= 1; --l)
       for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(GB::wt_off(L, l)) + c * KC * H, KC * H * 4);
     for (int c = 0; c < nkh; ++c) table[j++] = make_uint2(uint32_t(GB::wt0_off(L)) + c * KC * K0_PAD, KC * K0_PAD * 4);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, WARPS);
-    }
-    fence_mbar_init();
   }
-  __syncthreads();
 
   const int lm = lane / LN, ln = lane % LN;
   const int wm = warp % WM, wn = warp / WM;
@@ -202,28 +196,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
   const int gtid = tid - wn * Cfg::GROUP_THREADS;
   auto group_bar = [&]() { named_bar_sync(1 + wn, Cfg::GROUP_THREADS); };
 
-  constexpr uint32_t LEAD = Cfg::LEAD;  // see nfb_ffma_groups.cuh
-  uint32_t it = 0;
-  auto issue = [&](uint32_t j) {
-    const uint2 e = table[j % slices_per_tile];
-    const uint32_t s = j % STAGES, ph = (j / STAGES) & 1;
-    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-    mbar_arrive_expect_tx(bar_full + 8 * s, e.y);
-    bulk_copy_g2s(smem_u32(ring + s * SLOT), p.blob + e.x, e.y, bar_full + 8 * s);
-  };
-  if (tid == 0)
-    for (uint32_t j = 0; j < LEAD && j < total_slices; ++j) issue(j);
-  auto wait_slice = [&](uint32_t& s_out) {
-    const uint32_t j = it + LEAD;
-    if (lane == 0 && (j & (WARPS - 1)) == uint32_t(warp) && j < total_slices) issue(j);
-    s_out = it % STAGES;
-    mbar_wait(bar_full + 8 * s_out, (it / STAGES) & 1);
-  };
-  auto release_slice = [&](uint32_t s) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-    ++it;
-  };
+  // the weight stream (nfb_ring.cuh); init ends with the CTA barrier that also publishes `table`
+  WeightRing<STAGES, Cfg::LEAD, WARPS, SLOT> wr;
+  wr.init(ring, table, p.blob, bar_full, bar_empty, slices_per_tile, total_slices);
   // this thread's tile element (row i of 8, float4 v of its query columns / twin columns) in a [.][H][NC] block
   auto tile_offset = [&](int i, int v, bool twin) {
     const int row = (i < 4) ? h_row + i : H / 2 + h_row + (i - 4);
@@ -257,10 +232,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
       }
       const int nk = (l == 0) ? K0_PAD / KC : nkh;
       for (int c = 0; c < nk; ++c) {
-        uint32_t s;
-        wait_slice(s);
-        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-        release_slice(s);
+        const float* ws = wr.wait();
+        ffma_slice<8, TN, H, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+        wr.release();
       }
       group_bar();
       float* const sl = slopes + size_t(l) * H * NC;
@@ -334,10 +308,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           }
         }
         for (int c = 0; c < nkh; ++c) {
-          uint32_t s;
-          wait_slice(s);
-          ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-          release_slice(s);
+          const float* ws = wr.wait();
+          ffma_slice<8, TN, H, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+          wr.release();
         }
         const int g = sw * (H / 4) + wm * LM + lm;
         vjp_rows(reinterpret_cast<const float2(&)[4][TN / 2]>(acc[0]), g);
@@ -353,10 +326,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(b, b);
         }
         for (int c = 0; c < nkh; ++c) {
-          uint32_t s;
-          wait_slice(s);
-          ffma_slice<4, TN, H / 2, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-          release_slice(s);
+          const float* ws = wr.wait();
+          ffma_slice<4, TN, H / 2, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+          wr.release();
         }
         vjp_rows(acc, SB::HALF_ROW0 / 4 + wm * LM + lm);
       }
@@ -365,8 +337,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
 
     // ---------------- turn: scalar latents, outputs, their cotangents, d a_{L-2} ----------------
     {
-      uint32_t s;
-      wait_slice(s);
+      const float* ws = wr.wait();
       if (wm == 0 && lane < QG) {
         const int c = wn * QG + lane;
         const long long q = tile_q0 + c;
@@ -374,7 +345,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
         float yq[6], yt[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) yq[i] = yt[i] = __ldg(bs + i);
-        const float* w = ring + s * SLOT;
+        const float* w = ws;
         float* const aq = act + c;
         const int kh = p.k_hidden;
 #pragma unroll 4
@@ -454,7 +425,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           }
         }
       }
-      release_slice(s);
+      __syncwarp();  // the turn diverges (one query per lane, q < n); every lane has finished with the slot
+      wr.release();
     }
     group_bar();
 
@@ -476,10 +448,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
         }
         group_bar();
         for (int c = 0; c < rows_here / KC; ++c) {
-          uint32_t s;
-          wait_slice(s);
-          ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-          release_slice(s);
+          const float* ws = wr.wait();
+          ffma_slice<8, TN, H, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+          wr.release();
         }
       }
       group_bar();
@@ -508,10 +479,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
 #pragma unroll
         for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(0.0f, 0.0f);
       for (int c = 0; c < nkh; ++c) {
-        uint32_t s;
-        wait_slice(s);
-        ffma_slice<8, TN, H, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-        release_slice(s);
+        const float* ws = wr.wait();
+        ffma_slice<8, TN, H, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+        wr.release();
       }
       group_bar();  // the group has finished reading d z_l
       const float* const sl = slopes + size_t(l - 1) * H * NC;
@@ -539,10 +509,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
 #pragma unroll
         for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(0.0f, 0.0f);
       for (int c = 0; c < nkh; ++c) {
-        uint32_t s;
-        wait_slice(s);
-        if (mine) ffma_slice<4, TN, K0_PAD, NC, KC>(ring + s * SLOT + h_row, act + (c * KC) * NC + h_col, acc);
-        release_slice(s);
+        const float* ws = wr.wait();
+        if (mine) ffma_slice<4, TN, K0_PAD, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
+        wr.release();
       }
       group_bar();
       if (mine) {
