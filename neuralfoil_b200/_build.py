@@ -74,10 +74,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         tmp.unlink(missing_ok=True)
         raise RuntimeError(f"nvcc failed with exit code {proc.returncode}")
     if os.environ.get("NFB_NO_SASS_PASS", "") != "1":  # A/B only: the library as ptxas left it
-        # operand-reuse flags of the FFMA2 blocks (see _sass.py): same instructions, same order, bit-identical results
+        # operand-reuse flags of the FFMA2 blocks of the 8-warp fp32 kernels (see _sass.py): same instructions, same order,
+        # bit-identical results
         from . import _sass
 
-        stats = _sass.patch_file(str(tmp), verbose=verbose)
+        stats = _sass.patch_file(str(tmp), verbose=verbose, select=_sass.DEFAULT_SELECT)
         if verbose:
             print(f"sass pass: {stats}", flush=True)
     os.replace(tmp, LIB_PATH)
