@@ -378,6 +378,39 @@ def patch_file(path: str, want: str = "", dry: bool = False, clear_yield: bool =
     return total
 
 
+HINT_BITS = YIELD_BIT | REUSE_MASK  # what the default (flags-only) pass may change, and only on FFMA2 instructions
+
+
+def verify_hint_bits_only(original: str, patched: str) -> int:
+    """Raises unless `patched` differs from `original` ONLY in yield / reuse bits of FFMA2 instructions (same file size, same
+    bytes everywhere else).  Returns the number of instructions that differ."""
+    a, b = open(original, "rb").read(), open(patched, "rb").read()
+    if len(a) != len(b):
+        raise ValueError("patched library changed size")
+    ffma2_words = {}
+    for _, body in functions(original):
+        for _, text, lo, hi in body:
+            if text.startswith("FFMA2 "):
+                ffma2_words.setdefault(lo, set()).add(hi)
+    changed = 0
+    if a == b:
+        return 0
+    # compare in 16-byte instruction slots aligned to the start of the differing region's instruction
+    diff_at = [i for i in range(0, len(a) - 15, 8) if a[i:i + 8] != b[i:i + 8]]
+    for off in diff_at:
+        wa, wb = struct.unpack_from("<Q", a, off)[0], struct.unpack_from("<Q", b, off)[0]
+        if (wa ^ wb) & ~HINT_BITS:
+            raise ValueError(f"patched library differs outside the hint bits at offset {off:#x}")
+        lo = struct.unpack_from("<Q", a, off - 8)[0] if off >= 8 else None
+        if lo not in ffma2_words or wa not in ffma2_words[lo]:
+            raise ValueError(f"patched library differs in a word that is not the upper half of an FFMA2 at offset {off:#x}")
+        changed += 1
+    # bytes not 8-aligned cannot differ if every aligned word with a difference was accounted for
+    if sum(1 for i in range(0, len(a) - 7, 8) if a[i:i + 8] != b[i:i + 8]) != changed or a[len(a) // 8 * 8:] != b[len(b) // 8 * 8:]:
+        raise ValueError("patched library differs in unaccounted bytes")
+    return changed
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     mr = int(sys.argv[sys.argv.index("--min-run") + 1]) if "--min-run" in sys.argv else 32
