@@ -39,7 +39,7 @@ def _sources() -> list[Path]:
 
 
 def _dependencies() -> list[Path]:
-    return _sources() + sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h")) + [Path(__file__)]
+    return _sources() + sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h")) + [Path(__file__), PKG_DIR / "_sass.py"]
 
 
 def is_stale() -> bool:
