@@ -27,6 +27,13 @@
 #include "nfb_ffma_groups.cuh"
 #include "nfb_jac.cuh"  // maha_gradient_regs
 
+// Timing experiments only (results are wrong with any bit set): 1 no slope traffic, 2 trivial boundary-layer epilogue (no
+// cotangent loads, no transcendental work, no output stores), 4 no finish step, 8 no featurisation, 16 no parked rows,
+// 32 no turn.
+#ifndef NFB_GRAD_EXP
+#define NFB_GRAD_EXP 0
+#endif
+
 namespace nfb {
 
 struct GradParams {
@@ -73,6 +80,11 @@ __device__ __forceinline__ void bl_group_vjp(const EvalParams& p, const GradPara
 #pragma unroll
   for (int j = 0; j < 4; ++j) re_part[j] = 0.0f;
   if (g >= 48) return;
+#if NFB_GRAD_EXP & 2
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) dl[i][j] = 0.5f * yf[i][j];
+  return;
+#endif
   int r[4];
   if (g < N_BL) {
     r[0] = 6 + g; r[1] = 6 + 2 * N_BL + g; r[2] = 6 + 3 * N_BL + g; r[3] = 6 + 5 * N_BL + g;
@@ -81,15 +93,32 @@ __device__ __forceinline__ void bl_group_vjp(const EvalParams& p, const GradPara
     r[0] = 6 + N_BL + s; r[1] = r[0] + 1; r[2] = 6 + 4 * N_BL + s; r[3] = r[2] + 1;
   }
   float ct[4][4], o[4][4];
+  // cotangents: one 16-byte load per row where the four queries exist and the block is aligned (the usual case)
+  const bool cot_vec = nvalid == 4 && (p.out_f64 ? ((gp.cot_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(gp.cot) & 15) == 0 && (q0 & 1) == 0)
+                                                 : ((gp.cot_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(gp.cot) & 15) == 0 && (q0 & 3) == 0));
+  if (cot_vec) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      ct[i][j] = 0.0f;
-      if (j < nvalid)
-        ct[i][j] = p.out_f64 ? float(__ldg(static_cast<const double*>(gp.cot) + r[i] * gp.cot_ld + q0 + j))
-                             : __ldg(static_cast<const float*>(gp.cot) + r[i] * gp.cot_ld + q0 + j);
+    for (int i = 0; i < 4; ++i) {
+      if (p.out_f64) {
+        const double2* src = reinterpret_cast<const double2*>(static_cast<const double*>(gp.cot) + r[i] * gp.cot_ld + q0);
+        const double2 a = __ldg(src), b = __ldg(src + 1);
+        ct[i][0] = float(a.x); ct[i][1] = float(a.y); ct[i][2] = float(b.x); ct[i][3] = float(b.y);
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(gp.cot) + r[i] * gp.cot_ld + q0));
+        ct[i][0] = a.x; ct[i][1] = a.y; ct[i][2] = a.z; ct[i][3] = a.w;
+      }
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ct[i][j] = 0.0f;
+        if (j < nvalid)
+          ct[i][j] = p.out_f64 ? float(__ldg(static_cast<const double*>(gp.cot) + r[i] * gp.cot_ld + q0 + j))
+                               : __ldg(static_cast<const float*>(gp.cot) + r[i] * gp.cot_ld + q0 + j);
+      }
+  }
   if (g < N_BL) {  // theta_u, ue_u, theta_l, ue_l of station g
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -103,11 +132,13 @@ __device__ __forceinline__ void bl_group_vjp(const EvalParams& p, const GradPara
       o[0][j] = th_u; o[1][j] = zu_u; o[2][j] = th_l; o[3][j] = zu_l;
       // a zero cotangent contributes zero even where theta or its derivative is infinite (|ue| -> 0, 10^z overflow)
       const bool cu = ct[0][j] != 0.0f, cl = ct[2][j] != 0.0f;
-      const float g_ztu = cu ? ct[0][j] * 2.302585092994046f * pu / (fabsf(zu_u) * re) : 0.0f;
-      const float g_zuu = ct[1][j] - (cu ? ct[0][j] * th_u / zu_u : 0.0f);
-      const float g_ztl = cl ? ct[2][j] * 2.302585092994046f * pl / (fabsf(zu_l) * re) : 0.0f;
-      const float g_zul = ct[3][j] - (cl ? ct[2][j] * th_l / zu_l : 0.0f);
-      re_part[j] = -((cu ? ct[0][j] * th_u : 0.0f) + (cl ? ct[2][j] * th_l : 0.0f)) / re;
+      // the outputs above are the value kernel's expressions, bit for bit; the derivative terms below only feed the gradient and
+      // use the two-instruction division (2 ulp) -- seven IEEE divisions per query and station were a sixth of this kernel's time
+      const float g_ztu = cu ? __fdividef(ct[0][j] * 2.302585092994046f * pu, fabsf(zu_u) * re) : 0.0f;
+      const float g_zuu = ct[1][j] - (cu ? __fdividef(ct[0][j] * th_u, zu_u) : 0.0f);
+      const float g_ztl = cl ? __fdividef(ct[2][j] * 2.302585092994046f * pl, fabsf(zu_l) * re) : 0.0f;
+      const float g_zul = ct[3][j] - (cl ? __fdividef(ct[2][j] * th_l, zu_l) : 0.0f);
+      re_part[j] = -__fdividef((cu ? ct[0][j] * th_u : 0.0f) + (cl ? ct[2][j] * th_l : 0.0f), re);
       dl[0][j] = 0.5f * g_ztu; dl[2][4 + j] = 0.5f * g_ztu;
       dl[1][j] = 0.5f * g_zuu; dl[3][4 + j] = -0.5f * g_zuu;
       dl[2][j] = 0.5f * g_ztl; dl[0][4 + j] = 0.5f * g_ztl;
@@ -205,6 +236,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
     return row * NC + (twin ? NC / 2 : 0) + h_col + 4 * v;
   };
 
+  // Slopes come back from the scratch block (mostly from DRAM: the block is larger than the L2) in the epilogue of each reverse
+  // GEMM; asking the L2 for them when that GEMM starts hides the trip (xlarge: the slope traffic cost 13 % of the kernel).
+  auto prefetch_slopes = [&](const float* sl) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int v = 0; v < TN / 8; ++v)
+#pragma unroll
+        for (int tw = 0; tw < 2; ++tw)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(sl + tile_offset(i, v, tw == 1)));
+  };
+
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long tile_q0 = tile * NQ;
 
@@ -213,7 +256,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
       const bool twin = t >= QG;
       const int c = wn * QG + (t % QG);
       const long long q = tile_q0 + c;
+#if NFB_GRAD_EXP & 8
+      const int col = twin ? NQ + c : c;
+      maha[col] = 0.f;
+      if (!twin) re_s[c] = 1e6f;
+      for (int k = 0; k < K0_PAD; ++k) act[k * NC + col] = 1e-3f * float(k + (q & 7));
+#else
       featurise_column<NC>(p, q, q < p.n, twin, twin ? NQ + c : c, act, maha, re_s);
+#endif
     }
     group_bar();
 
@@ -257,7 +307,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
             }
             const int off = tile_offset(i, v, tw == 1);
             *reinterpret_cast<float4*>(act + off) = make_float4(y[0], y[1], y[2], y[3]);
+#if !(NFB_GRAD_EXP & 1)
             __stcg(reinterpret_cast<float4*>(sl + off), make_float4(d[0], d[1], d[2], d[3]));
+#endif
           }
         }
       }
@@ -285,6 +337,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           const long long left = p.n - q0;
           const int nvalid = left >= 4 ? 4 : (left > 0 ? int(left) : 0);
           bl_group_vjp(p, gp, g, q0, nvalid, vec_ok, yf, re_s + c4, dl, re_part);
+#if NFB_GRAD_EXP & 16
+          if (dl[0][0] == 123.456f) dlat[c4] = dl[1][1] + dl[2][2] + dl[3][3] + re_part[0];
+#else
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float* const row = dlat + size_t(4 * g + i) * NC;
@@ -293,6 +348,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           }
           if (g < N_BL)
             __stcg(reinterpret_cast<float4*>(dlat + size_t(256 + g) * NC + c4), make_float4(re_part[0], re_part[1], re_part[2], re_part[3]));
+#endif
         }
       };
       for (int sw = 0; sw < NFULL; ++sw) {
@@ -338,7 +394,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
     // ---------------- turn: scalar latents, outputs, their cotangents, d a_{L-2} ----------------
     {
       const float* ws = wr.wait();
-      if (wm == 0 && lane < QG) {
+      if (wm == 0 && lane < QG && !(NFB_GRAD_EXP & 32)) {
         const int c = wn * QG + lane;
         const long long q = tile_q0 + c;
         const float* const bs = p.blob + GB::scal_bias_off(L);
@@ -437,6 +493,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(0.0f, 0.0f);
+      if (!(NFB_GRAD_EXP & 1)) prefetch_slopes(slopes + size_t(L - 2) * H * NC);
       for (int r0 = 0; r0 < NB; r0 += H) {
         const int rows_here = (NB - r0 < H) ? NB - r0 : H;
         if (r0 > 0) group_bar();  // the previous chunk has been read
@@ -444,7 +501,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
         for (int idx = gtid; idx < rows_here * V4; idx += Cfg::GROUP_THREADS) {
           const int r = idx / V4, cc = idx % V4;
           const int col = (cc < QG / 4) ? wn * QG + 4 * cc : NQ + wn * QG + 4 * (cc - QG / 4);
+#if !(NFB_GRAD_EXP & 16)
           *reinterpret_cast<float4*>(act + r * NC + col) = __ldcg(reinterpret_cast<const float4*>(dlat + size_t(r0 + r) * NC + col));
+#endif
         }
         group_bar();
         for (int c = 0; c < rows_here / KC; ++c) {
@@ -463,7 +522,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           for (int tw = 0; tw < 2; ++tw) {
             const float2 a0 = acc[i][tw * (TN / 4) + 2 * v], a1 = acc[i][tw * (TN / 4) + 2 * v + 1];
             const int off = tile_offset(i, v, tw == 1);
-            const float4 m = __ldcg(reinterpret_cast<const float4*>(sl + off));
+            const float4 m = (NFB_GRAD_EXP & 1) ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldcg(reinterpret_cast<const float4*>(sl + off));
             *reinterpret_cast<float4*>(act + off) = make_float4(a0.x * m.x, a0.y * m.y, a1.x * m.z, a1.y * m.w);
           }
         }
@@ -478,6 +537,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int jj = 0; jj < TN / 2; ++jj) acc[i][jj] = make_float2(0.0f, 0.0f);
+      if (!(NFB_GRAD_EXP & 1)) prefetch_slopes(slopes + size_t(l - 1) * H * NC);
       for (int c = 0; c < nkh; ++c) {
         const float* ws = wr.wait();
         ffma_slice<8, TN, H, NC, KC>(ws + h_row, act + (c * KC) * NC + h_col, acc);
@@ -494,7 +554,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
             const float2 a0 = acc[i][tw * (TN / 4) + 2 * v], a1 = acc[i][tw * (TN / 4) + 2 * v + 1];
             const int off = tile_offset(i, v, tw == 1);
             // d z_{l-1} = d a_{l-1} * SiLU'(z_{l-1}); this thread stored those slopes itself
-            const float4 m = __ldcg(reinterpret_cast<const float4*>(sl + off));
+            const float4 m = (NFB_GRAD_EXP & 1) ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldcg(reinterpret_cast<const float4*>(sl + off));
             *reinterpret_cast<float4*>(act + off) = make_float4(a0.x * m.x, a0.y * m.y, a1.x * m.z, a1.y * m.w);
           }
         }
@@ -531,32 +591,41 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
     }
 
     // ---------------- finish: rows 0..24 of the tile now hold d f / d x of the query and of its twin ----------------
-    for (int t = gtid; t < QG; t += Cfg::GROUP_THREADS) {
-      const int c = wn * QG + t;
+    // Two lanes per query: lane l < 16 of a warp takes the query, lane l + 16 its twin (the 625 fp64 multiply-adds of the
+    // Mahalanobis gradient, once per twin, were 12 % of the kernel when one thread did both in turn); the twin's vector comes
+    // over by shuffle.  QG is 16 or 32: one or two warps of the group, all 32 lanes in step.
+    static_assert(QG % 16 == 0 && 2 * QG <= Cfg::GROUP_THREADS, "finish step: 16 queries and their twins per warp");
+    if (gtid < 2 * QG) {
+      const int tw = lane >> 4;
+      const int c = wn * QG + (gtid >> 5) * 16 + (lane & 15);
       const long long q = tile_q0 + c;
-      if (q >= p.n) continue;
-      double x[N_IN], xt[N_IN];
+      const bool valid = q < p.n;
+#if NFB_GRAD_EXP & 4
+      if (valid && tw == 0)
+        for (int i = 0; i < N_RAW; ++i) static_cast<float*>(gp.grad)[i * gp.grad_ld + q] = act[i * NC + c];
+#else
+      double x[N_IN];
       float m_unused, re_unused;
-      featurise_query(p, q, true, false, x, m_unused, re_unused);
-#pragma unroll
-      for (int i = 0; i < N_IN; ++i) xt[i] = x[i];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { xt[i] = -x[8 + i]; xt[8 + i] = -x[i]; }  // main.py:253-265
-      xt[16] = -x[16]; xt[18] = -x[18]; xt[23] = x[24]; xt[24] = x[23];
+      featurise_query(p, q, valid, false, x, m_unused, re_unused);
       double G[N_IN], T[N_IN];
-#pragma unroll 1
-      for (int tw = 0; tw < 2; ++tw) {  // one copy of the 625 DFMAs for both twins
+      {
         double xx[N_IN], gg[N_IN];
 #pragma unroll
-        for (int i = 0; i < N_IN; ++i) xx[i] = tw ? xt[i] : x[i];
+        for (int i = 0; i < N_IN; ++i) xx[i] = x[i];
+        if (tw) {  // main.py:253-265
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { xx[i] = -x[8 + i]; xx[8 + i] = -x[i]; }
+          xx[16] = -x[16]; xx[18] = -x[18]; xx[23] = x[24]; xx[24] = x[23];
+        }
         maha_gradient_regs(p, xx, gg);
         const double mc = double(maha[tw * NQ + c]) / (2.0 * N_IN);
 #pragma unroll
         for (int k = 0; k < N_IN; ++k) {
-          const double val = double(act[k * NC + tw * NQ + c]) + mc * gg[k];
-          if (tw) T[k] = val; else G[k] = val;
+          G[k] = double(act[k * NC + tw * NQ + c]) + mc * gg[k];
+          T[k] = __shfl_down_sync(0xffffffffu, G[k], 16);  // the query's lane receives its twin's
         }
       }
+      if (valid && tw == 0) {
       // pull the twin's gradient back through the flip (its transpose: the same signed permutation)
 #pragma unroll
       for (int i = 0; i < 8; ++i) { G[8 + i] -= T[i]; G[i] -= T[8 + i]; }
@@ -590,6 +659,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
 #pragma unroll
         for (int i = 0; i < N_RAW; ++i) static_cast<float*>(gp.grad)[i * gp.grad_ld + q] = float(out[i]);
       }
+      }  // valid && tw == 0
+#endif
     }
   }
 }
