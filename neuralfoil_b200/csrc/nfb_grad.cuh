@@ -248,14 +248,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           asm volatile("prefetch.global.L2 [%0];" ::"l"(sl + tile_offset(i, v, tw == 1)));
   };
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long tile_q0 = tile * NQ;
-
-    group_bar();
+  // Featurisation of a tile's columns of this group: threads gtid < 2 QG, one column each.
+  auto featurise_tile = [&](long long tq0) {
     for (int t = gtid; t < 2 * QG; t += Cfg::GROUP_THREADS) {
       const bool twin = t >= QG;
       const int c = wn * QG + (t % QG);
-      const long long q = tile_q0 + c;
+      const long long q = tq0 + c;
 #if NFB_GRAD_EXP & 8
       const int col = twin ? NQ + c : c;
       maha[col] = 0.f;
@@ -265,7 +263,21 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
       featurise_column<NC>(p, q, q < p.n, twin, twin ? NQ + c : c, act, maha, re_s);
 #endif
     }
+  };
+  // The finish step of tile t and the featurisation of tile t + 1 are both fp64 work of a few threads (two lanes per query /
+  // one thread per column) during which the group's GEMM stands still.  Where the group has warps to spare (4 QG <= its threads)
+  // they run AT THE SAME TIME on different warps: the finish warps take their 26 inputs out of the tile into registers, one
+  // barrier later the featurise warps may overwrite it.  (H = 64: two warps per group, both needed by either step: in turn.)
+  constexpr bool SPLIT_STEPS = 4 * QG <= Cfg::GROUP_THREADS;
+  constexpr int FIN0 = SPLIT_STEPS ? Cfg::GROUP_THREADS - 2 * QG : 0;  // first finish thread of the group
+  static_assert(QG % 16 == 0 && 2 * QG <= Cfg::GROUP_THREADS && FIN0 % 32 == 0, "finish step: 16 queries and their twins per warp");
+
+  if (blockIdx.x < n_tiles) {
+    featurise_tile((long long)blockIdx.x * NQ);
     group_bar();
+  }
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long tile_q0 = tile * NQ;
 
     // ---------------- forward: hidden layers, SiLU and its slope ----------------
     for (int l = 0; l < L - 1; ++l) {
@@ -594,15 +606,25 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
     // Two lanes per query: lane l < 16 of a warp takes the query, lane l + 16 its twin (the 625 fp64 multiply-adds of the
     // Mahalanobis gradient, once per twin, were 12 % of the kernel when one thread did both in turn); the twin's vector comes
     // over by shuffle.  QG is 16 or 32: one or two warps of the group, all 32 lanes in step.
-    static_assert(QG % 16 == 0 && 2 * QG <= Cfg::GROUP_THREADS, "finish step: 16 queries and their twins per warp");
-    if (gtid < 2 * QG) {
-      const int tw = lane >> 4;
-      const int c = wn * QG + (gtid >> 5) * 16 + (lane & 15);
+    const bool fin = gtid >= FIN0 && gtid < FIN0 + 2 * QG;
+    const int fin_tw = lane >> 4;
+    const int fin_c = wn * QG + ((gtid - FIN0) >> 5) * 16 + (lane & 15);
+    float fin_v[N_IN], fin_m = 0.0f;
+    if (fin) {
+#pragma unroll
+      for (int k = 0; k < N_IN; ++k) fin_v[k] = act[k * NC + fin_tw * NQ + fin_c];
+      fin_m = maha[fin_tw * NQ + fin_c];
+    }
+    group_bar();  // the tile may be overwritten
+    const long long next_tile = tile + gridDim.x;
+    if (SPLIT_STEPS && next_tile < n_tiles) featurise_tile(next_tile * NQ);  // threads gtid < 2 QG: not the finish warps
+    if (fin) {
+      const int tw = fin_tw, c = fin_c;
       const long long q = tile_q0 + c;
       const bool valid = q < p.n;
 #if NFB_GRAD_EXP & 4
       if (valid && tw == 0)
-        for (int i = 0; i < N_RAW; ++i) static_cast<float*>(gp.grad)[i * gp.grad_ld + q] = act[i * NC + c];
+        for (int i = 0; i < N_RAW; ++i) static_cast<float*>(gp.grad)[i * gp.grad_ld + q] = fin_v[i];
 #else
       double x[N_IN];
       float m_unused, re_unused;
@@ -618,10 +640,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
           xx[16] = -x[16]; xx[18] = -x[18]; xx[23] = x[24]; xx[24] = x[23];
         }
         maha_gradient_regs(p, xx, gg);
-        const double mc = double(maha[tw * NQ + c]) / (2.0 * N_IN);
+        const double mc = double(fin_m) / (2.0 * N_IN);
 #pragma unroll
         for (int k = 0; k < N_IN; ++k) {
-          G[k] = double(act[k * NC + tw * NQ + c]) + mc * gg[k];
+          G[k] = double(fin_v[k]) + mc * gg[k];
           T[k] = __shfl_down_sync(0xffffffffu, G[k], 16);  // the query's lane receives its twin's
         }
       }
@@ -662,6 +684,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
       }  // valid && tw == 0
 #endif
     }
+    if (!SPLIT_STEPS && next_tile < n_tiles) featurise_tile(next_tile * NQ);  // the same threads: after their finish step
+    group_bar();  // the next tile's inputs are in place
   }
 }
 
