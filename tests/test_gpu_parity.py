@@ -925,3 +925,24 @@ def test_reverse_kernels_contain_nan_queries(evaluator):
         for q in poisoned:
             assert not torch.isfinite(g_bad[:, q]).all() and not torch.isfinite(s_bad[:, q]).all(), (size, q)
             assert torch.isnan(v_bad[1, q])
+
+
+def test_pinned_host_blocks_default_chunk_is_invisible(evaluator):
+    """Pinned caller memory takes the direct-copy path of nfb_eval_host, whose default chunk is a sixteenth of the batch
+    (64 Ki .. 512 Ki queries): a shard of 1.25 M queries -- one of eight GPUs' share of BASELINE configs[2] -- runs as 16
+    ragged chunks on two streams.  Same bits as one device-resident launch and as 512 Ki chunks."""
+    import torch
+
+    n = 1_250_003
+    raw = torch.from_numpy(synthetic.sample_training_distribution(n, seed=77).astype(np.float32)).pin_memory()
+    out_a = torch.empty((198, (n + 3) & ~3), dtype=torch.float32).pin_memory()
+    out_b = torch.empty_like(out_a).pin_memory()
+    dev = evaluator.evaluate_device(raw.cuda(), "small")
+    torch.cuda.synchronize()
+    want = dev.cpu().numpy()
+    got = evaluator.evaluate_host_into(raw.numpy(), "small", out_a.numpy())
+    np.testing.assert_array_equal(got, want)
+    got_b = evaluator.evaluate_host_into(raw.numpy(), "small", out_b.numpy(), chunk=1 << 19)
+    np.testing.assert_array_equal(got_b, want)
+    six = torch.empty((6, (n + 3) & ~3), dtype=torch.float32).pin_memory()
+    np.testing.assert_array_equal(evaluator.evaluate_host_into(raw.numpy(), "small", six.numpy(), outputs="scalars"), want[:6])
