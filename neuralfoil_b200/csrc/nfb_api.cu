@@ -148,6 +148,9 @@ using Grad256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, NFB_GRAD_
 #endif
 using Grp512 = nfb::GroupCfg<512, 8, NFB_GRP_STAGES_512, NFB_TN_WIDE, 16, NFB_GRP_LEAD_512>;
 using Grad512 = nfb::GroupCfg<512, 8, NFB_GRP_STAGES_512, NFB_GRAD_TN_WIDE, 16, NFB_GRP_LEAD_512>;
+// the training kernels are written for the 8 x 8 thread tile, whatever the reverse-mode kernels use
+using Train256 = nfb::GroupCfg<256, NFB_GRP_KC_256, NFB_GRP_STAGES_256, 8>;
+using Train512 = nfb::GroupCfg<512, 8, NFB_GRP_STAGES_512, 8, 16, NFB_GRP_LEAD_512>;
 
 struct HostSlot {  // one in-flight chunk of nfb_eval_host
   cudaStream_t stream = nullptr;
@@ -1439,8 +1442,8 @@ int nfb_train_step_device(nfb_context* ctx, int model_id, int64_t batch, const f
   switch (m.h_pad) {
     case 64: return launch_train<Grp64, nfb::WgradCfg<64, 64>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
     case 128: return launch_train<Grad128, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
-    case 256: return launch_train<Grad256, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
-    case 512: return launch_train<Grad512, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
+    case 256: return launch_train<Train256, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
+    case 512: return launch_train<Train512, nfb::WgradCfg<128, 128>>(ctx, m, batch, x, x_ld, y_data, y_ld, loss_weights, huber_delta, loss_components, grad_weights, grad_biases, st);
   }
   return fail(NFB_ERR_UNSUPPORTED_MODEL, "no kernel for padded width %d", m.h_pad);
 }
