@@ -195,6 +195,8 @@ __device__ __forceinline__ void ffma_slice(const float* __restrict__ w, const fl
 // ---- step 1: featurisation + Mahalanobis (shared by every kernel) -----------------------------------
 // One query (or its flipped twin): 23 raw scalars -> the 25 latent inputs x (fp64) [main.py:171-184, 253-265],
 // d2 / 50 of the Mahalanobis correction [main.py:47-61, 244-246] and Re.  fp64 throughout: cond(S^-1) ~ 7e7.
+// WITH_MAHA = false (the reverse pass's finish step, which only needs x again) leaves the quadratic form out.
+template <bool WITH_MAHA = true>
 __device__ __forceinline__ void featurise_query(const EvalParams& p, long long q, bool valid, bool twin,
                                                 double (&x)[N_IN], float& maha, float& re) {
   double r[N_RAW];
@@ -243,6 +245,11 @@ __device__ __forceinline__ void featurise_query(const EvalParams& p, long long q
     x[24] = t;
   }
 
+  re = static_cast<float>(r[19]);
+  if constexpr (!WITH_MAHA) {
+    maha = 0.0f;
+    return;
+  }
   // (x - mu)^T S^-1 (x - mu) with the packed symmetric form
   double d[N_IN];
 #pragma unroll
@@ -257,7 +264,6 @@ __device__ __forceinline__ void featurise_query(const EvalParams& p, long long q
     d2 = fma(d[i], t, d2);
   }
   maha = static_cast<float>(d2 / (2.0 * N_IN));  // main.py:244-246
-  re = static_cast<float>(r[19]);
 }
 
 // fp32 kernels: one thread per tile column; the 25 inputs go, rounded to fp32, into rows 0..31 of the activation tile

@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) nfb_grad_kernel(const GradPar
 #else
       double x[N_IN];
       float m_unused, re_unused;
-      featurise_query(p, q, valid, false, x, m_unused, re_unused);
+      featurise_query<false>(p, q, valid, false, x, m_unused, re_unused);
       double G[N_IN], T[N_IN];
       {
         double xx[N_IN], gg[N_IN];
