@@ -946,3 +946,35 @@ def test_pinned_host_blocks_default_chunk_is_invisible(evaluator):
     np.testing.assert_array_equal(got_b, want)
     six = torch.empty((6, (n + 3) & ~3), dtype=torch.float32).pin_memory()
     np.testing.assert_array_equal(evaluator.evaluate_host_into(raw.numpy(), "small", six.numpy(), outputs="scalars"), want[:6])
+
+
+def test_result_pool_never_hands_out_memory_that_is_still_referenced(evaluator):
+    """The drop-in call's large result blocks are recycled (main._ResultPool).  A dict that is still alive keeps its memory;
+    memory comes back only after every array of a result is gone, and the values are the same either way."""
+    import gc
+
+    from neuralfoil_b200.main import _result_pool
+
+    n = 50_000  # 198 x 50,000 float64 = 79 MB: pooled
+    K = synthetic.FIXED_KULFAN
+    alpha = np.linspace(-8.0, 12.0, n)
+    _result_pool.clear()
+    first = evaluator.get_aero_from_kulfan_parameters(K, alpha=alpha, Re=2e6, model_size="small")
+    cl_first = first["CL"].copy()
+    addr_first = first["CL"].__array_interface__["data"][0]
+    second = evaluator.get_aero_from_kulfan_parameters(K, alpha=alpha[::-1].copy(), Re=2e6, model_size="small")
+    assert second["CL"].__array_interface__["data"][0] != addr_first  # `first` is alive: fresh memory
+    np.testing.assert_array_equal(first["CL"], cl_first)               # ... and untouched by the second call
+    np.testing.assert_array_equal(second["CL"], cl_first[::-1])
+    keep = first["CD"]  # one surviving view keeps the whole block
+    del first
+    gc.collect()
+    third = evaluator.get_aero_from_kulfan_parameters(K, alpha=alpha, Re=2e6, model_size="small")
+    assert third["CL"].__array_interface__["data"][0] != addr_first
+    cd = keep.copy()
+    del keep, third
+    gc.collect()
+    fourth = evaluator.get_aero_from_kulfan_parameters(K, alpha=alpha, Re=2e6, model_size="small")
+    np.testing.assert_array_equal(fourth["CL"], cl_first)  # recycled memory, same values
+    np.testing.assert_array_equal(fourth["CD"], cd)
+    assert len(fourth) == 198 and all(v.shape == (n,) and v.dtype == np.float64 for v in fourth.values())
