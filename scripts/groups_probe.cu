@@ -20,6 +20,9 @@
 #ifndef PROBE_H
 #define PROBE_H 512
 #endif
+#ifndef PROBE_KC
+#define PROBE_KC 8
+#endif
 #ifndef PROBE_L
 #define PROBE_L 7   // affine layers: xxxlarge 7, xxlarge / xlarge 6, large / medium 5, small / xsmall 4, xxsmall 3
 #endif
@@ -27,7 +30,7 @@
 #define PROBE_KH PROBE_H  // real hidden width rounded up to 16 (48 for xsmall / xxsmall)
 #endif
 #if PROBE_H == 512
-using Cfg = nfb::GroupCfg<512, 8, PROBE_STAGES, PROBE_TN, 16, PROBE_LEAD>;
+using Cfg = nfb::GroupCfg<512, PROBE_KC, PROBE_STAGES, PROBE_TN, 16, PROBE_LEAD>;
 #else
 using Cfg = nfb::GroupCfg<PROBE_H, 8, PROBE_STAGES, PROBE_TN, 32, PROBE_LEAD>;
 #endif
