@@ -12,6 +12,12 @@
 #pragma once
 #include "nfb_ffma.cuh"
 
+// weight loads in flight per thread and round (every K is a multiple of 32): a layer is K / U dependent round trips to the L2.
+// Measured 16 against 32: one query on xlarge 42.4 -> 41.0 us through nfb_eval_host, but 1,024 queries 199 -> 213 us (registers).
+#ifndef NFB_SMALL_U
+#define NFB_SMALL_U 16
+#endif
+
 namespace nfb {
 
 constexpr int SMALL_QUERIES = 4;                 // per CTA
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(SmallCfg<H>::THREADS, 1) nfb_small_kernel(cons
       const float b = __ldg(w + size_t(K) * H + tid);
 #pragma unroll
       for (int j = 0; j < SMALL_COLS; ++j) acc[j] = b;
-      small_layer<16>(w + tid, H, K, cur, acc);
+      small_layer<NFB_SMALL_U>(w + tid, H, K, cur, acc);
       float4 lo, hi;
       lo.x = silu(acc[0]); lo.y = silu(acc[1]); lo.z = silu(acc[2]); lo.w = silu(acc[3]);
       hi.x = silu(acc[4]); hi.y = silu(acc[5]); hi.z = silu(acc[6]); hi.w = silu(acc[7]);
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(SmallCfg<H>::THREADS, 1) nfb_small_kernel(cons
       const float b = __ldg(w + size_t(H) * M_LAST + tid);
 #pragma unroll
       for (int j = 0; j < SMALL_COLS; ++j) acc[j] = b;
-      small_layer<16>(w + tid, M_LAST, H, cur, acc);
+      small_layer<NFB_SMALL_U>(w + tid, M_LAST, H, cur, acc);
 #pragma unroll
       for (int j = 0; j < SMALL_COLS; ++j) stage[tid * SMALL_COLS + j] = acc[j];
     }
