@@ -977,6 +977,12 @@ int nfb_eval_device(nfb_context* ctx, int model_id, int variant, int64_t n, cons
                           static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+inline int64_t default_chunk(int64_t n) {  // a sixteenth of the batch within [64 Ki, 512 Ki] queries
+  return std::min<int64_t>(1 << 19, std::max<int64_t>(1 << 16, (n / 16 + 3) & ~int64_t(3)));
+}
+}  // namespace
+
 int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const void* const* in_rows,
                   const int64_t* in_strides, int in_dtype, void* out, int64_t out_ld, int out_dtype,
                   int64_t chunk) {
@@ -1006,7 +1012,7 @@ int nfb_eval_host(nfb_context* ctx, int model_id, int variant, int64_t n, const 
   // sixteenth of the batch within [64 Ki, 512 Ki]: the last chunk's device->host copy is the one nothing hides, and when eight
   // GPUs share the host's 92 GB/s (profiles/r2_pcie_pitched_8gpu.jsonl) a 512 Ki chunk of full outputs is a 36 ms tail on a
   // 115 ms shard (8 GPUs x 1.25 M queries, xxxlarge fp32: 148 ms per pass with 512 Ki chunks, 123 ms with 128 Ki)
-  if (chunk <= 0) chunk = stage_out ? (1 << 17) : std::min<int64_t>(1 << 19, std::max<int64_t>(1 << 16, (n / 16 + 3) & ~int64_t(3)));
+  if (chunk <= 0) chunk = stage_out ? (1 << 17) : default_chunk(n);
   chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
   const int out_rows = (variant & NFB_OUTPUT_SCALARS) ? 6 : nfb::N_OUT;
   const size_t in_need = size_t(nfb::N_RAW) * chunk * isz, out_need = size_t(out_rows) * chunk * osz;
@@ -1249,7 +1255,7 @@ int nfb_eval_host_mixed(nfb_context* ctx, int model_id, int variant, int64_t n, 
   std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   NFB_CUDA(cudaSetDevice(ctx->device));
   const size_t isz = in_dtype == NFB_F64 ? 8 : 4;
-  if (chunk <= 0) chunk = 1 << 19;
+  if (chunk <= 0) chunk = default_chunk(n);
   chunk = std::min<int64_t>((chunk + 3) & ~int64_t(3), (n + 3) & ~int64_t(3));
   constexpr int BL_ROWS = nfb::N_OUT - 6;
   const size_t in_need = size_t(nfb::N_RAW) * chunk * isz;
