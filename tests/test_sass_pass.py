@@ -1,4 +1,5 @@
 """The SASS post-pass of the build (neuralfoil_b200/_sass.py): what it may touch, and that it is a fixed point.  CPU only."""
+import os
 import shutil
 import struct
 
@@ -33,6 +34,8 @@ def test_default_selection_is_the_eight_warp_value_kernels():
 
 
 def test_pass_is_a_fixed_point_and_touches_hint_bits_only(lib_path, tmp_path):
+    if os.environ.get("NFB_NO_SASS_PASS", "") == "1":
+        pytest.skip("the library was built without the pass (A/B build)")
     copy = tmp_path / "lib.so"
     shutil.copyfile(lib_path, copy)
     stats = _sass.patch_file(str(copy), verbose=False, select=_sass.DEFAULT_SELECT)
